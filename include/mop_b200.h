@@ -1,0 +1,172 @@
+/*
+ * mop_b200.h - C ABI of libmop_b200.so: the B200 (sm_100a) implementation of the
+ * Mixture-of-Products attention hot path of Eran-BA/MoP.
+ *
+ * The reference has no FFI of its own (it is eager PyTorch); each entry point
+ * below replaces the body of one reference `nn.Module.forward` (and its
+ * autograd) between the input projections and the output projection:
+ *
+ *   mop_edgewise_fwd/bwd   EdgewiseMSA.forward      mop/models/attention_variants.py:500-562
+ *                          EdgewiseGateHead.forward mop/models/attention_variants.py:311-331
+ *                          (clone: experiments/cifar100_edgewise_gates.py:99-115,211-310)
+ *   mop_sdpa_fwd/bwd       MSA.forward              mop/models/components.py:61-64
+ *                          BaselineMSA.forward      mop/models/attention_variants.py:42-46
+ *                          MultiheadSelfAttention   mop/models/whisper_mop.py:163-175
+ *                          MultiheadCrossAttention  mop/models/whisper_mop.py:212-219
+ *   mop_quartet_fwd/bwd    CausalSelfAttention      mop/models/quartet_attn_patch.py:88-121
+ *
+ * Conventions
+ *   - plain C, POD structs, raw device pointers; no torch / C++ types cross the ABI.
+ *   - the caller owns every buffer (inputs, outputs, saved statistics, workspace);
+ *     the library never allocates or frees device memory and never synchronises.
+ *   - all work is enqueued on the `cuda_stream` argument (a cudaStream_t).
+ *   - return 0 on success, a negative MOP_E* code otherwise; the message is
+ *     available from mop_last_error() (thread local).  No exceptions cross the ABI.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with MOP_ECUDA.
+ *   - every struct starts with `struct_bytes = sizeof(struct)`; a mismatch is
+ *     rejected with MOP_EABI.
+ *   - `dtype` selects the storage type of the activation tensors (qkv / q,k,v /
+ *     y / dy / gradients).  Parameters, statistics and partial parameter
+ *     gradients are always fp32.  MOP_F32 = "fp32 mode" (fp32 CUDA-core math,
+ *     <=1e-5 of the reference); MOP_BF16 = bf16 storage, tensor-core contractions
+ *     with fp32 accumulation and fp32 statistics.
+ */
+#ifndef MOP_B200_H
+#define MOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOP_ABI_VERSION 1
+
+enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
+enum { MOP_F32 = 0, MOP_BF16 = 1 };
+enum { MOP_GATE_DENSE = 0, MOP_GATE_LOWRANK = 1 };
+/* which implementation ran (written to `impl_used` by the *_fwd / *_bwd calls) */
+enum { MOP_IMPL_SIMT = 1, MOP_IMPL_TCGEN05 = 2 };
+/* `impl` request: AUTO picks tcgen05 when the shape/dtype is covered, else SIMT */
+enum { MOP_IMPL_AUTO = 0 };
+
+int mop_abi_version(void);
+const char* mop_last_error(void);
+/* number of SMs of the current device (cached), <0 on error */
+int mop_device_sm_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Edgewise (Mixture-of-Products) attention core                              */
+/* ------------------------------------------------------------------------- */
+typedef struct MopEdgewiseParams {
+  int32_t struct_bytes;
+  int32_t dtype;      /* MOP_F32 | MOP_BF16: type of qkv, y, dy, dqkv */
+  int32_t impl;       /* MOP_IMPL_AUTO | MOP_IMPL_SIMT | MOP_IMPL_TCGEN05 */
+  int32_t impl_used;  /* out */
+  int32_t B, H, N, dk;
+  int32_t V;          /* number of views / score maps (>=2)            :362 */
+  int32_t Vp;         /* 1: share_qkv (one projection + per-view scales) :459-464; V: one projection per view :466-470 */
+  int32_t gate_mode;  /* MOP_GATE_DENSE | MOP_GATE_LOWRANK               :250,273 */
+  int32_t gate_rank;  /* r (lowrank)                                     :277 */
+  int32_t hidden;     /* dense head hidden channels (reference: 16)      :445 */
+  int32_t use_k3;     /* dense head only: 3x3 stage present              :253 */
+  float beta_not;     /*                                                 :546 */
+  float eps;          /* 1e-6                                            :516 */
+  /* activations */
+  const void* qkv;    /* [B,N,Vp,3,H,dk] contiguous, `dtype`: output of the qkv Linear(s) */
+  void* y;            /* [B,N,H,dk] contiguous, `dtype`: merge-heads layout :563 */
+  /* parameters (fp32, device) */
+  const float* q_scale; /* [V,H,dk] or NULL (all ones)                   :376-378 */
+  const float* k_scale;
+  const float* v_scale;
+  const float* chain_value_logit; /* [1]                                 :451 */
+  const float* row_w;   /* lowrank: [4r,C], C = 2V+2                     :277 */
+  const float* row_b;   /* [4r] */
+  const float* col_w;   /* [4r,C]                                        :278 */
+  const float* col_b;   /* [4r] */
+  const float* conv1_w; /* dense: [hidden,C]                             :251 */
+  const float* conv1_b; /* [hidden] */
+  const float* mid3_w;  /* [hidden,hidden,3,3] iff use_k3                :254 */
+  const float* mid3_b;  /* [hidden] */
+  const float* conv2_w; /* [4,hidden]                                    :255 */
+  const float* conv2_b; /* [4] */
+  /* backward only */
+  const void* dy;       /* [B,N,H,dk] `dtype` */
+  void* dqkv;           /* [B,N,Vp,3,H,dk] `dtype`, fully overwritten */
+  float* dscale_part;   /* [B*H,3,V,dk] per-(b,h) partial grads of q/k/v_scale (sum over b on the host side); NULL if scales are NULL */
+  float* dhead_part;    /* [B*H, mop_edgewise_head_param_count()] partial grads of the gate head, packed in the order
+                           lowrank: row_w,row_b,col_w,col_b ; dense: conv1_w,conv1_b,(mid3_w,mid3_b),conv2_w,conv2_b */
+  float* dlogit_part;   /* [B*H] */
+  /* scratch */
+  void* workspace;
+  size_t workspace_bytes;
+} MopEdgewiseParams;
+
+size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);
+/* bytes of workspace needed by mop_edgewise_fwd (backward=0) / mop_edgewise_bwd (backward=1) */
+size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward);
+int mop_edgewise_fwd(MopEdgewiseParams* p, void* cuda_stream);
+int mop_edgewise_bwd(MopEdgewiseParams* p, void* cuda_stream);
+
+/* ------------------------------------------------------------------------- */
+/* Plain / causal / biased / cross attention                                  */
+/* ------------------------------------------------------------------------- */
+typedef struct MopSdpaParams {
+  int32_t struct_bytes;
+  int32_t dtype, impl, impl_used;
+  int32_t B, H, Nq, Nk, dk;
+  int32_t causal;       /* j > i -> -inf            whisper_mop.py:165-167 */
+  float scale;          /* 1/sqrt(dk) */
+  /* q[b,n,h,:] = q + b*q_sb + n*q_sn + h*q_sh (element strides, last dim contiguous) */
+  const void *q, *k, *v;
+  int64_t q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh;
+  void* y;              /* [B,Nq,H,dk] contiguous */
+  /* optional additive bias (fp32), element strides may be 0 for broadcast   whisper_mop.py:169-170,213-214 */
+  const float* bias; int64_t bias_sb, bias_sh, bias_sq, bias_sk;
+  /* optional keep-mask: entries == 0 are filled with -inf      attention_variants.py:43-44 */
+  const float* zero_mask; int64_t zm_sb, zm_sh, zm_sq, zm_sk;
+  float* lse;           /* [B,H,Nq] saved row log-sum-exp (fwd out, bwd in) */
+  /* backward */
+  const void* dy;       /* [B,Nq,H,dk] */
+  void *dq, *dk_, *dv;  /* contiguous [B,Nq,H,dk], [B,Nk,H,dk], [B,Nk,H,dk] */
+  void* workspace; size_t workspace_bytes;
+} MopSdpaParams;
+
+size_t mop_sdpa_workspace_bytes(const MopSdpaParams* p, int backward);
+int mop_sdpa_fwd(MopSdpaParams* p, void* cuda_stream);
+int mop_sdpa_bwd(MopSdpaParams* p, void* cuda_stream);
+
+/* ------------------------------------------------------------------------- */
+/* Quartet causal attention                                                   */
+/* ------------------------------------------------------------------------- */
+typedef struct MopQuartetParams {
+  int32_t struct_bytes;
+  int32_t dtype, impl, impl_used;
+  int32_t B, H, T, dk;
+  int32_t use_quartet;  /* 0: single z-scored map         quartet_attn_patch.py:108-110 */
+  float scale;          /* 1/sqrt(dk) */
+  float eps;            /* score_norm_eps (1e-5) */
+  /* all of q,k,v,q2,k2: [B,T,H,dk] contiguous (the Linear outputs viewed as heads, :84-92) */
+  const void *q, *k, *v, *q2, *k2;
+  const float* mixture;        /* [1] :52 */
+  const float* quartet_scale;  /* [1] :55 */
+  const float* add_mask; int64_t am_sb, am_sh, am_sq, am_sk; /* optional additive mask :115-116 */
+  void* y;              /* [B,T,H,dk] */
+  float* stats;         /* [B,H,T,3]: sigma1, sigma2, lse  (fwd out, bwd in) */
+  /* backward */
+  const void* dy;
+  void *dq, *dk_, *dv, *dq2, *dk2;
+  float* dscalar_part;  /* [B*H,2] partial grads of (mixture, quartet_scale) */
+  void* workspace; size_t workspace_bytes;
+} MopQuartetParams;
+
+size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward);
+int mop_quartet_fwd(MopQuartetParams* p, void* cuda_stream);
+int mop_quartet_bwd(MopQuartetParams* p, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOP_B200_H */

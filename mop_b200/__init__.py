@@ -1,0 +1,17 @@
+"""mop_b200 - B200 (sm_100a) implementation of the MoP attention hot path.
+
+Drop-in ``nn.Module`` replacements for the attention classes of Eran-BA/MoP,
+backed by hand-written CUDA kernels behind a C ABI (``libmop_b200.so``,
+``include/mop_b200.h``).  There is no CPU fallback.
+"""
+from .attention_variants import BaselineMSA, EdgewiseGateHead, EdgewiseMSA, UnifiedMSA
+from .components import MLP, MSA, Block, DropPath, PatchEmbed
+from .functional import edgewise_attention, sdpa
+from .vit_edgewise import BlockEdgewise, ViTEdgewise
+from .whisper_mop import MultiheadCrossAttention, MultiheadSelfAttention
+
+__all__ = [
+    "BaselineMSA", "EdgewiseGateHead", "EdgewiseMSA", "UnifiedMSA", "MSA", "MLP", "Block", "DropPath", "PatchEmbed",
+    "BlockEdgewise", "ViTEdgewise", "MultiheadSelfAttention", "MultiheadCrossAttention",
+    "edgewise_attention", "sdpa",
+]

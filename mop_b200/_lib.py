@@ -1,0 +1,118 @@
+"""ctypes binding of libmop_b200.so (the C ABI declared in include/mop_b200.h).
+
+The library is built in-tree by ``mop_b200.build.build()`` (nvcc, sm_100a).
+There is no CPU fallback: if the shared object is missing or a call fails the
+caller gets a ``RuntimeError`` carrying ``mop_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmop_b200.so")
+
+MOP_ABI_VERSION = 1
+MOP_F32, MOP_BF16 = 0, 1
+MOP_GATE_DENSE, MOP_GATE_LOWRANK = 0, 1
+MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
+IMPL_NAMES = {MOP_IMPL_SIMT: "simt", MOP_IMPL_TCGEN05: "tcgen05"}
+
+i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+
+
+class EdgewiseParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("dtype", i32), ("impl", i32), ("impl_used", i32),
+        ("B", i32), ("H", i32), ("N", i32), ("dk", i32), ("V", i32), ("Vp", i32),
+        ("gate_mode", i32), ("gate_rank", i32), ("hidden", i32), ("use_k3", i32),
+        ("beta_not", f32), ("eps", f32),
+        ("qkv", vp), ("y", vp),
+        ("q_scale", vp), ("k_scale", vp), ("v_scale", vp), ("chain_value_logit", vp),
+        ("row_w", vp), ("row_b", vp), ("col_w", vp), ("col_b", vp),
+        ("conv1_w", vp), ("conv1_b", vp), ("mid3_w", vp), ("mid3_b", vp), ("conv2_w", vp), ("conv2_b", vp),
+        ("dy", vp), ("dqkv", vp), ("dscale_part", vp), ("dhead_part", vp), ("dlogit_part", vp),
+        ("workspace", vp), ("workspace_bytes", sz),
+    ]
+
+
+class SdpaParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("dtype", i32), ("impl", i32), ("impl_used", i32),
+        ("B", i32), ("H", i32), ("Nq", i32), ("Nk", i32), ("dk", i32), ("causal", i32), ("scale", f32),
+        ("q", vp), ("k", vp), ("v", vp),
+        ("q_sb", i64), ("q_sn", i64), ("q_sh", i64), ("k_sb", i64), ("k_sn", i64), ("k_sh", i64),
+        ("v_sb", i64), ("v_sn", i64), ("v_sh", i64),
+        ("y", vp),
+        ("bias", vp), ("bias_sb", i64), ("bias_sh", i64), ("bias_sq", i64), ("bias_sk", i64),
+        ("zero_mask", vp), ("zm_sb", i64), ("zm_sh", i64), ("zm_sq", i64), ("zm_sk", i64),
+        ("lse", vp),
+        ("dy", vp), ("dq", vp), ("dk_", vp), ("dv", vp),
+        ("workspace", vp), ("workspace_bytes", sz),
+    ]
+
+
+class QuartetParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("dtype", i32), ("impl", i32), ("impl_used", i32),
+        ("B", i32), ("H", i32), ("T", i32), ("dk", i32), ("use_quartet", i32), ("scale", f32), ("eps", f32),
+        ("q", vp), ("k", vp), ("v", vp), ("q2", vp), ("k2", vp),
+        ("mixture", vp), ("quartet_scale", vp),
+        ("add_mask", vp), ("am_sb", i64), ("am_sh", i64), ("am_sq", i64), ("am_sk", i64),
+        ("y", vp), ("stats", vp),
+        ("dy", vp), ("dq", vp), ("dk_", vp), ("dv", vp), ("dq2", vp), ("dk2", vp),
+        ("dscalar_part", vp),
+        ("workspace", vp), ("workspace_bytes", sz),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import mop_b200.build as b; b.build()'` "
+                "(nvcc, sm_100a).  mop_b200 has no CPU/PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.mop_abi_version.restype = C.c_int
+        lib.mop_last_error.restype = C.c_char_p
+        lib.mop_device_sm_count.restype = C.c_int
+        for name, st in (("edgewise", EdgewiseParams), ("sdpa", SdpaParams), ("quartet", QuartetParams)):
+            ws = getattr(lib, f"mop_{name}_workspace_bytes")
+            ws.restype = C.c_size_t
+            ws.argtypes = [C.POINTER(st), C.c_int]
+            for d in ("fwd", "bwd"):
+                fn = getattr(lib, f"mop_{name}_{d}")
+                fn.restype = C.c_int
+                fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_edgewise_head_param_count.restype = C.c_size_t
+        lib.mop_edgewise_head_param_count.argtypes = [C.POINTER(EdgewiseParams)]
+        if lib.mop_abi_version() != MOP_ABI_VERSION:
+            raise RuntimeError(f"libmop_b200 ABI {lib.mop_abi_version()} != binding {MOP_ABI_VERSION}; rebuild")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().mop_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def new_params(cls):
+    p = cls()
+    p.struct_bytes = C.sizeof(cls)
+    return p

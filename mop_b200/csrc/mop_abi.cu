@@ -1,0 +1,220 @@
+// libmop_b200.so - C ABI entry points (see include/mop_b200.h).
+// Host side only validates, sizes scratch and enqueues kernels on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "edgewise_simt.cuh"
+#include "quartet_simt.cuh"
+#include "sdpa_simt.cuh"
+
+namespace mop {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return MOP_ECUDA;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------
+static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
+  MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
+  MOP_REQUIRE(p->struct_bytes == (int32_t)sizeof(MopEdgewiseParams), MOP_EABI,
+              "MopEdgewiseParams size mismatch: caller %d, library %d", p->struct_bytes, (int)sizeof(MopEdgewiseParams));
+  MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "bad dtype %d", p->dtype);
+  MOP_REQUIRE(p->B > 0 && p->H > 0 && p->N > 0 && p->dk > 0, MOP_EINVAL, "bad shape B=%d H=%d N=%d dk=%d", p->B, p->H, p->N, p->dk);
+  MOP_REQUIRE(p->V >= 2 && p->V <= ew::kMaxViews, MOP_EUNSUPPORTED, "n_views=%d outside [2,%d]", p->V, ew::kMaxViews);
+  MOP_REQUIRE(p->Vp == 1 || p->Vp == p->V, MOP_EINVAL, "Vp must be 1 or V");
+  MOP_REQUIRE(p->gate_mode == MOP_GATE_DENSE || p->gate_mode == MOP_GATE_LOWRANK, MOP_EINVAL, "bad gate_mode %d", p->gate_mode);
+  MOP_REQUIRE(p->qkv && p->y && p->chain_value_logit, MOP_EINVAL, "qkv / y / chain_value_logit must be set");
+  MOP_REQUIRE((p->q_scale != nullptr) == (p->k_scale != nullptr) && (p->q_scale != nullptr) == (p->v_scale != nullptr),
+              MOP_EINVAL, "q/k/v_scale must be all set or all NULL");
+  if (p->gate_mode == MOP_GATE_LOWRANK) {
+    MOP_REQUIRE(p->gate_rank >= 1 && p->gate_rank <= ew::kMaxRank, MOP_EUNSUPPORTED, "gate_rank=%d outside [1,%d]", p->gate_rank, ew::kMaxRank);
+    MOP_REQUIRE(p->row_w && p->row_b && p->col_w && p->col_b, MOP_EINVAL, "lowrank head tensors missing");
+  } else {
+    MOP_REQUIRE(p->hidden >= 1 && p->hidden <= ew::kMaxHidden, MOP_EUNSUPPORTED, "hidden=%d outside [1,%d]", p->hidden, ew::kMaxHidden);
+    MOP_REQUIRE(p->conv1_w && p->conv1_b && p->conv2_w && p->conv2_b, MOP_EINVAL, "dense head tensors missing");
+    MOP_REQUIRE(!p->use_k3 || (p->mid3_w && p->mid3_b), MOP_EINVAL, "use_k3 set but mid3 tensors missing");
+  }
+  if (bwd) {
+    MOP_REQUIRE(p->dy && p->dqkv && p->dhead_part && p->dlogit_part, MOP_EINVAL, "backward buffers missing");
+    MOP_REQUIRE((p->q_scale == nullptr) || p->dscale_part, MOP_EINVAL, "dscale_part missing");
+  }
+  return MOP_OK;
+}
+
+static int edgewise_grid(const MopEdgewiseParams* p) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;  // sizing only (no device): B200
+  int G = p->B * p->H;
+  return G < 2 * sms ? G : 2 * sms;
+}
+
+static ew::Layout edgewise_layout(const MopEdgewiseParams* p, int bwd) {
+  ew::Layout L;
+  const bool dense = p->gate_mode == MOP_GATE_DENSE;
+  L.build(p->N, p->dk, p->V, p->Vp, dense ? 1 : p->gate_rank, dense ? p->hidden : 1, dense ? 1 : 0,
+          dense && p->use_k3 ? 1 : 0, bwd);
+  return L;
+}
+
+}  // namespace mop
+
+using namespace mop;
+
+extern "C" {
+
+int mop_abi_version(void) { return MOP_ABI_VERSION; }
+const char* mop_last_error(void) { return g_err; }
+int mop_device_sm_count(void) {
+  int n = sm_count();
+  if (n < 0) { set_error("no CUDA device"); return MOP_ECUDA; }
+  return n;
+}
+
+size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
+  if (!p) return 0;
+  const bool dense = p->gate_mode == MOP_GATE_DENSE;
+  return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3);
+}
+
+size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  ew::Layout L = edgewise_layout(p, backward ? 1 : 0);
+  return (size_t)edgewise_grid(p) * L.total * sizeof(float);
+}
+
+static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
+  int rc = check_edgewise(p, bwd);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available for this shape", p->impl);
+  ew::Layout L = edgewise_layout(p, bwd ? 1 : 0);
+  const int grid = edgewise_grid(p);
+  const size_t need = (size_t)grid * L.total * sizeof(float);
+  MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(p->workspace);
+  if (p->dtype == MOP_F32) {
+    if (bwd) ew::bwd_kernel<float><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+    else ew::fwd_kernel<float><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+  } else {
+    if (bwd) ew::bwd_kernel<__nv_bfloat16><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+    else ew::fwd_kernel<__nv_bfloat16><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_SIMT;
+  return MOP_OK;
+}
+
+int mop_edgewise_fwd(MopEdgewiseParams* p, void* stream) { return edgewise_launch(p, stream, false); }
+int mop_edgewise_bwd(MopEdgewiseParams* p, void* stream) { return edgewise_launch(p, stream, true); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// SDPA
+// ---------------------------------------------------------------------------
+namespace mop {
+static int check_sdpa(const MopSdpaParams* p, bool bwd) {
+  MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
+  MOP_REQUIRE(p->struct_bytes == (int32_t)sizeof(MopSdpaParams), MOP_EABI,
+              "MopSdpaParams size mismatch: caller %d, library %d", p->struct_bytes, (int)sizeof(MopSdpaParams));
+  MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "bad dtype %d", p->dtype);
+  MOP_REQUIRE(p->B > 0 && p->H > 0 && p->Nq > 0 && p->Nk > 0 && p->dk > 0, MOP_EINVAL, "bad shape");
+  MOP_REQUIRE(p->dk <= sdpa::kMaxDk, MOP_EUNSUPPORTED, "head dim %d > %d", p->dk, sdpa::kMaxDk);
+  MOP_REQUIRE(p->q && p->k && p->v && p->y, MOP_EINVAL, "q/k/v/y must be set");
+  if (bwd) MOP_REQUIRE(p->dy && p->dq && p->dk_ && p->dv && p->lse, MOP_EINVAL, "backward buffers (dy,dq,dk,dv,lse) missing");
+  return MOP_OK;
+}
+template <typename K> static int allow_smem(K kernel, size_t bytes) {
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MOP_OK;
+}
+}  // namespace mop
+
+extern "C" {
+
+size_t mop_sdpa_workspace_bytes(const MopSdpaParams* p, int backward) {
+  if (check_sdpa(p, false) != MOP_OK) return 0;
+  return backward ? sdpa::bwd_workspace_floats(p) * sizeof(float) : 0;
+}
+
+int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
+  int rc = check_sdpa(p, false);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
+  const size_t smem = sdpa::smem_bytes(p->dk);
+  const int grid = p->B * p->H * ((p->Nq + sdpa::TQ - 1) / sdpa::TQ);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->dtype == MOP_F32) {
+    if ((rc = allow_smem(sdpa::fwd_kernel<float>, smem))) return rc;
+    sdpa::fwd_kernel<float><<<grid, simt::kThreads, smem, st>>>(*p);
+  } else {
+    if ((rc = allow_smem(sdpa::fwd_kernel<__nv_bfloat16>, smem))) return rc;
+    sdpa::fwd_kernel<__nv_bfloat16><<<grid, simt::kThreads, smem, st>>>(*p);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_SIMT;
+  return MOP_OK;
+}
+
+int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
+  int rc = check_sdpa(p, true);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
+  const size_t need = sdpa::bwd_workspace_floats(p) * sizeof(float);
+  MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+  const size_t smem = sdpa::smem_bytes(p->dk);
+  const int gk = p->B * p->H * ((p->Nk + sdpa::TK - 1) / sdpa::TK);
+  const int gq = p->B * p->H * ((p->Nq + sdpa::TQ - 1) / sdpa::TQ);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(p->workspace);
+  if (p->dtype == MOP_F32) {
+    if ((rc = allow_smem(sdpa::bwd_dkdv_kernel<float>, smem))) return rc;
+    if ((rc = allow_smem(sdpa::bwd_dq_kernel<float>, smem))) return rc;
+    sdpa::bwd_dkdv_kernel<float><<<gk, simt::kThreads, smem, st>>>(*p, ws);
+    sdpa::bwd_dq_kernel<float><<<gq, simt::kThreads, smem, st>>>(*p, ws);
+  } else {
+    if ((rc = allow_smem(sdpa::bwd_dkdv_kernel<__nv_bfloat16>, smem))) return rc;
+    if ((rc = allow_smem(sdpa::bwd_dq_kernel<__nv_bfloat16>, smem))) return rc;
+    sdpa::bwd_dkdv_kernel<__nv_bfloat16><<<gk, simt::kThreads, smem, st>>>(*p, ws);
+    sdpa::bwd_dq_kernel<__nv_bfloat16><<<gq, simt::kThreads, smem, st>>>(*p, ws);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_SIMT;
+  return MOP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Quartet (entry points; kernels in quartet_simt.cuh)
+// ---------------------------------------------------------------------------
+size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward) { (void)p; (void)backward; return 0; }
+int mop_quartet_fwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; set_error("quartet: not built yet"); return MOP_EUNSUPPORTED; }
+int mop_quartet_bwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; set_error("quartet: not built yet"); return MOP_EUNSUPPORTED; }
+
+}  // extern "C"

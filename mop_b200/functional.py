@@ -1,0 +1,291 @@
+"""Autograd-aware Python entry points over the C ABI (libmop_b200.so).
+
+Each function takes the tensors that sit between the reference module's input
+projection(s) and its output projection, launches the CUDA kernels on the
+current stream through ``ctypes`` and returns the attention output in the
+merge-heads layout ``[B, N, H, dk]``.  Nothing here computes on the CPU: a
+non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.MOP_F32, torch.bfloat16: _lib.MOP_BF16}
+_IMPL = {None: _lib.MOP_IMPL_AUTO, "auto": _lib.MOP_IMPL_AUTO, "simt": _lib.MOP_IMPL_SIMT, "tcgen05": _lib.MOP_IMPL_TCGEN05}
+
+# what the most recent launch of each op used ("simt" | "tcgen05"); read by tests / bench
+last_impl: Dict[str, str] = {}
+# number of kernel-launching ABI calls made so far (bench.py reports launches from this)
+abi_calls: Dict[str, int] = {"edgewise_fwd": 0, "edgewise_bwd": 0, "sdpa_fwd": 0, "sdpa_bwd": 0, "quartet_fwd": 0, "quartet_bwd": 0}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"mop_b200: {name} must be a CUDA tensor (there is no CPU path; the CPU oracle lives in oracle/)")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype not in _DT:
+        raise RuntimeError(f"mop_b200: unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+    return _DT[t.dtype]
+
+
+def _f32c(t: Optional[torch.Tensor]):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ----------------------------------------------------------------------------
+# Edgewise
+# ----------------------------------------------------------------------------
+_LOWRANK_KEYS = ("row_proj.weight", "row_proj.bias", "col_proj.weight", "col_proj.bias")
+
+
+def _dense_keys(use_k3: bool):
+    return ("conv1.weight", "conv1.bias") + (("mid3.weight", "mid3.bias") if use_k3 else ()) + ("conv2.weight", "conv2.bias")
+
+
+def _fill_edgewise(p, qkv, scales, logit, head, cfg):
+    B, N, Vp, _, H, dk = qkv.shape
+    p.dtype = _dtype_code(qkv)
+    p.impl = _IMPL[cfg["impl"]]
+    p.B, p.H, p.N, p.dk, p.V, p.Vp = B, H, N, dk, cfg["n_views"], Vp
+    p.gate_mode = _lib.MOP_GATE_LOWRANK if cfg["gate_mode"] == "lowrank" else _lib.MOP_GATE_DENSE
+    p.gate_rank = cfg["gate_rank"]
+    p.hidden = cfg["hidden"]
+    p.use_k3 = int(cfg["use_k3"])
+    p.beta_not = cfg["beta_not"]
+    p.eps = 1e-6
+    p.qkv = _ptr(qkv)
+    if scales is not None:
+        p.q_scale, p.k_scale, p.v_scale = (_ptr(s) for s in scales)
+    p.chain_value_logit = _ptr(logit)
+    if cfg["gate_mode"] == "lowrank":
+        p.row_w, p.row_b, p.col_w, p.col_b = (_ptr(h) for h in head)
+    else:
+        it = iter(head)
+        p.conv1_w, p.conv1_b = _ptr(next(it)), _ptr(next(it))
+        if cfg["use_k3"]:
+            p.mid3_w, p.mid3_b = _ptr(next(it)), _ptr(next(it))
+        p.conv2_w, p.conv2_b = _ptr(next(it)), _ptr(next(it))
+
+
+class _Edgewise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, qkv, q_scale, k_scale, v_scale, logit, *head):
+        lib = _lib.load()
+        _need_cuda(qkv, "qkv")
+        qkv_c = qkv.detach().contiguous()
+        B, N, Vp, _, H, dk = qkv_c.shape
+        scales = None if q_scale is None else tuple(_f32c(s).reshape(cfg["n_views"], H, dk) for s in (q_scale, k_scale, v_scale))
+        logit32 = _f32c(logit).reshape(1)
+        head32 = tuple(_f32c(h) for h in head)
+        y = torch.empty(B, N, H, dk, dtype=qkv_c.dtype, device=qkv_c.device)
+        with torch.cuda.device(qkv_c.device):
+            p = _lib.new_params(_lib.EdgewiseParams)
+            _fill_edgewise(p, qkv_c, scales, logit32, head32, cfg)
+            p.y = _ptr(y)
+            nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 0)
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv_c.device)
+            p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            _lib.check(lib.mop_edgewise_fwd(C.byref(p), _stream()), "mop_edgewise_fwd")
+        last_impl["edgewise_fwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["edgewise_fwd"] += 1
+        ctx.cfg = cfg
+        ctx.has_scales = scales is not None
+        ctx.head_shapes = [h.shape for h in head]
+        ctx.in_dtypes = [None if t is None else t.dtype for t in (q_scale, k_scale, v_scale, logit, *head)]
+        ctx.scale_shape = None if q_scale is None else q_scale.shape
+        ctx.save_for_backward(qkv_c, logit32, *(scales or ()), *head32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        cfg = ctx.cfg
+        saved = ctx.saved_tensors
+        qkv_c, logit32 = saved[0], saved[1]
+        scales = tuple(saved[2:5]) if ctx.has_scales else None
+        head32 = tuple(saved[5:] if ctx.has_scales else saved[2:])
+        B, N, Vp, _, H, dk = qkv_c.shape
+        V = cfg["n_views"]
+        dy_c = dy.detach().to(qkv_c.dtype).contiguous()
+        dev = qkv_c.device
+        dqkv = torch.empty_like(qkv_c)
+        with torch.cuda.device(dev):
+            p = _lib.new_params(_lib.EdgewiseParams)
+            _fill_edgewise(p, qkv_c, scales, logit32, head32, cfg)
+            y_dummy = dqkv  # forward output is not needed by the backward kernels
+            p.y = _ptr(y_dummy)
+            nhead = lib.mop_edgewise_head_param_count(C.byref(p))
+            G = B * H
+            dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev)
+            dlogit_part = torch.empty(G, dtype=torch.float32, device=dev)
+            dscale_part = torch.empty(G, 3, V, dk, dtype=torch.float32, device=dev) if scales is not None else None
+            p.dy, p.dqkv = _ptr(dy_c), _ptr(dqkv)
+            p.dhead_part, p.dlogit_part, p.dscale_part = _ptr(dhead_part), _ptr(dlogit_part), _ptr(dscale_part)
+            nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 1)
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            _lib.check(lib.mop_edgewise_bwd(C.byref(p), _stream()), "mop_edgewise_bwd")
+        last_impl["edgewise_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["edgewise_bwd"] += 1
+        dts = ctx.in_dtypes
+        if scales is not None:
+            ds = dscale_part.view(B, H, 3, V, dk).sum(0).permute(1, 2, 0, 3)  # [3,V,H,dk]
+            dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
+        else:
+            dq_s = dk_s = dv_s = None
+        dlogit = dlogit_part.sum().reshape(()).to(dts[3])
+        flat = dhead_part.sum(0)
+        dheads, off = [], 0
+        for shp, dt in zip(ctx.head_shapes, dts[4:]):
+            n = math.prod(shp)
+            dheads.append(flat[off:off + n].reshape(shp).to(dt))
+            off += n
+        return (None, dqkv, dq_s, dk_s, dv_s, dlogit, *dheads)
+
+
+def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value_logit: torch.Tensor,
+                       head: Dict[str, torch.Tensor], *, n_views: int, beta_not: float, gate_mode: str,
+                       gate_rank: int = 4, use_k3: bool = False, impl: Optional[str] = None) -> torch.Tensor:
+    """Edgewise Mixture-of-Products attention core (reference attention_variants.py:500-562).
+
+    qkv   ``[B, N, Vp, 3, H, dk]``: output of the shared qkv Linear (Vp=1, with
+          per-view ``q/k/v_scale [V,H,1,dk]``) or of one Linear per view (Vp=V,
+          scales None).
+    head  gate-head tensors under the reference names (``row_proj.weight`` ... or
+          ``conv1.weight`` ...).
+    Returns ``y [B, N, H, dk]``; differentiable w.r.t. qkv, the scales,
+    ``chain_value_logit`` and every head tensor.
+    """
+    if gate_mode not in ("lowrank", "dense"):
+        raise ValueError(f"gate_mode {gate_mode!r}")
+    if qkv.dim() != 6 or qkv.shape[3] != 3:
+        raise ValueError("qkv must be [B,N,Vp,3,H,dk]")
+    dense_k3 = bool(use_k3) and gate_mode == "dense"  # use_k3 has no effect on the low-rank head (:273-278)
+    keys = _LOWRANK_KEYS if gate_mode == "lowrank" else _dense_keys(dense_k3)
+    hidden = head["conv1.weight"].shape[0] if gate_mode == "dense" else 16
+    cfg = dict(n_views=int(n_views), beta_not=float(beta_not), gate_mode=gate_mode, gate_rank=int(gate_rank),
+               use_k3=dense_k3, hidden=int(hidden), impl=impl)
+    return _Edgewise.apply(cfg, qkv, q_scale, k_scale, v_scale, chain_value_logit, *[head[k] for k in keys])
+
+
+# ----------------------------------------------------------------------------
+# SDPA
+# ----------------------------------------------------------------------------
+def _bstrides(t: torch.Tensor):
+    """Element strides of a 4-d tensor broadcastable to [B,H,Nq,Nk] (0 on size-1 dims)."""
+    return [0 if t.shape[i] == 1 else t.stride(i) for i in range(4)]
+
+
+def _as4(t: torch.Tensor, B, H, Nq, Nk, name):
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    for have, want in zip(t.shape, (B, H, Nq, Nk)):
+        if have not in (1, want):
+            raise ValueError(f"{name} shape {tuple(t.shape)} does not broadcast to {(B, H, Nq, Nk)}")
+    return t
+
+
+def _fill_sdpa(p, q, k, v, causal, bias, zero_mask, cfg):
+    B, Nq, H, dk = q.shape
+    Nk = k.shape[1]
+    p.dtype = _dtype_code(q)
+    p.impl = _IMPL[cfg.get("impl")]
+    p.B, p.H, p.Nq, p.Nk, p.dk, p.causal = B, H, Nq, Nk, dk, int(causal)
+    p.scale = 1.0 / math.sqrt(dk)
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        if t.stride(3) != 1:
+            raise ValueError(f"{name}: last dim must be contiguous")
+        setattr(p, name, _ptr(t))
+        setattr(p, f"{name}_sb", t.stride(0)); setattr(p, f"{name}_sn", t.stride(1)); setattr(p, f"{name}_sh", t.stride(2))
+    if bias is not None:
+        p.bias = _ptr(bias)
+        p.bias_sb, p.bias_sh, p.bias_sq, p.bias_sk = _bstrides(bias)
+    if zero_mask is not None:
+        p.zero_mask = _ptr(zero_mask)
+        p.zm_sb, p.zm_sh, p.zm_sq, p.zm_sk = _bstrides(zero_mask)
+
+
+class _Sdpa(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, q, k, v, bias, zero_mask):
+        lib = _lib.load()
+        for n, t in (("q", q), ("k", k), ("v", v)):
+            _need_cuda(t, n)
+        q, k, v = q.detach(), k.detach(), v.detach()
+        B, Nq, H, dk = q.shape
+        y = torch.empty(B, Nq, H, dk, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            p = _lib.new_params(_lib.SdpaParams)
+            _fill_sdpa(p, q, k, v, cfg["causal"], bias, zero_mask, cfg)
+            p.y, p.lse = _ptr(y), _ptr(lse)
+            _lib.check(lib.mop_sdpa_fwd(C.byref(p), _stream()), "mop_sdpa_fwd")
+        last_impl["sdpa_fwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["sdpa_fwd"] += 1
+        ctx.cfg = cfg
+        ctx.save_for_backward(q, k, v, y, lse, *[t for t in (bias, zero_mask) if t is not None])
+        ctx.has = (bias is not None, zero_mask is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        q, k, v, y, lse, *rest = ctx.saved_tensors
+        rest = list(rest)
+        bias = rest.pop(0) if ctx.has[0] else None
+        zero_mask = rest.pop(0) if ctx.has[1] else None
+        B, Nq, H, dk = q.shape
+        Nk = k.shape[1]
+        dy_c = dy.detach().to(q.dtype).contiguous()
+        dq = torch.empty(B, Nq, H, dk, dtype=q.dtype, device=q.device)
+        dk_ = torch.empty(B, Nk, H, dk, dtype=q.dtype, device=q.device)
+        dv = torch.empty(B, Nk, H, dk, dtype=q.dtype, device=q.device)
+        with torch.cuda.device(q.device):
+            p = _lib.new_params(_lib.SdpaParams)
+            _fill_sdpa(p, q, k, v, ctx.cfg["causal"], bias, zero_mask, ctx.cfg)
+            p.y, p.lse, p.dy = _ptr(y), _ptr(lse), _ptr(dy_c)
+            p.dq, p.dk_, p.dv = _ptr(dq), _ptr(dk_), _ptr(dv)
+            nbytes = lib.mop_sdpa_workspace_bytes(C.byref(p), 1)
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=q.device)
+            p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            _lib.check(lib.mop_sdpa_bwd(C.byref(p), _stream()), "mop_sdpa_bwd")
+        last_impl["sdpa_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["sdpa_bwd"] += 1
+        return None, dq, dk_, dv, None, None
+
+
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = False,
+         bias: Optional[torch.Tensor] = None, zero_mask: Optional[torch.Tensor] = None,
+         impl: Optional[str] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(dk) [zero_mask==0 -> -inf] [causal] [+ bias]) v.
+
+    q ``[B,Nq,H,dk]``, k/v ``[B,Nk,H,dk]`` (any batch/token/head strides, last
+    dim contiguous - e.g. slices of a fused qkv projection).  ``bias`` and
+    ``zero_mask`` broadcast to ``[B,H,Nq,Nk]`` and are not differentiated.
+    Returns ``[B,Nq,H,dk]``.
+    """
+    B, Nq, H, dk = q.shape
+    Nk = k.shape[1]
+    if bias is not None:
+        if bias.requires_grad:
+            raise NotImplementedError("gradient w.r.t. the additive attention bias is not provided")
+        bias = _as4(bias.detach().float(), B, H, Nq, Nk, "bias")
+    if zero_mask is not None:
+        zero_mask = _as4(zero_mask.detach().float(), B, H, Nq, Nk, "zero_mask")
+    return _Sdpa.apply(dict(causal=bool(causal), impl=impl), q, k, v, bias, zero_mask)

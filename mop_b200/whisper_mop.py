@@ -1,0 +1,68 @@
+"""Whisper-MoP attention blocks on the fused kernels.
+
+Drop-in for ``MultiheadSelfAttention`` / ``MultiheadCrossAttention`` of
+``mop/models/whisper_mop.py:137-221``: same constructors, same
+``{q,k,v,o}_proj`` parameters; the matmul-softmax-matmul core runs in
+libmop_b200 (causal fill and additive bias handled in-kernel).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as MF
+
+
+def _no_dropout(m):
+    if m.training and m.attn_drop.p > 0.0:
+        raise NotImplementedError("attention dropout inside the fused kernel is not provided; use dropout=0.0")
+
+
+class MultiheadSelfAttention(nn.Module):
+    def __init__(self, dim: int, n_head: int, dropout: float, bias: bool, causal: bool):
+        super().__init__()
+        if dim % n_head:
+            raise AssertionError("dim must be divisible by n_head")
+        self.dim, self.n_head, self.head_dim = dim, n_head, dim // n_head
+        self.scale = self.head_dim ** -0.5
+        self.causal = causal
+        self.q_proj = nn.Linear(dim, dim, bias=bias)
+        self.k_proj = nn.Linear(dim, dim, bias=bias)
+        self.v_proj = nn.Linear(dim, dim, bias=bias)
+        self.o_proj = nn.Linear(dim, dim, bias=bias)
+        self.attn_drop = nn.Dropout(dropout)
+        self.resid_drop = nn.Dropout(dropout)
+
+    def forward(self, x: torch.Tensor, attn_bias: Optional[torch.Tensor] = None):
+        _no_dropout(self)
+        B, T, D = x.shape
+        shp = (B, T, self.n_head, self.head_dim)
+        y = MF.sdpa(self.q_proj(x).view(shp), self.k_proj(x).view(shp), self.v_proj(x).view(shp),
+                    causal=self.causal, bias=attn_bias)
+        return self.resid_drop(self.o_proj(y.reshape(B, T, D)))
+
+
+class MultiheadCrossAttention(nn.Module):
+    def __init__(self, dim_q: int, dim_kv: int, n_head: int, dropout: float, bias: bool):
+        super().__init__()
+        if dim_q % n_head:
+            raise AssertionError("dim_q must be divisible by n_head")
+        self.n_head, self.head_dim = n_head, dim_q // n_head
+        self.scale = self.head_dim ** -0.5
+        self.q_proj = nn.Linear(dim_q, dim_q, bias=bias)
+        self.k_proj = nn.Linear(dim_kv, dim_q, bias=bias)
+        self.v_proj = nn.Linear(dim_kv, dim_q, bias=bias)
+        self.o_proj = nn.Linear(dim_q, dim_q, bias=bias)
+        self.attn_drop = nn.Dropout(dropout)
+        self.resid_drop = nn.Dropout(dropout)
+
+    def forward(self, x_q: torch.Tensor, x_kv: torch.Tensor, attn_mask: Optional[torch.Tensor] = None):
+        _no_dropout(self)
+        B, Tq, Dq = x_q.shape
+        Tk = x_kv.shape[1]
+        H, dh = self.n_head, self.head_dim
+        y = MF.sdpa(self.q_proj(x_q).view(B, Tq, H, dh), self.k_proj(x_kv).view(B, Tk, H, dh),
+                    self.v_proj(x_kv).view(B, Tk, H, dh), bias=attn_mask)
+        return self.resid_drop(self.o_proj(y.reshape(B, Tq, Dq)))

@@ -1,0 +1,165 @@
+"""GPU parity of the Edgewise path (CUDA kernels through the C ABI) vs the CPU oracle.
+
+Tolerances (north_star): fp32 mode max-abs <= 1e-5 (scaled by max|ref| when the
+tensor is larger than O(1), parameter gradients relative to ||g||_inf as in
+SURVEY.md 8c); bf16 mode (max abs err)/(max abs ref) <= 2e-2 against the fp64
+oracle evaluated on the same bf16-rounded inputs.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import bf16_round, max_abs, rel_to_max, scaled_tol
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+PARAM_TOL = 2e-5   # relative to ||g||_inf (reference fp32 self-noise reaches 5e-5 here)
+BF16_TOL = 2e-2
+
+EW_GOLDEN = ["ew_lowrank_share_v5", "ew_lowrank_sep_v3", "ew_lowrank_share_v2_n64", "ew_dense_share_v2",
+             "ew_dense_k3_share_v5", "ew_dense_k3_sep_v3", "ew_lensqk_lowrank", "ew_lensqk_causal_dense"]
+
+
+def _module_from_golden(case, device, dtype=torch.float32):
+    from mop_b200 import EdgewiseMSA
+    m = EdgewiseMSA(case["dim"], heads=case["heads"], **case["kwargs"])
+    missing = m.load_state_dict(case["state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.to(device=device, dtype=dtype)
+
+
+@pytest.mark.parametrize("name", EW_GOLDEN)
+def test_module_matches_reference_golden_fp32(name):
+    case = load_golden(name)
+    m = _module_from_golden(case, "cuda")
+    x = case["inputs"]["x"].cuda().requires_grad_(True)
+    y = m(x)
+    assert max_abs(y, case["y"]) <= scaled_tol(case["y"], FP32_TOL)
+    y.backward(case["dy"].cuda())
+    assert max_abs(x.grad, case["dinputs"]["x"]) <= scaled_tol(case["dinputs"]["x"], FP32_TOL)
+    for k, p in m.named_parameters():
+        ref = case["dparams"][k]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert max_abs(g, ref) <= PARAM_TOL * max(1.0, ref.abs().max().item()), k
+
+
+def _rand_problem(B, H, N, dk, V, shared, mode, k3, r, seed, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=dtype)
+    Vp = 1 if shared else V
+    C = 2 * V + 2
+    qkv = rn(B, N, Vp, 3, H, dk)
+    scales = [1 + 0.1 * rn(V, H, 1, dk) for _ in range(3)] if shared else [None] * 3
+    if mode == "lowrank":
+        head = {"row_proj.weight": rn(4 * r, C, 1) / math.sqrt(C), "row_proj.bias": 0.3 * rn(4 * r),
+                "col_proj.weight": rn(4 * r, C, 1) / math.sqrt(C), "col_proj.bias": 0.3 * rn(4 * r)}
+    else:
+        head = {"conv1.weight": rn(16, C, 1, 1) / math.sqrt(C), "conv1.bias": 0.2 * rn(16),
+                "conv2.weight": rn(4, 16, 1, 1) / 4, "conv2.bias": 0.3 * rn(4)}
+        if k3:
+            head["mid3.weight"] = rn(16, 16, 3, 3) / 12
+            head["mid3.bias"] = 0.2 * rn(16)
+    logit = torch.tensor(-2.0, dtype=dtype)
+    dy = rn(B, N, H, dk)
+    return qkv, scales, head, logit, dy
+
+
+def _oracle(qkv, scales, head, logit, dy, V, mode, r, beta):
+    from oracle.edgewise_manual import edgewise_packed
+    sc = [None if s is None else s.reshape(V, s.shape[1], -1) for s in scales]
+    return edgewise_packed(qkv, *sc, head, logit, V=V, beta_not=beta, gate_mode=mode, gate_rank=r, dy=dy)
+
+
+def _run_gpu(qkv, scales, head, logit, dy, V, mode, r, beta, k3, dtype):
+    from mop_b200 import edgewise_attention
+    dev = "cuda"
+    q = qkv.to(dev, dtype).requires_grad_(True)
+    sc = [None if s is None else s.to(dev, torch.float32).requires_grad_(True) for s in scales]
+    hd = {k: v.to(dev, torch.float32).requires_grad_(True) for k, v in head.items()}
+    lg = logit.to(dev, torch.float32).requires_grad_(True)
+    y = edgewise_attention(q, *sc, lg, hd, n_views=V, beta_not=beta, gate_mode=mode, gate_rank=r, use_k3=k3)
+    y.backward(dy.to(dev, dtype))
+    grads = {"qkv": q.grad, "logit": lg.grad}
+    if sc[0] is not None:
+        grads.update(q_scale=sc[0].grad.reshape(V, -1, q.shape[-1]), k_scale=sc[1].grad.reshape(V, -1, q.shape[-1]),
+                     v_scale=sc[2].grad.reshape(V, -1, q.shape[-1]))
+    grads.update({k: v.grad for k, v in hd.items()})
+    return y, grads
+
+
+CORE_CASES = [
+    # B, H, N, dk, V, shared, mode, k3, r
+    (2, 2, 8, 16, 2, True, "lowrank", False, 4),
+    (2, 3, 64, 56, 5, True, "lowrank", False, 4),      # config-1 core shape
+    (1, 2, 100, 54, 3, False, "lowrank", False, 2),    # ragged N, dk=54
+    (1, 2, 196, 64, 5, True, "lowrank", False, 4),     # ViT-B/16 core shape
+    (2, 2, 33, 24, 3, True, "dense", False, 4),
+    (1, 2, 40, 16, 5, True, "dense", True, 4),
+    (1, 1, 1, 8, 2, True, "lowrank", False, 1),        # single token
+]
+
+
+@pytest.mark.parametrize("B,H,N,dk,V,shared,mode,k3,r", CORE_CASES)
+def test_core_vs_oracle_fp32(B, H, N, dk, V, shared, mode, k3, r):
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, shared, mode, k3, r, seed=N * 131 + V)
+    y_ref, g_ref = _oracle(qkv, scales, head, logit, dy, V, mode, r, 0.5)
+    y, g = _run_gpu(qkv, scales, head, logit, dy, V, mode, r, 0.5, k3, torch.float32)
+    assert max_abs(y, y_ref) <= FP32_TOL
+    assert max_abs(g["qkv"], g_ref["qkv"]) <= scaled_tol(g_ref["qkv"], FP32_TOL)
+    for k, ref in g_ref.items():
+        if k == "qkv":
+            continue
+        assert max_abs(g[k].reshape(ref.shape), ref) <= PARAM_TOL * max(1.0, ref.abs().max().item()), k
+
+
+@pytest.mark.parametrize("B,H,N,dk,V,shared,mode,k3,r", CORE_CASES[:5])
+def test_core_vs_oracle_bf16(B, H, N, dk, V, shared, mode, k3, r):
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, shared, mode, k3, r, seed=N * 17 + V)
+    qkv, dy = bf16_round(qkv), bf16_round(dy)
+    y_ref, g_ref = _oracle(qkv, scales, head, logit, dy, V, mode, r, 0.5)
+    y, g = _run_gpu(qkv, scales, head, logit, dy, V, mode, r, 0.5, k3, torch.bfloat16)
+    assert y.dtype == torch.bfloat16
+    assert rel_to_max(y, y_ref) <= BF16_TOL
+    for k, ref in g_ref.items():
+        assert rel_to_max(g[k].reshape(ref.shape), ref) <= BF16_TOL, k
+
+
+def test_full_size_properties_config1():
+    """Config-1 core size (B=256,H=4,N=64,dk=56,V=5): properties that need no oracle.
+
+    (1) rows of A and of the chain product F are stochastic, so constant values
+        v[n,:] = c give y = (vs_1 + w vs_V) * c for every token;
+    (2) y is linear in the value tensor for fixed Q,K;
+    (3) the batch is processed independently: permuting it permutes y bit-exactly.
+    """
+    from mop_b200 import edgewise_attention
+    B, H, N, dk, V, r = 256, 4, 64, 56, 5, 4
+    qkv, scales, head, logit, _ = _rand_problem(B, H, N, dk, V, True, "lowrank", False, r, seed=5, dtype=torch.float32)
+    dev = "cuda"
+    qkv = qkv.to(dev); sc = [s.to(dev) for s in scales]; hd = {k: v.to(dev) for k, v in head.items()}; lg = logit.to(dev)
+    f = lambda t: edgewise_attention(t, *sc, lg, hd, n_views=V, beta_not=0.5, gate_mode="lowrank", gate_rank=r)
+    c = torch.randn(H, dk, device=dev)
+    qc = qkv.clone(); qc[:, :, 0, 2] = c
+    w = torch.sigmoid(lg)
+    want = (sc[2][0, :, 0] + w * sc[2][V - 1, :, 0]) * c
+    assert (f(qc) - want[None, None]).abs().max().item() <= 1e-5
+    y1 = f(qkv)
+    q2 = qkv.clone(); q2[:, :, 0, 2] = torch.randn(B, N, H, dk, device=dev)
+    y2 = f(q2)
+    q3 = qkv.clone(); q3[:, :, 0, 2] = 0.5 * qkv[:, :, 0, 2] - 2.0 * q2[:, :, 0, 2]
+    assert (f(q3) - (0.5 * y1 - 2.0 * y2)).abs().max().item() <= 2e-5
+    perm = torch.randperm(B, device=dev)
+    assert torch.equal(f(qkv[perm]), y1[perm])
+
+
+def test_unsupported_paths_raise():
+    from mop_b200 import EdgewiseMSA
+    m = EdgewiseMSA(16, heads=2, n_views=2, share_qkv=True, gate_mode="lowrank").cuda()
+    x = torch.randn(1, 4, 16, device="cuda")
+    with pytest.raises(RuntimeError, match="attn_mask"):
+        m(x, torch.ones(4, 4, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        m.cpu()(x.cpu())
