@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the MoP attention hot path: ViT-MoP (model "E+") training throughput.
+
+Workload (BASELINE.json configs[1]): ViTEdgewise E+ - dim 224, depth 8, heads 4,
+100 classes, mlp_ratio 3, 5 views, share_qkv, use_k3, lowrank:mix5 gates (rank 4) -
+on synthetic CIFAR-shaped data (32x32, batch 256 per GPU), bf16 autocast,
+forward + cross-entropy + backward + AdamW step.  One "step" = one such pass over
+one batch.  Batch-sharded data parallel (DDP/NCCL) for --gpus N > 1 (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]        # this repo (CUDA kernels)
+    python bench.py --impl reference ...                       # CPU port of the reference path
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM
+(device-timed, CUDA events per step, L2 flushed between steps, max over ranks);
+`e2e` = the same step driven from pinned HOST buffers through the public module
+API (H2D of the batch + D2H of the loss inside the timed region);
+`roofline` = achieved algorithmic TFLOP/s of the dominant attention kernel
+against the measured dense-bf16 peak; `cpu_baseline` = the oracle port of the
+reference's eager path timed on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+MODEL = dict(dim=224, depth=8, heads=4, n_classes=100, mlp_ratio=3.0, n_views=5, share_qkv=True, use_k3=True,
+             gate_mode="lowrank", gate_rank=4, gate_init="mix5", drop_path=0.1)
+BATCH, IMG, PATCH, NTOK = 256, 32, 4, 64
+WORKLOAD = "ViTEdgewise E+ (dim224 depth8 heads4 V5 share_qkv use_k3 lowrank:mix5 r4), CIFAR-shaped 32x32, batch 256/GPU, fwd+bwd+AdamW"
+
+
+def edgewise_fwd_flops(B, H, N, dk, V, r):
+    """Algorithmic FLOPs of one Edgewise forward (dense contractions only)."""
+    return B * H * (2 * N * N * dk * V + 2 * N ** 3 * 2 * (V - 1) + 2 * N * N * dk * 2 + 2 * N * N * 4 * r)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return dict(bf16=float(d["bf16_tflops_sustained"]), bf16_burst=float(d["bf16_tflops"]), hbm=float(d["hbm_gbs"]),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    except Exception:
+        return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's eager path, on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_port_throughput(steps: int, warmup: int, sample_batch: int):
+    from oracle.edgewise import EdgewiseConfig
+    from oracle.vit_edgewise_ref import train_step_cpu
+    import mop_b200
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    kw = {k: v for k, v in MODEL.items()}
+    skeleton = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **kw)  # parameters only (same init as the GPU arm)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in skeleton.state_dict().items()}
+    cfg = EdgewiseConfig(dim=MODEL["dim"], heads=MODEL["heads"], n_views=MODEL["n_views"], share_qkv=True, use_k3=True,
+                         gate_mode="lowrank", gate_rank=MODEL["gate_rank"], gate_init="mix5")
+    opt = torch.optim.AdamW([p for p in sd.values() if p.requires_grad], lr=1e-3, weight_decay=0.05)
+    x = torch.randn(sample_batch, 3, IMG, IMG)
+    y = torch.randint(0, MODEL["n_classes"], (sample_batch,))
+    run = lambda: train_step_cpu(sd, cfg, x, y, depth=MODEL["depth"], patch=PATCH, drop_path_rate=MODEL["drop_path"], opt=opt)
+    for _ in range(warmup):
+        run()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return dict(value=sample_batch / best, unit="images/s", cores=cores, kind="port",
+                sample=f"{steps} eager fp32 fwd+bwd+AdamW steps of the same model at batch {sample_batch} (of {BATCH}), best step, "
+                       f"torch CPU {cores} threads"), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 32
+    steps = max(1, min(args.steps, 5))
+    cb, mean_s = cpu_port_throughput(steps, min(args.warmup, 1), sample)
+    line = {"impl": "reference", "metric": "vit_mop_train_images_per_sec", "value": cb["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": mean_s * 1e3 * BATCH / sample,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU port of the reference eager path (oracle/), host cores only"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import mop_b200
+    from mop_b200 import functional as MF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = world > 1
+    if ddp:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **MODEL).to(dev)
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
+                                                    gradient_as_bucket_view=True) if ddp else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True)
+    gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    x_host = torch.randn(BATCH, 3, IMG, IMG, generator=gen).pin_memory()
+    y_host = torch.randint(0, MODEL["n_classes"], (BATCH,), generator=gen).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -------------
+    sampler = ClockSampler(local)
+    MF.kernel_timing = True
+    MF.kernel_events.clear()
+    calls0 = dict(MF.abi_calls)
+    if ddp:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(x_dev, y_dev)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    MF.kernel_timing = False
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in MF.kernel_events.items()}
+    launches = sum(MF.abi_calls[k] - calls0[k] for k in calls0)
+    impl_used = dict(MF.last_impl)
+
+    # ---- end to end: host buffers in, loss out, wall clock ------------------------------------
+    for _ in range(2):
+        float(step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)))
+    if ddp:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        loss_val = float(loss)  # D2H read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    t = torch.tensor([step_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if ddp:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        B, H, N, dk, V, r = BATCH, MODEL["heads"], NTOK, MODEL["dim"] // MODEL["heads"], MODEL["n_views"], MODEL["gate_rank"]
+        f_fwd = edgewise_fwd_flops(B, H, N, dk, V, r)
+        dom = "edgewise_bwd" if kern_ms.get("edgewise_bwd", 0) >= kern_ms.get("edgewise_fwd", 0) else "edgewise_fwd"
+        dom_flops = 2 * f_fwd if dom == "edgewise_bwd" else f_fwd
+        dom_ms = kern_ms.get(dom, float("nan"))
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+        attn_ms = MODEL["depth"] * (kern_ms.get("edgewise_fwd", 0) + kern_ms.get("edgewise_bwd", 0))
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_port_throughput(steps=2, warmup=1, sample_batch=32)
+        line = {
+            "metric": "vit_mop_train_images_per_sec", "value": world * BATCH / (step_ms * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
+                       "attention_impl": impl_used, "loss": loss_val},
+            "clocks": clocks,
+            "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["source"],
+                         "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
+                         "fwd_ms": kern_ms.get("edgewise_fwd"), "bwd_ms": kern_ms.get("edgewise_bwd"),
+                         "attention_tflops_fwd_bwd": 3 * f_fwd * MODEL["depth"] / (attn_ms * 1e-3) / 1e12 if attn_ms else None,
+                         "attention_share_of_step": attn_ms / step_ms if step_ms else None},
+            "cpu_baseline": cb,
+        }
+        print(json.dumps(line), flush=True)
+    if ddp:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,30 @@ last_impl: Dict[str, str] = {}
 abi_calls: Dict[str, int] = {"edgewise_fwd": 0, "edgewise_bwd": 0, "sdpa_fwd": 0, "sdpa_bwd": 0, "quartet_fwd": 0, "quartet_bwd": 0}
 
 
+# Optional per-launch device timing: when `kernel_timing` is True every ABI call is bracketed by
+# CUDA events on the launching stream; bench.py reads `kernel_events` after a synchronize.
+kernel_timing = False
+kernel_events: Dict[str, list] = {}
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if kernel_timing:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if kernel_timing:
+            self.e1.record()
+            kernel_events.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -101,7 +125,8 @@ class _Edgewise(torch.autograd.Function):
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 0)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv_c.device)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
-            _lib.check(lib.mop_edgewise_fwd(C.byref(p), _stream()), "mop_edgewise_fwd")
+            with _Timed("edgewise_fwd"):
+                _lib.check(lib.mop_edgewise_fwd(C.byref(p), _stream()), "mop_edgewise_fwd")
         last_impl["edgewise_fwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["edgewise_fwd"] += 1
         ctx.cfg = cfg
@@ -140,7 +165,8 @@ class _Edgewise(torch.autograd.Function):
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
-            _lib.check(lib.mop_edgewise_bwd(C.byref(p), _stream()), "mop_edgewise_bwd")
+            with _Timed("edgewise_bwd"):
+                _lib.check(lib.mop_edgewise_bwd(C.byref(p), _stream()), "mop_edgewise_bwd")
         last_impl["edgewise_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["edgewise_bwd"] += 1
         dts = ctx.in_dtypes
@@ -235,7 +261,8 @@ class _Sdpa(torch.autograd.Function):
             p = _lib.new_params(_lib.SdpaParams)
             _fill_sdpa(p, q, k, v, cfg["causal"], bias, zero_mask, cfg)
             p.y, p.lse = _ptr(y), _ptr(lse)
-            _lib.check(lib.mop_sdpa_fwd(C.byref(p), _stream()), "mop_sdpa_fwd")
+            with _Timed("sdpa_fwd"):
+                _lib.check(lib.mop_sdpa_fwd(C.byref(p), _stream()), "mop_sdpa_fwd")
         last_impl["sdpa_fwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["sdpa_fwd"] += 1
         ctx.cfg = cfg
@@ -264,7 +291,8 @@ class _Sdpa(torch.autograd.Function):
             nbytes = lib.mop_sdpa_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=q.device)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
-            _lib.check(lib.mop_sdpa_bwd(C.byref(p), _stream()), "mop_sdpa_bwd")
+            with _Timed("sdpa_bwd"):
+                _lib.check(lib.mop_sdpa_bwd(C.byref(p), _stream()), "mop_sdpa_bwd")
         last_impl["sdpa_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["sdpa_bwd"] += 1
         return None, dq, dk_, dv, None, None
