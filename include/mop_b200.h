@@ -166,6 +166,12 @@ size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward);
 int mop_quartet_fwd(MopQuartetParams* p, void* cuda_stream);
 int mop_quartet_bwd(MopQuartetParams* p, void* cuda_stream);
 
+/* Bring-up check of the tcgen05 building blocks: D = (a_mn ? A^T : A) * (b_mn ? B : B^T) on 64x64 fp32
+ * device matrices (rounded to bf16), accumulator at TMEM lane offset {0,16} / column offset; D2 = D + 1
+ * after a tcgen05.st/ld round trip. */
+int mop_selftest_umma(const float* A, const float* B, float* D, float* D2, int a_mn, int b_mn, int lane_off,
+                      int col_off, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

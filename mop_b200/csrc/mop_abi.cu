@@ -7,6 +7,7 @@
 #include "edgewise_simt.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
+#include "tc_selftest.cuh"
 
 namespace mop {
 
@@ -218,3 +219,15 @@ int mop_quartet_fwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; 
 int mop_quartet_bwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; set_error("quartet: not built yet"); return MOP_EUNSUPPORTED; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// tcgen05 primitive self-test (tests/test_gpu_tc_primitives.py)
+// ---------------------------------------------------------------------------
+extern "C" int mop_selftest_umma(const float* A, const float* B, float* D, float* D2, int a_mn, int b_mn, int lane_off,
+                                 int col_off, void* stream) {
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");
+  MOP_REQUIRE((lane_off == 0 || lane_off == 16) && col_off >= 0 && col_off <= 64, MOP_EINVAL, "bad lane/col offset");
+  tc::selftest_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(A, B, D, D2, a_mn, b_mn, lane_off, col_off);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}

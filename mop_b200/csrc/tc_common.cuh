@@ -1,0 +1,198 @@
+// tcgen05 / TMEM / mbarrier primitives (inline PTX, sm_100a) used by the tensor-core kernels.
+//
+// Shared-memory operand tiles use ONE physical layout, "chunk-major":
+//     byte_offset(r, c) = (c / 8) * (R * 16) + r * 16 + (c % 8) * 2          (bf16, R rows)
+// i.e. the matrix is cut into 8-column chunks; inside a chunk every row is 16 contiguous bytes.
+// A 8-row x 16-byte block is exactly one UMMA "core matrix" of the no-swizzle canonical layouts,
+// so the same tile can be handed to tcgen05.mma either as
+//   * a K-major operand   (tile rows = M/N index, tile cols = K index):  SBO = 128,    LBO = R*16
+//   * an MN-major operand (tile rows = K index,  tile cols = M/N index): SBO = R*16,   LBO = 128
+// which means no kernel in this library ever transposes a tile: X, X^T, A_k and A_k^T are the same bytes.
+#pragma once
+#include "common.cuh"
+
+namespace mop {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap instead.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("mop_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+
+// ---- proxies / fences ---------------------------------------------------------------------------
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp) ---------------------------------------------------------------
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------
+// shared-memory matrix descriptor, no swizzle (layout_type 0), Blackwell version field = 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// chunk-major tile with R rows used as a K-major operand starting at K offset k0 (multiple of 8)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t R, uint32_t k0) {
+  return smem_desc(tile_saddr + (k0 >> 3) * R * 16, R * 16, 128);
+}
+// chunk-major tile with R rows (= K extent) used as an MN-major operand starting at K offset k0
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t R, uint32_t k0) {
+  return smem_desc(tile_saddr + k0 * 16, 128, R * 16);
+}
+// instruction descriptor: kind::f16, bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one K=16 step.  Issued by ONE thread.
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM <-> registers, 16 lanes x 256 bit shape --------------------------------------------------
+// One warp reads 16 TMEM lanes x (8*X) columns.  Thread T receives, for n in [0,X):
+//   v[4n+0], v[4n+1] = lane (T/4),     columns 8n + 2(T%4) + {0,1}
+//   v[4n+2], v[4n+3] = lane (T/4) + 8, same columns
+// (the mma.sync accumulator fragment shape).  taddr = (lane_base << 16) | column.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- chunk-major tile addressing (bf16) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t tile_off(uint32_t R, uint32_t r, uint32_t c) { return (c >> 3) * R * 16 + r * 16 + (c & 7) * 2; }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+
+// Fragment geometry of a 64x64 tile held by 128 threads (4 warps x 16 TMEM lanes):
+//   row_lo = 16*warp + lane/4, row_hi = row_lo + 8, columns 8n + 2*(lane%4) + {0,1} for n in [0,8)
+struct Frag {
+  int warp, lane, row_lo, row_hi, cq;
+  __device__ Frag() {
+    warp = (threadIdx.x >> 5) & 3;
+    lane = threadIdx.x & 31;
+    row_lo = 16 * warp + (lane >> 2);
+    row_hi = row_lo + 8;
+    cq = 2 * (lane & 3);
+  }
+  __device__ __forceinline__ int col(int n) const { return 8 * n + cq; }
+};
+
+// write a 64x64 fp32 fragment as bf16 into a chunk-major 64-row tile (conflict-free 4-byte stores)
+__device__ __forceinline__ void frag_store_bf16(unsigned char* tile, const Frag& f, const float* v) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    *reinterpret_cast<uint32_t*>(tile + tile_off(64, f.row_lo, f.col(n))) = pack_bf16(v[4 * n + 0], v[4 * n + 1]);
+    *reinterpret_cast<uint32_t*>(tile + tile_off(64, f.row_hi, f.col(n))) = pack_bf16(v[4 * n + 2], v[4 * n + 3]);
+  }
+}
+__device__ __forceinline__ void frag_load_bf16(const unsigned char* tile, const Frag& f, float* v) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(tile + tile_off(64, f.row_lo, f.col(n))));
+    float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(tile + tile_off(64, f.row_hi, f.col(n))));
+    v[4 * n + 0] = a.x; v[4 * n + 1] = a.y; v[4 * n + 2] = b.x; v[4 * n + 3] = b.y;
+  }
+}
+
+// sum over the 4 threads that share a row
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+
+// ---- issue a 64x64x(16*KSTEPS) GEMM into TMEM: D = op(A) * op(B) ------------------------------------------
+// a_mn / b_mn: operand tile is used MN-major (see header comment).  One thread issues.
+template <int KSTEPS>
+__device__ __forceinline__ void gemm64(uint32_t d_tmem, uint32_t a_tile, bool a_mn, uint32_t b_tile, bool b_mn, bool accumulate) {
+  const uint32_t id = idesc_bf16(64, 64, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    uint64_t ad = a_mn ? desc_mnmajor(a_tile, 64, 16 * k) : desc_kmajor(a_tile, 64, 16 * k);
+    uint64_t bd = b_mn ? desc_mnmajor(b_tile, 64, 16 * k) : desc_kmajor(b_tile, 64, 16 * k);
+    mma_ss(d_tmem, ad, bd, id, (accumulate || k > 0) ? 1u : 0u);
+  }
+}
+
+}  // namespace tc
+}  // namespace mop

@@ -1,0 +1,29 @@
+"""tcgen05 / TMEM building blocks (descriptors, M=64 MMA, lane-interleaved accumulators, 16x256b ld/st)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("lane_off,col_off", [(0, 0), (16, 0), (0, 64), (16, 32)])
+def test_umma_64x64x64(a_mn, b_mn, lane_off, col_off):
+    from mop_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(a_mn * 2 + b_mn)
+    A = torch.randn(64, 64, generator=g).bfloat16().float()
+    B = torch.randn(64, 64, generator=g).bfloat16().float()
+    ref = (A.double().T if a_mn else A.double()) @ (B.double() if b_mn else B.double().T)
+    Ad, Bd = A.cuda(), B.cuda()
+    D = torch.full((64, 64), float("nan"), device="cuda")
+    D2 = torch.full((64, 64), float("nan"), device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.mop_selftest_umma(p(Ad), p(Bd), p(D), p(D2), a_mn, b_mn, lane_off, col_off,
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert (D.double().cpu() - ref).abs().max().item() < 1e-4
+    assert torch.equal(D2, D + 1.0)
