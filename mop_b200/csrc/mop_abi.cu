@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "edgewise_simt.cuh"
+#include "edgewise_tc.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
 #include "tc_selftest.cuh"
@@ -111,12 +112,29 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
   int rc = check_edgewise(p, bwd);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available for this shape", p->impl);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = ewtc::supported(p) && !bwd;
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
+              "impl %d not available for this shape/direction (tcgen05 path: bf16, N=64, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4)", p->impl);
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t smem = sizeof(ewtc::SmemFwd) + 1024;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MOP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    const int G = p->B * p->H, sms = sm_count();
+    ewtc::fwd_kernel<<<G < sms ? G : sms, 128, smem, st>>>(*p);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
   ew::Layout L = edgewise_layout(p, bwd ? 1 : 0);
   const int grid = edgewise_grid(p);
   const size_t need = (size_t)grid * L.total * sizeof(float);
   MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
-  cudaStream_t st = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(p->workspace);
   if (p->dtype == MOP_F32) {
     if (bwd) ew::bwd_kernel<float><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);

@@ -73,14 +73,14 @@ def _oracle(qkv, scales, head, logit, dy, V, mode, r, beta):
     return edgewise_packed(qkv, *sc, head, logit, V=V, beta_not=beta, gate_mode=mode, gate_rank=r, dy=dy)
 
 
-def _run_gpu(qkv, scales, head, logit, dy, V, mode, r, beta, k3, dtype):
+def _run_gpu(qkv, scales, head, logit, dy, V, mode, r, beta, k3, dtype, impl=None):
     from mop_b200 import edgewise_attention
     dev = "cuda"
     q = qkv.to(dev, dtype).requires_grad_(True)
     sc = [None if s is None else s.to(dev, torch.float32).requires_grad_(True) for s in scales]
     hd = {k: v.to(dev, torch.float32).requires_grad_(True) for k, v in head.items()}
     lg = logit.to(dev, torch.float32).requires_grad_(True)
-    y = edgewise_attention(q, *sc, lg, hd, n_views=V, beta_not=beta, gate_mode=mode, gate_rank=r, use_k3=k3)
+    y = edgewise_attention(q, *sc, lg, hd, n_views=V, beta_not=beta, gate_mode=mode, gate_rank=r, use_k3=k3, impl=impl)
     y.backward(dy.to(dev, dtype))
     grads = {"qkv": q.grad, "logit": lg.grad}
     if sc[0] is not None:
@@ -163,3 +163,26 @@ def test_unsupported_paths_raise():
         m(x, torch.ones(4, 4, device="cuda"))
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         m.cpu()(x.cpu())
+
+
+@pytest.mark.parametrize("B,H,dk,V,r", [(3, 4, 56, 5, 4), (2, 2, 64, 2, 2), (5, 3, 32, 3, 1), (1, 1, 16, 4, 3)])
+def test_tcgen05_forward_vs_oracle_and_simt(B, H, dk, V, r):
+    """The fused tcgen05 forward (N=64 hot shape) against the fp64 oracle on the same bf16 inputs,
+    and against the fp32-math SIMT kernel run on the same bf16 storage."""
+    from mop_b200 import functional as MF
+    N = 64
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, True, "lowrank", False, r, seed=dk + V)
+    qkv, dy = bf16_round(qkv), bf16_round(dy)
+    y_ref, _ = _oracle(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5)
+    from mop_b200 import edgewise_attention
+    dev = "cuda"
+    args = (qkv.to(dev, torch.bfloat16), *[s.to(dev, torch.float32) for s in scales], logit.to(dev, torch.float32),
+            {k: v.to(dev, torch.float32) for k, v in head.items()})
+    kw = dict(n_views=V, beta_not=0.5, gate_mode="lowrank", gate_rank=r)
+    with torch.no_grad():
+        y_tc = edgewise_attention(*args, impl="tcgen05", **kw)
+        assert MF.last_impl["edgewise_fwd"] == "tcgen05"
+        y_simt = edgewise_attention(*args, impl="simt", **kw)
+        assert MF.last_impl["edgewise_fwd"] == "simt"
+    assert rel_to_max(y_tc, y_ref) <= BF16_TOL
+    assert rel_to_max(y_tc, y_simt) <= BF16_TOL
