@@ -113,20 +113,23 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_ok = ewtc::supported(p) && !bwd;
+  const bool tc_ok = ewtc::supported(p);
   MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
-              "impl %d not available for this shape/direction (tcgen05 path: bf16, N=64, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4)", p->impl);
+              "impl %d not available for this shape (tcgen05 path: bf16, N=64, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4)", p->impl);
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem = sizeof(ewtc::SmemFwd) + 1024;
+    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOP_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
       configured_dev = dev;
     }
     const int G = p->B * p->H, sms = sm_count();
-    ewtc::fwd_kernel<<<G < sms ? G : sms, 128, smem, st>>>(*p);
+    const int grid = G < sms ? G : sms;
+    if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
+    else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

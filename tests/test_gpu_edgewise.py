@@ -186,3 +186,22 @@ def test_tcgen05_forward_vs_oracle_and_simt(B, H, dk, V, r):
         assert MF.last_impl["edgewise_fwd"] == "simt"
     assert rel_to_max(y_tc, y_ref) <= BF16_TOL
     assert rel_to_max(y_tc, y_simt) <= BF16_TOL
+
+
+@pytest.mark.parametrize("B,H,dk,V,r", [(3, 4, 56, 5, 4), (2, 2, 64, 2, 2), (5, 3, 32, 3, 1), (1, 1, 16, 4, 3)])
+def test_tcgen05_backward_vs_oracle_and_simt(B, H, dk, V, r):
+    """Fused tcgen05 backward: every gradient against the fp64 oracle (same bf16 inputs) and the SIMT kernel."""
+    from mop_b200 import functional as MF
+    N = 64
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, True, "lowrank", False, r, seed=3 * dk + V)
+    qkv, dy = bf16_round(qkv), bf16_round(dy)
+    _, g_ref = _oracle(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5)
+    _, g_tc = _run_gpu(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5, False, torch.bfloat16, impl="tcgen05")
+    assert MF.last_impl["edgewise_bwd"] == "tcgen05"
+    _, g_simt = _run_gpu(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5, False, torch.bfloat16, impl="simt")
+    assert MF.last_impl["edgewise_bwd"] == "simt"
+    worst = {}
+    for k, ref in g_ref.items():
+        worst[k] = (rel_to_max(g_tc[k].reshape(ref.shape), ref), rel_to_max(g_simt[k].reshape(ref.shape), ref))
+    bad = {k: v for k, v in worst.items() if v[0] > BF16_TOL}
+    assert not bad, f"tcgen05 grads off (tc_err, simt_err): {worst}"
