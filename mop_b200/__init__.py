@@ -6,12 +6,13 @@ backed by hand-written CUDA kernels behind a C ABI (``libmop_b200.so``,
 """
 from .attention_variants import BaselineMSA, EdgewiseGateHead, EdgewiseMSA, UnifiedMSA
 from .components import MLP, MSA, Block, DropPath, PatchEmbed
-from .functional import edgewise_attention, sdpa
+from .functional import edgewise_attention, quartet_attention, sdpa
+from .quartet_attn_patch import CausalSelfAttention, TransformerConfig
 from .vit_edgewise import BlockEdgewise, ViTEdgewise
 from .whisper_mop import MultiheadCrossAttention, MultiheadSelfAttention
 
 __all__ = [
     "BaselineMSA", "EdgewiseGateHead", "EdgewiseMSA", "UnifiedMSA", "MSA", "MLP", "Block", "DropPath", "PatchEmbed",
     "BlockEdgewise", "ViTEdgewise", "MultiheadSelfAttention", "MultiheadCrossAttention",
-    "edgewise_attention", "sdpa",
+    "CausalSelfAttention", "TransformerConfig", "edgewise_attention", "quartet_attention", "sdpa",
 ]

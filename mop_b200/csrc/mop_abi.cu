@@ -233,11 +233,65 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
 }
 
 // ---------------------------------------------------------------------------
-// Quartet (entry points; kernels in quartet_simt.cuh)
+// Quartet
 // ---------------------------------------------------------------------------
-size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward) { (void)p; (void)backward; return 0; }
-int mop_quartet_fwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; set_error("quartet: not built yet"); return MOP_EUNSUPPORTED; }
-int mop_quartet_bwd(MopQuartetParams* p, void* stream) { (void)p; (void)stream; set_error("quartet: not built yet"); return MOP_EUNSUPPORTED; }
+}  // extern "C" (reopened below)
+namespace mop {
+static int check_quartet(const MopQuartetParams* p, bool bwd) {
+  MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
+  MOP_REQUIRE(p->struct_bytes == (int32_t)sizeof(MopQuartetParams), MOP_EABI,
+              "MopQuartetParams size mismatch: caller %d, library %d", p->struct_bytes, (int)sizeof(MopQuartetParams));
+  MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "bad dtype %d", p->dtype);
+  MOP_REQUIRE(p->B > 0 && p->H > 0 && p->T > 1 && p->dk > 0, MOP_EINVAL, "bad shape (T must be >= 2: unbiased std)");
+  MOP_REQUIRE(p->dk <= quartet::kMaxDk, MOP_EUNSUPPORTED, "head dim %d > %d", p->dk, quartet::kMaxDk);
+  MOP_REQUIRE(p->q && p->k && p->v && p->y, MOP_EINVAL, "q/k/v/y must be set");
+  if (p->use_quartet) MOP_REQUIRE(p->q2 && p->k2 && p->mixture && p->quartet_scale, MOP_EINVAL, "quartet tensors missing");
+  if (bwd) {
+    MOP_REQUIRE(p->dy && p->dq && p->dk_ && p->dv && p->stats, MOP_EINVAL, "backward buffers missing");
+    if (p->use_quartet) MOP_REQUIRE(p->dq2 && p->dk2 && p->dscalar_part, MOP_EINVAL, "quartet backward buffers missing");
+  }
+  return MOP_OK;
+}
+template <typename T>
+static int quartet_run(MopQuartetParams* p, cudaStream_t st, bool bwd) {
+  const quartet::Ws w = quartet::layout(p, bwd ? 1 : 0);
+  float* ws = reinterpret_cast<float*>(p->workspace);
+  const size_t smem = quartet::smem_bytes(p->dk);
+  const int BH = p->B * p->H;
+  int rc;
+  quartet::prep_kernel<T><<<BH * w.nm, simt::kThreads, 0, st>>>(*p, w, ws);
+  if (!bwd) {
+    if ((rc = allow_smem(quartet::fwd_kernel<T>, smem))) return rc;
+    quartet::fwd_kernel<T><<<BH * w.nqb, simt::kThreads, smem, st>>>(*p, w, ws);
+  } else {
+    if ((rc = allow_smem(quartet::bwd_dq_kernel<T>, smem))) return rc;
+    if ((rc = allow_smem(quartet::bwd_dkdv_kernel<T>, smem))) return rc;
+    quartet::bwd_dq_kernel<T><<<BH * w.nqb, simt::kThreads, smem, st>>>(*p, w, ws);
+    quartet::gmat_kernel<<<BH * w.nm, simt::kThreads, 0, st>>>(*p, w, ws);
+    quartet::bwd_dkdv_kernel<T><<<BH * w.nqb, simt::kThreads, smem, st>>>(*p, w, ws);
+    quartet::finish_kernel<T><<<BH * w.nm, simt::kThreads, 0, st>>>(*p, w, ws);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_SIMT;
+  return MOP_OK;
+}
+static int quartet_launch(MopQuartetParams* p, void* stream, bool bwd) {
+  int rc = check_quartet(p, bwd);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
+  const size_t need = quartet::layout(p, bwd ? 1 : 0).total * sizeof(float);
+  MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+  return p->dtype == MOP_F32 ? quartet_run<float>(p, (cudaStream_t)stream, bwd) : quartet_run<__nv_bfloat16>(p, (cudaStream_t)stream, bwd);
+}
+}  // namespace mop
+extern "C" {
+size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward) {
+  if (check_quartet(p, false) != MOP_OK) return 0;
+  return quartet::layout(p, backward).total * sizeof(float);
+}
+int mop_quartet_fwd(MopQuartetParams* p, void* stream) { return quartet_launch(p, stream, false); }
+int mop_quartet_bwd(MopQuartetParams* p, void* stream) { return quartet_launch(p, stream, true); }
 
 }  // extern "C"
 

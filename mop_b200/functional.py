@@ -317,3 +317,110 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = Fa
     if zero_mask is not None:
         zero_mask = _as4(zero_mask.detach().float(), B, H, Nq, Nk, "zero_mask")
     return _Sdpa.apply(dict(causal=bool(causal), impl=impl), q, k, v, bias, zero_mask)
+
+
+# ----------------------------------------------------------------------------
+# Quartet
+# ----------------------------------------------------------------------------
+def _fill_quartet(p, q, k, v, q2, k2, mixture, gamma, add_mask, cfg):
+    B, T, H, dk = q.shape
+    p.dtype = _dtype_code(q)
+    p.impl = _IMPL[cfg.get("impl")]
+    p.B, p.H, p.T, p.dk = B, H, T, dk
+    p.use_quartet = int(q2 is not None)
+    p.scale = 1.0 / math.sqrt(dk)
+    p.eps = cfg["eps"]
+    p.q, p.k, p.v = _ptr(q), _ptr(k), _ptr(v)
+    if q2 is not None:
+        p.q2, p.k2, p.mixture, p.quartet_scale = _ptr(q2), _ptr(k2), _ptr(mixture), _ptr(gamma)
+    if add_mask is not None:
+        p.add_mask = _ptr(add_mask)
+        p.am_sb, p.am_sh, p.am_sq, p.am_sk = _bstrides(add_mask)
+
+
+class _Quartet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, q, k, v, q2, k2, mixture, gamma, add_mask):
+        lib = _lib.load()
+        _need_cuda(q, "q")
+        quart = q2 is not None
+        q, k, v = (t.detach().contiguous() for t in (q, k, v))
+        if quart:
+            q2, k2 = q2.detach().contiguous(), k2.detach().contiguous()
+            mix32, gam32 = _f32c(mixture).reshape(1), _f32c(gamma).reshape(1)
+        else:
+            mix32 = gam32 = None
+        B, T, H, dk = q.shape
+        y = torch.empty_like(q)
+        stats = torch.empty(B, H, T, 3, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            p = _lib.new_params(_lib.QuartetParams)
+            _fill_quartet(p, q, k, v, q2, k2, mix32, gam32, add_mask, cfg)
+            p.y, p.stats = _ptr(y), _ptr(stats)
+            nbytes = lib.mop_quartet_workspace_bytes(C.byref(p), 0)
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=q.device)
+            p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            with _Timed("quartet_fwd"):
+                _lib.check(lib.mop_quartet_fwd(C.byref(p), _stream()), "mop_quartet_fwd")
+        last_impl["quartet_fwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["quartet_fwd"] += 1
+        ctx.cfg, ctx.quart, ctx.has_mask = cfg, quart, add_mask is not None
+        ctx.scalar_dtypes = (None, None) if not quart else (mixture.dtype, gamma.dtype)
+        saved = [q, k, v, y, stats] + ([q2, k2, mix32, gam32] if quart else []) + ([add_mask] if add_mask is not None else [])
+        ctx.save_for_backward(*saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        q, k, v, y, stats = saved[:5]
+        rest = saved[5:]
+        q2 = k2 = mix32 = gam32 = add_mask = None
+        if ctx.quart:
+            q2, k2, mix32, gam32 = rest[:4]
+            rest = rest[4:]
+        if ctx.has_mask:
+            add_mask = rest[0]
+        B, T, H, dk = q.shape
+        dev = q.device
+        dy_c = dy.detach().to(q.dtype).contiguous()
+        dq, dk_, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        dq2 = dk2 = dsc = None
+        if ctx.quart:
+            dq2, dk2 = torch.empty_like(q), torch.empty_like(q)
+            dsc = torch.empty(B * H, 2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            p = _lib.new_params(_lib.QuartetParams)
+            _fill_quartet(p, q, k, v, q2, k2, mix32, gam32, add_mask, ctx.cfg)
+            p.y, p.stats, p.dy = _ptr(y), _ptr(stats), _ptr(dy_c)
+            p.dq, p.dk_, p.dv, p.dq2, p.dk2, p.dscalar_part = _ptr(dq), _ptr(dk_), _ptr(dv), _ptr(dq2), _ptr(dk2), _ptr(dsc)
+            nbytes = lib.mop_quartet_workspace_bytes(C.byref(p), 1)
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            with _Timed("quartet_bwd"):
+                _lib.check(lib.mop_quartet_bwd(C.byref(p), _stream()), "mop_quartet_bwd")
+        last_impl["quartet_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
+        abi_calls["quartet_bwd"] += 1
+        dmix = dgam = None
+        if ctx.quart:
+            tot = dsc.sum(0)
+            dmix = tot[0].reshape(1).to(ctx.scalar_dtypes[0])
+            dgam = tot[1].reshape(1).to(ctx.scalar_dtypes[1])
+        return None, dq, dk_, dv, dq2, dk2, dmix, dgam, None
+
+
+def quartet_attention(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=None, *, eps: float = 1e-5,
+                      add_mask: Optional[torch.Tensor] = None, impl: Optional[str] = None) -> torch.Tensor:
+    """GPT Quartet causal attention core (reference quartet_attn_patch.py:88-121).
+
+    q,k,v,(q2,k2) ``[B,T,H,dk]`` (the Linear outputs viewed as heads).  ``q2 is None`` selects the
+    ``use_quartet=False`` branch (single z-scored map).  ``add_mask`` broadcasts to ``[B,H,T,T]`` and is
+    added after the causal fill.  Returns ``[B,T,H,dk]``.
+    """
+    B, T, H, dk = q.shape
+    if add_mask is not None:
+        if add_mask.requires_grad:
+            raise NotImplementedError("gradient w.r.t. the additive attention mask is not provided")
+        add_mask = _as4(add_mask.detach().float(), B, H, T, T, "attention_mask")
+    return _Quartet.apply(dict(eps=float(eps), impl=impl), q, k, v, q2, k2, mixture, quartet_scale, add_mask)

@@ -1,0 +1,76 @@
+"""GPU parity of the Quartet causal attention path vs the CPU oracle / reference golden vectors."""
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import bf16_round, max_abs, rel_to_max, scaled_tol
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, PARAM_TOL, BF16_TOL = 1e-5, 2e-5, 2e-2
+
+
+@pytest.mark.parametrize("name", ["quartet_T24", "quartet_bias_T9", "quartet_off_T16"])
+def test_module_golden(name):
+    from mop_b200 import CausalSelfAttention, TransformerConfig
+    case = load_golden(name)
+    cfg = TransformerConfig(n_layer=1, n_head=case["n_head"], n_embd=32, dropout=0.0, block_size=32,
+                            bias=("q_proj.bias" in case["state_dict"]), use_quartet=case["use_quartet"])
+    m = CausalSelfAttention(cfg)
+    m.load_state_dict(case["state_dict"])
+    m.cuda()
+    x = case["inputs"]["x"].cuda().requires_grad_(True)
+    am = case["add_mask"]
+    y = m(x, attention_mask=None if am is None else am.cuda())
+    assert max_abs(y, case["y"]) <= scaled_tol(case["y"], FP32_TOL)
+    y.backward(case["dy"].cuda())
+    assert max_abs(x.grad, case["dinputs"]["x"]) <= scaled_tol(case["dinputs"]["x"], FP32_TOL)
+    for k, p in m.named_parameters():
+        ref = case["dparams"][k]
+        assert max_abs(p.grad, ref) <= PARAM_TOL * max(1.0, ref.abs().max().item()), k
+
+
+@pytest.mark.parametrize("B,H,T,dk,quart,dtype", [
+    (2, 2, 64, 16, True, torch.float32), (1, 2, 200, 64, True, torch.float32), (1, 2, 130, 32, False, torch.float32),
+    (1, 1, 2, 8, True, torch.float32), (1, 2, 257, 64, True, torch.bfloat16)])
+def test_core_vs_oracle(B, H, T, dk, quart, dtype):
+    from mop_b200 import quartet_attention
+    from oracle.quartet import quartet_core
+    g = torch.Generator().manual_seed(T)
+    mk = lambda: torch.randn(B, T, H, dk, generator=g, dtype=torch.float64)
+    q, k, v, q2, k2, dy = mk(), mk(), mk(), mk(), mk(), mk()
+    if dtype == torch.bfloat16:
+        q, k, v, q2, k2, dy = map(bf16_round, (q, k, v, q2, k2, dy))
+    mix = torch.tensor([0.4], dtype=torch.float64)
+    gam = torch.tensor([1.2], dtype=torch.float64)
+    ins = [q, k, v] + ([q2, k2, mix, gam] if quart else [])
+    ref_in = [t.clone().requires_grad_(True) for t in ins]
+    tr = lambda t: t.transpose(1, 2)
+    if quart:
+        y_ref = tr(quartet_core(tr(ref_in[0]), tr(ref_in[1]), tr(ref_in[2]), tr(ref_in[3]), tr(ref_in[4]), ref_in[5], ref_in[6]))
+    else:
+        y_ref = tr(quartet_core(tr(ref_in[0]), tr(ref_in[1]), tr(ref_in[2])))
+    g_ref = torch.autograd.grad(y_ref, ref_in, dy)
+    gin = [t.to("cuda", dtype if t.dim() == 4 else torch.float32).requires_grad_(True) for t in ins]
+    y = quartet_attention(*gin)
+    y.backward(dy.to("cuda", dtype))
+    if dtype == torch.float32:
+        assert max_abs(y, y_ref) <= FP32_TOL
+        for a, b in zip(gin, g_ref):
+            tol = scaled_tol(b, FP32_TOL) if b.dim() == 4 else PARAM_TOL * max(1.0, b.abs().max().item())
+            assert max_abs(a.grad, b) <= tol
+    else:
+        assert rel_to_max(y, y_ref) <= BF16_TOL
+        for a, b in zip(gin[:5], g_ref[:5]):
+            assert rel_to_max(a.grad, b) <= BF16_TOL
+
+
+def test_causal_logic_bit_exact():
+    """V = identity exposes the probability matrix: strictly-upper entries exactly 0, first row exactly e_0."""
+    from mop_b200 import quartet_attention
+    T = 64
+    mk = lambda: torch.randn(1, T, 1, T, device="cuda")
+    v = torch.eye(T, device="cuda").view(1, T, 1, T)
+    P = quartet_attention(mk(), mk(), v, mk(), mk(), torch.tensor([0.3], device="cuda"), torch.tensor([1.1], device="cuda"))[0, :, 0]
+    assert torch.equal(torch.triu(P, diagonal=1), torch.zeros_like(P))
+    assert P[0, 0].item() == 1.0
+    assert (P.sum(-1) - 1).abs().max().item() <= 1e-6
