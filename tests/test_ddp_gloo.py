@@ -1,0 +1,49 @@
+"""World-size-2 gloo run of the batch-sharding helpers on CPU: sharded DDP gradients == full-batch gradients."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from mop_b200 import ddp
+    r, _, w = ddp.init("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    net = ddp.wrap(model)
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    lo, hi = ddp.shard_bounds(10, rank, world)
+    loss = torch.nn.functional.cross_entropy(net(X[lo:hi]), Y[lo:hi], reduction="sum") / 10 * world
+    loss.backward()  # DDP averages over ranks: sum-over-shard/10*world averaged == full-batch mean loss grad
+    slow = ddp.max_over_ranks(float(rank + 1), "cpu")
+    if rank == 0:
+        torch.save({"grads": [p.grad.clone() for p in model.parameters()], "slow": slow}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_match_full_batch(tmp_path):
+    from mop_b200 import ddp
+    assert [ddp.shard_bounds(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()
+    for a, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(a, p.grad, atol=1e-6)
+    assert got["slow"] == 2.0
