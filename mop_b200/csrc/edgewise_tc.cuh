@@ -18,6 +18,8 @@
 // Math: SURVEY.md appendix A / D.1 (reference attention_variants.py:500-562, :319-331); the
 // executable specification is oracle/edgewise_manual.py.
 #pragma once
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace mop {
@@ -33,7 +35,13 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 // ---- TMEM tile map: tile i -> lane offset 16*(i/8), column 64*(i%8) ---------------------------------
-__host__ __device__ constexpr uint32_t ttile(int i) { return ((uint32_t)(i >= 8 ? 16 : 0) << 16) + 64u * (uint32_t)(i & 7); }
+// backward: 16 tiles in 512 columns (tile i -> lane offset 16*(i/8), column 64*(i%8));
+// forward: 8 tiles in 256 columns (lane offset 16*(i/4), column 64*(i%4)) so that two CTAs fit on one SM.
+template <bool BWD>
+__host__ __device__ constexpr uint32_t ttile(int i) {
+  return BWD ? ((uint32_t)(i >= 8 ? 16 : 0) << 16) + 64u * (uint32_t)(i & 7) : ((uint32_t)(i >= 4 ? 16 : 0) << 16) + 64u * (uint32_t)(i & 3);
+}
+template <bool BWD> struct TmemCols { static constexpr uint32_t value = BWD ? 512 : 256; };
 constexpr int kTS = 0;     // S_1..S_5 (later: dS_k accumulators)   tiles 0..4
 constexpr int kTF = 5;     // forward chain product F
 constexpr int kTR = 6;     // reverse chain product R
@@ -46,9 +54,11 @@ __host__ __device__ constexpr int tileU(int k) { return k < 3 ? 5 + k : 10 + k; 
 // ---- shared-memory tile slots -------------------------------------------------------------------------
 template <bool BWD> struct Slots;
 template <> struct Slots<false> {
-  static constexpr int K = 0, V1 = 1, VL = 2, QC = 3, A = 8, AMIX = 7, N = 13;
-  __device__ static int P(int s) { return 3 + (s & 1); }        // chain outputs ping-pong over the dead Qc tiles
-  __device__ static int R(int s) { return 5 + (s & 1); }
+  // A_i overwrites Qc_i (dead once S_i is in TMEM); the forward chain product is updated in place in the dead K
+  // tile, the reverse one in tile 8 (an MMA that read X has completed before X is rewritten); Amix reuses tile 8.
+  static constexpr int QC = 0, A = 0, K = 5, V1 = 6, VL = 7, AMIX = 8, N = 9;
+  __device__ static int P(int) { return 5; }
+  __device__ static int R(int) { return 8; }
 };
 template <> struct Slots<true> {
   static constexpr int K = 0, V1 = 1, VL = 2, DY = 3, AMIX = 4, QC = 5, A = 12, X = 17, N = 21;
@@ -61,22 +71,26 @@ struct SmemVec {
   float kap[kMaxC][64];
   float a[kMaxQ][64];               // bwd: reused for da
   float b[kMaxQ][64];               // bwd: reused for db
-  float drho[kMaxC][64];            // bwd only
-  float dkap[kMaxC][64];            // bwd only
   float cvec[kMaxV][64];
   float vs1[64], vsL[64];
   float red[kMaxV + 2][4][64];      // cross-warp column sums
-  float da[kMaxQ][64];              // bwd: grad of the row factors (fp32, CUDA-core accumulation)
-  unsigned char a_bf[64 * 16 * 2];  // bwd: bf16 [token][q] operand tile of the column-factor gradient GEMM
   float scal[8];
   uint64_t bar;
   uint32_t tmem_slot;
 };
 
+struct SmemBwdVec {
+  float drho[kMaxC][64];
+  float dkap[kMaxC][64];
+  float da[kMaxQ][64];              // grad of the row factors (fp32, CUDA-core accumulation)
+  unsigned char a_bf[64 * 16 * 2];  // bf16 [token][q] operand tile of the column-factor gradient GEMM
+};
+struct Empty {};
 template <bool BWD>
 struct __align__(1024) Smem {
   unsigned char T[Slots<BWD>::N][kTile];
   SmemVec v;
+  typename std::conditional<BWD, SmemBwdVec, Empty>::type bv;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -187,17 +201,18 @@ __device__ __forceinline__ float cta_sum(float v, float* scratch4) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
+__global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseParams p) {
   using SL = Slots<BWD>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem<BWD>& sm = *reinterpret_cast<Smem<BWD>*>(smem_raw);
   SmemVec& sv_ = sm.v;
+  auto& bv_ = sm.bv;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int V = p.V, r = p.gate_rank, C = 2 * V + 2, dk = p.dk, H = p.H;
   const int ksteps = (dk + 15) >> 4;
   const Frag f;
 
-  if (warp == 0) tmem_alloc<512>(&sv_.tmem_slot);
+  if (warp == 0) tmem_alloc<TmemCols<BWD>::value>(&sv_.tmem_slot);
   if (tid == 0) { mbar_init(&sv_.bar, 1); fence_mbar_init(); }
   tc_fence_before();
   __syncthreads();
@@ -217,12 +232,12 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
     for (int k = 0; k < ks; ++k) {
       uint64_t ad = a_mn ? desc_mnmajor(a_tile, 64, 16 * k) : desc_kmajor(a_tile, 64, 16 * k);
       uint64_t bd = b_mn ? desc_mnmajor(b_tile, 64, 16 * k) : desc_kmajor(b_tile, 64, 16 * k);
-      mma_ss(tbase + ttile(dt) + dcol, ad, bd, id, (acc || k > 0) ? 1u : 0u);
+      mma_ss(tbase + ttile<BWD>(dt) + dcol, ad, bd, id, (acc || k > 0) ? 1u : 0u);
     }
   };
   auto wait_mma = [&]() { mbar_wait(&sv_.bar, phase); phase ^= 1; tc_fence_after(); };
-  auto ld_tile = [&](int t, float* v) { tmem_ld_16x256b_x8(tlane + ttile(t), v); tmem_ld_wait(); };
-  auto st_tile = [&](int t, const float* v) { tmem_st_16x256b_x8(tlane + ttile(t), v); tmem_st_wait(); };
+  auto ld_tile = [&](int t, float* v) { tmem_ld_16x256b_x8(tlane + ttile<BWD>(t), v); tmem_ld_wait(); };
+  auto st_tile = [&](int t, const float* v) { tmem_st_16x256b_x8(tlane + ttile<BWD>(t), v); tmem_st_wait(); };
 
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
   const size_t hd = (size_t)H * dk;
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
         }
         (which ? sv_.b : sv_.a)[qq][tok] = acc;
         if constexpr (BWD)
-          if (which == 0) *reinterpret_cast<__nv_bfloat16*>(sv_.a_bf + tile_off(64, tok, qq)) = __float2bfloat16_rn(acc);
+          if (which == 0) *reinterpret_cast<__nv_bfloat16*>(bv_.a_bf + tile_off(64, tok, qq)) = __float2bfloat16_rn(acc);
       }
     }
     __syncthreads();
@@ -376,12 +391,12 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) { alo[q] = sv_.a[q][f.row_lo]; ahi[q] = sv_.a[q][f.row_hi]; }
 #pragma unroll
-    for (int blk = 0; blk < 4; ++blk) {
+    for (int blk = 0; blk < 4; ++blk) {   // (kept unrolled: amix[] must stay in registers)
       float sv[kMaxV][8], fv[8];
 #pragma unroll
       for (int i = 0; i < kMaxV; ++i)
-        if (i < V) tmem_ld_16x256b_x2(tlane + ttile(kTS + i) + 16 * blk, sv[i]);
-      tmem_ld_16x256b_x2(tlane + ttile(kTF) + 16 * blk, fv);
+        if (i < V) tmem_ld_16x256b_x2(tlane + ttile<BWD>(kTS + i) + 16 * blk, sv[i]);
+      tmem_ld_16x256b_x2(tlane + ttile<BWD>(kTF) + 16 * blk, fv);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -450,8 +465,8 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
         float sv[kMaxV][8], fv[8];
 #pragma unroll
         for (int i = 0; i < kMaxV; ++i)
-          if (i < V) tmem_ld_16x256b_x2(tlane + ttile(kTS + i) + 16 * blk, sv[i]);
-        tmem_ld_16x256b_x2(tlane + ttile(kTF) + 16 * blk, fv);
+          if (i < V) tmem_ld_16x256b_x2(tlane + ttile<BWD>(kTS + i) + 16 * blk, sv[i]);
+        tmem_ld_16x256b_x2(tlane + ttile<BWD>(kTF) + 16 * blk, fv);
         tmem_ld_wait();
         float hf[8], dgv[4][8];
 #pragma unroll
@@ -496,8 +511,8 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
         }
 #pragma unroll
         for (int i = 0; i < kMaxV; ++i)
-          if (i < V) tmem_st_16x256b_x2(tlane + ttile(kTS + i) + 16 * blk, sv[i]);
-        tmem_st_16x256b_x2(tlane + ttile(kTY) + 16 * blk, hf);
+          if (i < V) tmem_st_16x256b_x2(tlane + ttile<BWD>(kTS + i) + 16 * blk, sv[i]);
+        tmem_st_16x256b_x2(tlane + ttile<BWD>(kTY) + 16 * blk, hf);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
 #pragma unroll
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
 #pragma unroll
       for (int q = 0; q < kMaxQ; ++q) {
         const float lo = quad_sum(da_lo[q]), hi = quad_sum(da_hi[q]);
-        if ((f.lane & 3) == 0) { sv_.da[q][f.row_lo] = lo; sv_.da[q][f.row_hi] = hi; }
+        if ((f.lane & 3) == 0) { bv_.da[q][f.row_lo] = lo; bv_.da[q][f.row_hi] = hi; }
       }
       // ===============================================================================================
       // B2: dF += dY (w V_V)^T ; dV1 = A^T dY ; dVL = F^T dY ; db_t = dG_t^T a
@@ -522,7 +537,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
         gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::VL), false, true, ksteps, 64);
         gemm(kTdV1, 0, taddr(SB::AMIX), true, taddr(SB::DY), true, false, 4, 64);
         gemm(kTdVL, 0, sF, true, taddr(SB::DY), true, false, 4, 64);
-        for (int t = 0; t < 4; ++t) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(sv_.a_bf), true, false, 4, 16);
+        for (int t = 0; t < 4; ++t) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(bv_.a_bf), true, false, 4, 16);
         mma_commit(&sv_.bar);
       }
       wait_mma();
@@ -598,19 +613,19 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
           const int t = qq >> 2, k = qq & 3;
           if (k < r) {
             const int q = t * r + k;
-            sr = fmaf(__ldg(p.row_w + q * C + c), sv_.da[qq][tok], sr);
+            sr = fmaf(__ldg(p.row_w + q * C + c), bv_.da[qq][tok], sr);
             sc = fmaf(__ldg(p.col_w + q * C + c), sv_.b[qq][tok], sc);
           }
         }
-        sv_.drho[c][tok] = sr * (1.f / 64.f);
-        sv_.dkap[c][tok] = sc * (1.f / 64.f);
+        bv_.drho[c][tok] = sr * (1.f / 64.f);
+        bv_.dkap[c][tok] = sc * (1.f / 64.f);
       }
       {
         const int nW = 4 * r * C, nP = nW + 4 * r;
         float* dh = p.dhead_part + (size_t)g * 2 * nP;
         for (int idx = tid; idx < 2 * nP; idx += 128) {
           const int half = idx / nP, rem = idx % nP;
-          float (*dv)[64] = half ? sv_.b : sv_.da;
+          float (*dv)[64] = half ? sv_.b : bv_.da;
           float s = 0.f;
           if (rem < nW) {
             const int q = rem / C, c = rem % C, qq = 4 * (q / r) + (q % r);
@@ -640,7 +655,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int col = f.col(n) + (e & 1), row = (e & 2) ? f.row_hi : f.row_lo;
-            x[4 * n + e] += (sv_.drho[2 * V][row] + sv_.dkap[2 * V][col]) * fast_rcp(den[4 * n + e] + p.eps);
+            x[4 * n + e] += (bv_.drho[2 * V][row] + bv_.dkap[2 * V][col]) * fast_rcp(den[4 * n + e] + p.eps);
           }
         frag_store_bf16(tile(SB::X + 0), f, x);
         ld_tile(kTR, den);
@@ -649,7 +664,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int col = f.col(n) + (e & 1), row = (e & 2) ? f.row_hi : f.row_lo;
-            x[4 * n + e] = (sv_.drho[2 * V + 1][row] + sv_.dkap[2 * V + 1][col]) * fast_rcp(den[4 * n + e] + p.eps);
+            x[4 * n + e] = (bv_.drho[2 * V + 1][row] + bv_.dkap[2 * V + 1][col]) * fast_rcp(den[4 * n + e] + p.eps);
           }
         frag_store_bf16(tile(SB::X + 2), f, x);
         for (int k = 0; k < V; ++k) {
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = f.col(n) + (e & 1), row = (e & 2) ? f.row_hi : f.row_lo;
-              x[4 * n + e] += sv_.drho[k][row] + sv_.dkap[k][col] + sv_.drho[V + k][col] + sv_.dkap[V + k][row];
+              x[4 * n + e] += bv_.drho[k][row] + bv_.dkap[k][col] + bv_.drho[V + k][col] + bv_.dkap[V + k][row];
             }
           st_tile(kTS + k, x);
         }
@@ -805,7 +820,7 @@ __global__ void __launch_bounds__(128, 1) edgewise_kernel(MopEdgewiseParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tbase);
+  if (warp == 0) tmem_dealloc<TmemCols<BWD>::value>(tbase);
 }
 
 inline bool supported(const MopEdgewiseParams* p) {

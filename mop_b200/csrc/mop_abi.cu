@@ -127,7 +127,7 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
       configured_dev = dev;
     }
     const int G = p->B * p->H, sms = sm_count();
-    const int grid = G < sms ? G : sms;
+    const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
     if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
     else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
