@@ -8,6 +8,7 @@
 #include "edgewise_tc.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
+#include "sdpa_tc.cuh"
 #include "tc_selftest.cuh"
 
 namespace mop {
@@ -181,17 +182,29 @@ extern "C" {
 
 size_t mop_sdpa_workspace_bytes(const MopSdpaParams* p, int backward) {
   if (check_sdpa(p, false) != MOP_OK) return 0;
-  return backward ? sdpa::bwd_workspace_floats(p) * sizeof(float) : 0;
+  if (!backward) return 0;
+  const size_t simt = sdpa::bwd_workspace_floats(p) * sizeof(float), tcn = (size_t)p->B * p->H * p->Nq * sizeof(float);
+  return simt > tcn ? simt : tcn;
 }
 
 int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
   int rc = check_sdpa(p, false);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
-  const size_t smem = sdpa::smem_bytes(p->dk);
+  const bool tc_ok = sdpatc::supported(p);
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
+              "impl %d not available (tcgen05 path: bf16, dk%%8==0, dk<=64, 16-byte aligned rows)", p->impl);
   const int grid = p->B * p->H * ((p->Nq + sdpa::TQ - 1) / sdpa::TQ);
   cudaStream_t st = (cudaStream_t)stream;
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t smem_tc = sizeof(sdpatc::SmemFwd) + 1024;
+    if ((rc = allow_smem(sdpatc::fwd_kernel, smem_tc))) return rc;
+    sdpatc::fwd_kernel<<<grid, 128, smem_tc, st>>>(*p);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
+  const size_t smem = sdpa::smem_bytes(p->dk);
   if (p->dtype == MOP_F32) {
     if ((rc = allow_smem(sdpa::fwd_kernel<float>, smem))) return rc;
     sdpa::fwd_kernel<float><<<grid, simt::kThreads, smem, st>>>(*p);
@@ -208,7 +221,25 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
   int rc = check_sdpa(p, true);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
+  const bool tc_ok = sdpatc::supported(p);
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
+              "impl %d not available (tcgen05 path: bf16, dk%%8==0, dk<=64, 16-byte aligned rows)", p->impl);
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t need_tc = (size_t)p->B * p->H * p->Nq * sizeof(float);
+    MOP_REQUIRE(p->workspace && p->workspace_bytes >= need_tc, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need_tc);
+    float* delta = reinterpret_cast<float*>(p->workspace);
+    cudaStream_t st2 = (cudaStream_t)stream;
+    const size_t smem_tc = sizeof(sdpatc::SmemBwd) + 1024;
+    if ((rc = allow_smem(sdpatc::bwd_dkdv_kernel, smem_tc))) return rc;
+    if ((rc = allow_smem(sdpatc::bwd_dq_kernel, smem_tc))) return rc;
+    const int rows = p->B * p->Nq * p->H;
+    sdpatc::delta_kernel<<<(rows + 7) / 8, 256, 0, st2>>>(*p, delta);
+    sdpatc::bwd_dkdv_kernel<<<p->B * p->H * ((p->Nk + 63) / 64), 128, smem_tc, st2>>>(*p, delta);
+    sdpatc::bwd_dq_kernel<<<p->B * p->H * ((p->Nq + 63) / 64), 128, smem_tc, st2>>>(*p, delta);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
   const size_t need = sdpa::bwd_workspace_floats(p) * sizeof(float);
   MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
   const size_t smem = sdpa::smem_bytes(p->dk);
