@@ -1,11 +1,13 @@
 // libmop_b200.so - C ABI entry points (see include/mop_b200.h).
 // Host side only validates, sizes scratch and enqueues kernels on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 #include "edgewise_simt.cuh"
 #include "edgewise_tc.cuh"
+#include "edgewise_tc_bwd2.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
 #include "sdpa_tc.cuh"
@@ -118,18 +120,21 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
   MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
               "impl %d not available for this shape (tcgen05 path: bf16, N=64, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4)", p->impl);
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024;
+    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
+    static const bool one_wg = getenv("MOP_EW_BWD_1WG") != nullptr;   // A/B switch: single-warpgroup backward
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOP_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b2));
       configured_dev = dev;
     }
     const int G = p->B * p->H, sms = sm_count();
     const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
-    if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
+    if (bwd && !one_wg) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
+    else if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
     else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
