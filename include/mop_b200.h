@@ -172,6 +172,11 @@ int mop_quartet_bwd(MopQuartetParams* p, void* cuda_stream);
 int mop_selftest_umma(const float* A, const float* B, float* D, float* D2, int a_mn, int b_mn, int lane_off,
                       int col_off, void* cuda_stream);
 
+/* Bring-up check of the M=128 building blocks (thread-per-row 32x32b TMEM access, chunk-major tiles with Ra / Rb
+ * rows): D[256 x Nn] = A[Ma x K] * B^T (b_mn = 0, B is [Nn x K]) or A * B[b_k0 : b_k0 + K, :] (b_mn = 1, B is [Kb x Nn]). */
+int mop_selftest_umma128(const float* A, const float* B, float* D, int Ma, int Nn, int K, int b_mn, int Ra, int Rb, int Kb,
+                         int b_k0, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 #include "edgewise_simt.cuh"
 #include "edgewise_tc.cuh"
 #include "edgewise_tc_bwd2.cuh"
+#include "edgewise_tc_large.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
 #include "sdpa_tc.cuh"
@@ -117,8 +118,25 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_ok = ewtc::supported(p);
-  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
-              "impl %d not available for this shape (tcgen05 path: bf16, N=64, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4)", p->impl);
+  const bool large_ok = !tc_ok && !bwd && ewl::supported(p);   // forward for token counts up to 200 (ViT-B/16: 196)
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && (tc_ok || large_ok)), MOP_EUNSUPPORTED,
+              "impl %d not available for this shape (tcgen05 path: bf16, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4; "
+              "N=64 forward+backward, N<=200 forward)", p->impl);
+  if (large_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t smem = sizeof(ewl::Smem) + 128;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MOP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    const int G = p->B * p->H, sms = sm_count();
+    ewl::edgewise_fwd_kernel<<<G < sms ? G : sms, 256, smem, st>>>(*p);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
     const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
     static const bool one_wg = getenv("MOP_EW_BWD_1WG") != nullptr;   // A/B switch: single-warpgroup backward
@@ -334,6 +352,19 @@ int mop_quartet_bwd(MopQuartetParams* p, void* stream) { return quartet_launch(p
 // ---------------------------------------------------------------------------
 // tcgen05 primitive self-test (tests/test_gpu_tc_primitives.py)
 // ---------------------------------------------------------------------------
+extern "C" int mop_selftest_umma128(const float* A, const float* B, float* D, int Ma, int Nn, int K, int b_mn, int Ra, int Rb,
+                                    int Kb, int b_k0, void* stream) {
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");
+  MOP_REQUIRE(Ma > 0 && Ma <= 256 && Nn % 16 == 0 && Nn >= 16 && Nn <= 256 && K % 16 == 0 && K > 0 && Ra % 8 == 0 && Rb % 8 == 0, MOP_EINVAL,
+              "bad selftest shape");
+  const size_t smem = (size_t)Ra * 16 * (K / 8) + (size_t)Rb * 16 * ((b_mn ? Nn : K) / 8) + 4096;   // slack: M-row over-read
+  MOP_REQUIRE(smem <= 227 * 1024, MOP_EINVAL, "selftest tiles do not fit in shared memory");
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(tc::selftest128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::selftest128_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(A, B, D, Ma, Nn, K, b_mn, Ra, Rb, Kb, b_k0);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 extern "C" int mop_selftest_umma(const float* A, const float* B, float* D, float* D2, int a_mn, int b_mn, int lane_off,
                                  int col_off, void* stream) {
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");

@@ -205,3 +205,38 @@ def test_tcgen05_backward_vs_oracle_and_simt(B, H, dk, V, r):
         worst[k] = (rel_to_max(g_tc[k].reshape(ref.shape), ref), rel_to_max(g_simt[k].reshape(ref.shape), ref))
     bad = {k: v for k, v in worst.items() if v[0] > BF16_TOL}
     assert not bad, f"tcgen05 grads off (tc_err, simt_err): {worst}"
+
+
+LARGE_CASES = [
+    # B, H, N, dk, V, r  (edgewise_tc_large.cuh: thread-per-row M=128 kernel, N <= 200)
+    (1, 2, 196, 64, 5, 4),     # ViT-B/16 core shape
+    (2, 1, 100, 56, 3, 2),     # one row block, ragged
+    (1, 3, 130, 32, 2, 1),     # second row block almost empty
+    (1, 1, 200, 64, 4, 3),     # maximum
+    (3, 2, 17, 16, 5, 4),      # tiny
+    (150, 1, 80, 24, 2, 4),    # more problems than SMs: persistent loop reuses tiles / TMEM / barriers
+]
+
+
+@pytest.mark.parametrize("B,H,N,dk,V,r", LARGE_CASES)
+def test_tcgen05_large_forward_vs_oracle_and_simt(B, H, N, dk, V, r):
+    """Fused tcgen05 forward for N <= 200 against the fp64 oracle (same bf16 inputs) and the SIMT kernel."""
+    from mop_b200 import functional as MF
+    from mop_b200 import edgewise_attention
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, True, "lowrank", False, r, seed=7 * N + V)
+    qkv = bf16_round(qkv)
+    dev = "cuda"
+    args = (qkv.to(dev, torch.bfloat16), *[s.to(dev, torch.float32) for s in scales], logit.to(dev, torch.float32),
+            {k: v.to(dev, torch.float32) for k, v in head.items()})
+    kw = dict(n_views=V, beta_not=0.5, gate_mode="lowrank", gate_rank=r)
+    with torch.no_grad():
+        y_tc = edgewise_attention(*args, impl="tcgen05", **kw)
+        assert MF.last_impl["edgewise_fwd"] == "tcgen05"
+        y_simt = edgewise_attention(*args, impl="simt", **kw)
+        assert MF.last_impl["edgewise_fwd"] == "simt"
+    torch.cuda.synchronize()
+    assert torch.isfinite(y_tc.float()).all()
+    assert rel_to_max(y_tc, y_simt) <= BF16_TOL
+    if B * H <= 8:
+        y_ref, _ = _oracle(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5)
+        assert rel_to_max(y_tc, y_ref) <= BF16_TOL
