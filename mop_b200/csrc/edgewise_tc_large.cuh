@@ -9,10 +9,12 @@
 //       A  (86.5 KB)  the current per-view softmax A_k  (B operand of the chain products, K = its rows)
 //       X  (83.2 KB)  the running chain product (A operand; row block w is rewritten in place by warpgroup w)
 //       Q  (25.6 KB)  unscaled queries (A operand),  K (26.6 KB)  keys scaled by q_scale*k_scale/sqrt(dk) per view
-//     which is all of the 227 KB; no N x N map ever reaches HBM;
+//     which is all of the 227 KB;
 //   * pass R (views V-1..0):  S_k = Q Ks_k^T -> softmax -> A_k ;  Y <- Y A_k        -> R = A_{V-1}..A_0
-//     pass F (views 0..V-1):  S_k, A_k recomputed            ;  X <- X A_k        -> F = A_0..A_{V-1} (stays in X)
-//     Only the row / column means of S_k, log(F+eps), log(R+eps) leave the passes (gate features);
+//     pass F (views 1..V-1):  A_k comes back by bulk copy      ;  X <- X A_k        -> F = A_0..A_{V-1} (stays in X)
+//     Between the passes the bf16 A_k wait in a per-CTA scratch slot of the caller's workspace (V x 86.5 KB per
+//     CTA, 64 MB for 148 CTAs: L2 resident; moved by cp.async.bulk in both directions).  Only the row / column
+//     means of S_k, log(F+eps), log(R+eps) leave the passes (gate features);
 //   * final stage, flash style over 32-column panels: the V score panels are recomputed into TMEM, mixed with
 //     the rank-r gates in registers (AND sum, OR log-sum-exp, NOT, chain log F from X), online softmax,
 //     P V_1 accumulated in TMEM; y = (P V_1)/l + F (w V_V).
@@ -57,6 +59,7 @@ struct __align__(128) Smem {
   float cvec[kMaxV][64];           // q_scale*k_scale/sqrt(dk) per view
   float vs1[64], vsL[64];          // v_scale[0], sigmoid(chain_value_logit) * v_scale[V-1]
   uint64_t bar[2];                 // MMA completion, one per warpgroup
+  uint64_t ldbar;                  // bulk load of a spilled map into A
   uint32_t tmem_slot;
 };
 // final-stage aliases inside A (dead once the chain passes are done)
@@ -97,28 +100,41 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane, int* co
   return s;
 }
 
+// 16 fp32 -> 2 x (8 bf16), optionally scaled
+__device__ __forceinline__ void pack16(const float* v, float sc, uint4& lo, uint4& hi) {
+  lo.x = pack_bf16(v[0] * sc, v[1] * sc); lo.y = pack_bf16(v[2] * sc, v[3] * sc);
+  lo.z = pack_bf16(v[4] * sc, v[5] * sc); lo.w = pack_bf16(v[6] * sc, v[7] * sc);
+  hi.x = pack_bf16(v[8] * sc, v[9] * sc); hi.y = pack_bf16(v[10] * sc, v[11] * sc);
+  hi.z = pack_bf16(v[12] * sc, v[13] * sc); hi.w = pack_bf16(v[14] * sc, v[15] * sc);
+}
+
+constexpr int kSpillThread = 255;   // a lane of the warp that never owns a valid row (N <= 200 < 224): drives the bulk copies
+
 __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;
   const int N = p.N, V = p.V, r = p.gate_rank, C = 2 * V + 2, dk = p.dk, H = p.H;
   const int KS = (N + 15) >> 4, NN = KS * 16;   // MMA k-steps over tokens; padded token count
+  const int cfull = N >> 4;                     // column chunks of 16 without padding
   const int dks = (dk + 15) >> 4;
   const int row = 128 * wg + t;
   const bool row_ok = row < N;
   const bool blk_on = 128 * wg < N;                   // this warpgroup owns rows
   const bool warp_on = 128 * wg + 32 * warp4 < N;     // this warp owns at least one valid row
   const float invN = 1.f / (float)N;
+  const uint32_t map_bytes = (uint32_t)(2 * KS) * (kRA * 16);   // the chunks of A that hold data
+  unsigned char* spill = reinterpret_cast<unsigned char*>(p.workspace) + (size_t)blockIdx.x * kMaxV * kBufA;
 
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.ldbar, 1); fence_mbar_init(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = sm.tmem_slot;
   const uint32_t tD = tbase + 256u * (uint32_t)wg;                      // accumulator of this warpgroup (MMA address)
   const uint32_t tl = tD + ((uint32_t)(32 * warp4) << 16);              // the same, this warp's lane window
-  uint32_t phase = 0;
+  uint32_t phase = 0, ldphase = 0;
   const float w = 1.f / (1.f + __expf(-p.chain_value_logit[0]));
   const float bn = p.beta_not / (float)max(1, V - 1);
   const float sscale = rsqrtf((float)dk);
@@ -127,6 +143,40 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
   auto mma_wait = [&]() { mbar_wait(&sm.bar[wg], phase); phase ^= 1; tc_fence_after(); };
   auto publish_cta = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
   auto publish_wg = [&]() { fence_async_smem(); tc_fence_before(); wg_sync(wg); tc_fence_after(); };
+  // D = X[row block] A  (A: the map in the A buffer, K index = its rows)
+  auto chain_mma = [&]() {
+    const uint32_t id = idesc_bf16(128, NN, 0, 1);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_mnmajor(sA, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+    mma_commit(&sm.bar[wg]);
+  };
+  // accumulator -> bf16 row of X (STORE) and / or row + column sums of log(D + eps) (LOGS)
+  auto chain_epilogue = [&](bool store, bool logs, int slot, float& rowmean) {
+    float ls = 0.f;
+    for (int c = 0; c < KS; ++c) {
+      float v[16];
+      tmem_ld_32x32b_x16(tl + 16 * c, v);
+      tmem_ld_wait();
+      if (store && row < kRX) {
+        uint4 lo, hi;
+        pack16(v, 1.f, lo, hi);
+        *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
+        *reinterpret_cast<uint4*>(sm.X + (2 * c + 1) * (kRX * 16) + row * 16) = hi;
+      }
+      if (logs) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const bool ok = row_ok && 16 * c + e < N;
+          v[e] = ok ? kLn2 * fast_log2(v[e] + p.eps) : 0.f;
+          ls += v[e];
+        }
+        int col;
+        const float cs = warp_colsum16(v, lane, &col);
+        if ((lane & 1) == 0) atomicAdd(&sm.colsum[slot][16 * c + col], cs);
+      }
+    }
+    if (logs) rowmean = ls * invN;
+  };
 
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
   const size_t hd = (size_t)H * dk;
@@ -135,7 +185,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
     const int pb = g / H, ph = g % H;
     auto in_row = [&](int n) { return qkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };   // q; +hd: k; +2hd: v
     // =================================================================================================
-    // stage 0: per-view scale vectors, unscaled Q tile, zeroed column sums
+    // stage 0: per-view scale vectors, unscaled Q tile, this thread's key row (registers), zeroed column sums
     // =================================================================================================
     for (int idx = tid; idx < V * 64; idx += 256) {
       const int i = idx >> 6, d = idx & 63;
@@ -151,35 +201,35 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
       sm.vsL[d] = w * b;
     }
     for (int idx = tid; idx < (kMaxV + 2) * kNmax; idx += 256) (&sm.colsum[0][0])[idx] = 0.f;
-    if (tid < kRX) {
+    uint4 kraw[8];
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (tid < N && ch * 8 < dk) q = *reinterpret_cast<const uint4*>(in_row(tid) + ch * 8);
-        *reinterpret_cast<uint4*>(sm.Q + ch * (kRX * 16) + tid * 16) = q;
+    for (int ch = 0; ch < 8; ++ch) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      kraw[ch] = q;
+      if (tid < N && ch * 8 < dk) {
+        q = *reinterpret_cast<const uint4*>(in_row(tid) + ch * 8);
+        kraw[ch] = *reinterpret_cast<const uint4*>(in_row(tid) + hd + ch * 8);
       }
+      if (tid < kRX) *reinterpret_cast<uint4*>(sm.Q + ch * (kRX * 16) + tid * 16) = q;
     }
     __syncthreads();
     float rho[kMaxV], rhoF = 0.f, rhoR = 0.f;   // row means of S_k, log F, log R of this thread's row
 #pragma unroll
     for (int i = 0; i < kMaxV; ++i) rho[i] = 0.f;
     // =================================================================================================
-    // chain passes
+    // pass R (views V-1 .. 0): A_k = softmax(S_k) (spilled to the L2-resident scratch), Y <- Y A_k
     // =================================================================================================
-    for (int step = 0; step < 2 * V; ++step) {
-      const int pass = step / V, idx = step % V;
-      const int k = pass == 0 ? V - 1 - idx : idx;
+    for (int idx = 0; idx < V; ++idx) {
+      const int k = V - 1 - idx;
       const bool first = idx == 0, last = idx == V - 1;
-      // ---- scaled keys of view k (every S_{k'} MMA and every chain MMA issued so far has completed: each
-      //      thread waited for its warpgroup's MMAs before the last CTA barrier)
+      // scaled keys of view k (every MMA issued so far has completed: each thread waited for its warpgroup's
+      // MMAs before the last CTA barrier)
       if (tid < kRA) {
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 kk = make_uint4(0, 0, 0, 0);
-          if (tid < N && ch * 8 < dk) kk = scale_chunk(*reinterpret_cast<const uint4*>(in_row(tid) + hd + ch * 8), &sm.cvec[k][ch * 8]);
-          *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = kk;
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = scale_chunk(kraw[ch], &sm.cvec[k][ch * 8]);
       }
+      if (tid == kSpillThread && !first) bulk_wait_read();   // the spill of A_{k+1} has left the A buffer
       publish_cta();
       if (blk_on) {
         if (t == 0) {
@@ -190,55 +240,56 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
         }
         mma_wait();
       }
-      // ---- row softmax of S_k (thread per row); pass R also collects the row / column means of S_k
-      float inv_l = 0.f;
+      // ---- row softmax of S_k, thread per row; row / column sums of S_k for the gate features
       if (warp_on) {
         float mx = -INFINITY, rs = 0.f;
         for (int c = 0; c < KS; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
+          if (c < cfull) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool ok = 16 * c + e < N;
-            if (ok) { mx = fmaxf(mx, v[e]); rs += v[e]; }
-            v[e] = (ok && row_ok) ? v[e] : 0.f;
-          }
-          if (pass == 0) {
-            int col;
-            const float cs = warp_colsum16(v, lane, &col);
-            if ((lane & 1) == 0) atomicAdd(&sm.colsum[k][16 * c + col], cs);
-          }
-        }
-        if (pass == 0) {
+            for (int e = 0; e < 16; ++e) { mx = fmaxf(mx, v[e]); rs += v[e]; }
+          } else {
 #pragma unroll
-          for (int i = 0; i < kMaxV; ++i)
-            if (i == k) rho[i] = rs * invN;
+            for (int e = 0; e < 16; ++e) {
+              if (16 * c + e < N) { mx = fmaxf(mx, v[e]); rs += v[e]; } else v[e] = 0.f;
+            }
+          }
+          if (!row_ok) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          }
+          int col;
+          const float cs = warp_colsum16(v, lane, &col);
+          if ((lane & 1) == 0) atomicAdd(&sm.colsum[k][16 * c + col], cs);
         }
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i)
+          if (i == k) rho[i] = rs * invN;
         float l = 0.f;
         const float mb = mx * kLog2e;
         for (int c = 0; c < KS; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
+          if (c < cfull) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            v[e] = (16 * c + e < N) ? fast_exp2(fmaf(v[e], kLog2e, -mb)) : 0.f;
-            l += v[e];
+            for (int e = 0; e < 16; ++e) { v[e] = fast_exp2(fmaf(v[e], kLog2e, -mb)); l += v[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = (16 * c + e < N) ? fast_exp2(fmaf(v[e], kLog2e, -mb)) : 0.f; l += v[e]; }
           }
           tmem_st_32x32b_x16(tl + 16 * c, v);
         }
         tmem_st_wait();
-        inv_l = row_ok ? 1.f / l : 0.f;   // padded rows become zero rows of A_k
+        const float inv_l = row_ok ? 1.f / l : 0.f;   // padded rows become zero rows of A_k
         for (int c = 0; c < KS; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
           uint4 lo, hi;
-          lo.x = pack_bf16(v[0] * inv_l, v[1] * inv_l); lo.y = pack_bf16(v[2] * inv_l, v[3] * inv_l);
-          lo.z = pack_bf16(v[4] * inv_l, v[5] * inv_l); lo.w = pack_bf16(v[6] * inv_l, v[7] * inv_l);
-          hi.x = pack_bf16(v[8] * inv_l, v[9] * inv_l); hi.y = pack_bf16(v[10] * inv_l, v[11] * inv_l);
-          hi.z = pack_bf16(v[12] * inv_l, v[13] * inv_l); hi.w = pack_bf16(v[14] * inv_l, v[15] * inv_l);
+          pack16(v, inv_l, lo, hi);
           if (row < kRA) {
             *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
             *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
@@ -253,52 +304,51 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
         for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
       }
       publish_cta();
+      if (tid == kSpillThread && k >= 1) bulk_s2g(spill + (size_t)k * kBufA, sm.A, map_bytes);
       if (first) continue;
-      // ---- chain product: D = X[row block] A_k
       if (blk_on) {
-        if (t == 0) {
-          const uint32_t id = idesc_bf16(128, NN, 0, 1);
-          for (int ks = 0; ks < KS; ++ks)
-            mma_ss(tD, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_mnmajor(sA, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
-          mma_commit(&sm.bar[wg]);
-        }
+        if (t == 0) chain_mma();
         mma_wait();
       }
-      if (warp_on) {
-        const bool store = !(last && pass == 0);   // R itself is never needed again
-        float ls = 0.f;
-        for (int c = 0; c < KS; ++c) {
-          float v[16];
-          tmem_ld_32x32b_x16(tl + 16 * c, v);
-          tmem_ld_wait();
-          if (store && row < kRX) {
-            uint4 lo, hi;
-            lo.x = pack_bf16(v[0], v[1]); lo.y = pack_bf16(v[2], v[3]); lo.z = pack_bf16(v[4], v[5]); lo.w = pack_bf16(v[6], v[7]);
-            hi.x = pack_bf16(v[8], v[9]); hi.y = pack_bf16(v[10], v[11]); hi.z = pack_bf16(v[12], v[13]); hi.w = pack_bf16(v[14], v[15]);
-            *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
-            *reinterpret_cast<uint4*>(sm.X + (2 * c + 1) * (kRX * 16) + row * 16) = hi;
-          }
-          if (last) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const bool ok = row_ok && 16 * c + e < N;
-              v[e] = ok ? kLn2 * fast_log2(v[e] + p.eps) : 0.f;
-              ls += v[e];
-            }
-            int col;
-            const float cs = warp_colsum16(v, lane, &col);
-            if ((lane & 1) == 0) atomicAdd(&sm.colsum[V + (pass == 0 ? 1 : 0)][16 * c + col], cs);
-          }
-        }
-        if (last) { if (pass == 0) rhoR = ls * invN; else rhoF = ls * invN; }
+      if (warp_on) chain_epilogue(!last, last, V + 1, rhoR);   // R itself is never needed again
+      if (last && row < kRX) {
+        // X <- A_0: start of the forward chain (this warpgroup's MMA, the only reader of these X rows, is complete)
+        for (int c = 0; c < 2 * KS; ++c)
+          *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) =
+              row < kRA ? *reinterpret_cast<const uint4*>(sm.A + c * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0);
       }
-      // the next step's key tile / A_k writes are ordered behind this warpgroup's MMA wait + the CTA barrier
+    }
+    // =================================================================================================
+    // pass F (views 1 .. V-1): A_k comes back from the scratch, X <- X A_k; F stays in X
+    // =================================================================================================
+    publish_cta();   // X = A_0 visible to the MMAs; nobody reads the A buffer any more
+    if (tid == kSpillThread) {
+      bulk_wait_all();
+      mbar_expect_tx(&sm.ldbar, map_bytes);
+      bulk_g2s(sm.A, spill + (size_t)1 * kBufA, map_bytes, &sm.ldbar);
+    }
+    for (int k = 1; k < V; ++k) {
+      const bool last = k == V - 1;
+      if (blk_on) {
+        if (t == 0) { mbar_wait(&sm.ldbar, ldphase); chain_mma(); }
+        mma_wait();
+      }
+      ldphase ^= 1;
+      if (!last) {
+        tc_fence_before();
+        __syncthreads();   // both warpgroups' MMAs have read A_k: the next map may land while X is rewritten
+        if (tid == kSpillThread) {
+          mbar_expect_tx(&sm.ldbar, map_bytes);
+          bulk_g2s(sm.A, spill + (size_t)(k + 1) * kBufA, map_bytes, &sm.ldbar);
+        }
+      }
+      if (warp_on) chain_epilogue(true, last, V, rhoF);
+      if (!last) publish_cta();
     }
     // =================================================================================================
     // final stage
     // =================================================================================================
-    tc_fence_before();
-    __syncthreads();   // chain MMAs of both warpgroups are complete: A and K buffers are free, colsum is final
+    publish_cta();   // F complete in X; chain MMAs of both warpgroups are done: A and K buffers are free, colsum is final
     float* bfac = reinterpret_cast<float*>(sm.A + kOffBfac);
     unsigned char* Vt = sm.A + kOffVt;
     unsigned char* KsP = sm.A + kOffKsP + wg * (kMaxV * kKsP);
@@ -357,16 +407,25 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
     const uint32_t tlS = tl, tlO = tl + 160;          // this warp's lane window
     if (blk_on) {
       const int npanels = (N + kPanel - 1) / kPanel;
+      // raw key chunks of the next panel, prefetched while the current one is processed
+      uint4 raw[2];
+      auto fetch_panel = [&](int j0) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int item = t + 128 * it, jj = item & 31, ch = item >> 5, j = j0 + jj;
+          raw[it] = make_uint4(0, 0, 0, 0);
+          if (j < N && ch * 8 < dk) raw[it] = *reinterpret_cast<const uint4*>(in_row(j) + hd + ch * 8);
+        }
+      };
+      fetch_panel(0);
       for (int pn = 0; pn < npanels; ++pn) {
         const int j0 = pn * kPanel;
         // scaled key panels of the V views (the score MMAs of the previous panel have completed)
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-          const int item = t + 128 * it, jj = item & 31, ch = item >> 5, j = j0 + jj;
-          uint4 raw = make_uint4(0, 0, 0, 0);
-          if (j < N && ch * 8 < dk) raw = *reinterpret_cast<const uint4*>(in_row(j) + hd + ch * 8);
+          const int item = t + 128 * it, jj = item & 31, ch = item >> 5;
           for (int k = 0; k < V; ++k)
-            *reinterpret_cast<uint4*>(KsP + k * kKsP + ch * (kPanel * 16) + jj * 16) = scale_chunk(raw, &sm.cvec[k][ch * 8]);
+            *reinterpret_cast<uint4*>(KsP + k * kKsP + ch * (kPanel * 16) + jj * 16) = scale_chunk(raw[it], &sm.cvec[k][ch * 8]);
         }
         publish_wg();
         if (t == 0) {
@@ -376,11 +435,11 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
               mma_ss(tS + 32 * k, desc_kmajor(sQ + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(smem_u32(KsP) + k * kKsP, kPanel, 16 * ks), id, ks > 0 ? 1u : 0u);
           mma_commit(&sm.bar[wg]);
         }
+        if (pn + 1 < npanels) fetch_panel(j0 + kPanel);
         mma_wait();   // also covers the P V_1 MMA of the previous panel
-        float smix[kPanel];
-        float pmax = -INFINITY;
         if (warp_on) {
-#pragma unroll
+          float pmax = -INFINITY;
+#pragma unroll 1
           for (int sub = 0; sub < kPanel / 8; ++sub) {
             float sv[kMaxV][8];
 #pragma unroll
@@ -391,6 +450,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
             uint4 fraw = make_uint4(0, 0, 0, 0);
             if (row < kRX && jc < NN) fraw = *reinterpret_cast<const uint4*>(sm.X + (jc >> 3) * (kRX * 16) + row * 16);
             const uint32_t fw[4] = {fraw.x, fraw.y, fraw.z, fraw.w};
+            float val[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int j = jc + e;
@@ -406,7 +466,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
                 if (i < V) se += fast_exp2((sv[i][e] - mxv) * kLog2e);
               const float lse = mxv + kLn2 * fast_log2(se);
               const float U = sum - s0, O = lse - s0, lf = kLn2 * fast_log2(fval + p.eps);
-              float z[4] = {0.f, 0.f, 0.f, 0.f};
+              float z[4];
               const int jb = j < kNmax ? j : kNmax - 1;
               const float4* bp = reinterpret_cast<const float4*>(bfac + jb * 16);
 #pragma unroll
@@ -414,11 +474,13 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
                 const float4 b4 = bp[tg];
                 z[tg] = fmaf(afac[4 * tg], b4.x, fmaf(afac[4 * tg + 1], b4.y, fmaf(afac[4 * tg + 2], b4.z, afac[4 * tg + 3] * b4.w)));
               }
-              const float val = s0 + fast_sigmoid(z[0]) * U + fast_sigmoid(z[1]) * O - fast_sigmoid(z[2]) * bn * U + fast_sigmoid(z[3]) * lf;
-              smix[8 * sub + e] = (j < N && row_ok) ? val : -INFINITY;
-              pmax = fmaxf(pmax, smix[8 * sub + e]);
+              const float x = s0 + fast_sigmoid(z[0]) * U + fast_sigmoid(z[1]) * O - fast_sigmoid(z[2]) * bn * U + fast_sigmoid(z[3]) * lf;
+              val[e] = (j < N && row_ok) ? x : -INFINITY;
+              pmax = fmaxf(pmax, val[e]);
             }
+            tmem_st_32x32b_x8(tlS + 8 * sub, val);   // park the mixed scores in the (consumed) columns of S_0
           }
+          tmem_st_wait();
           // online softmax: rescale the running P V_1 accumulator when this row's maximum moved
           const float m_new = fmaxf(m_run, pmax);
           const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
@@ -439,6 +501,9 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
           }
           l_run *= sc;
           m_run = m_new;
+          float smix[kPanel];
+          tmem_ld_32x32b_x32(tlS, smix);
+          tmem_ld_wait();
           float ps = 0.f;
 #pragma unroll
           for (int e = 0; e < kPanel; ++e) {
@@ -518,6 +583,14 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
 inline bool supported(const MopEdgewiseParams* p) {
   return p->dtype == MOP_BF16 && p->N >= 1 && p->N <= kMaxTokens && p->dk <= 64 && p->dk % 8 == 0 && p->V >= 2 && p->V <= kMaxV &&
          p->Vp == 1 && p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr;
+}
+
+// one persistent CTA per SM (sizing without a device: B200)
+inline int grid_size(const MopEdgewiseParams* p) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const int G = p->B * p->H;
+  return G < sms ? G : sms;
 }
 
 }  // namespace ewl

@@ -108,6 +108,8 @@ size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
 
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {
   if (check_edgewise(p, false) != MOP_OK) return 0;
+  if (!backward && p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p))
+    return (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;   // per-CTA spill slots of the per-view softmax maps
   ew::Layout L = edgewise_layout(p, backward ? 1 : 0);
   return (size_t)edgewise_grid(p) * L.total * sizeof(float);
 }
@@ -131,8 +133,10 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured_dev = dev;
     }
-    const int G = p->B * p->H, sms = sm_count();
-    ewl::edgewise_fwd_kernel<<<G < sms ? G : sms, 256, smem, st>>>(*p);
+    const size_t need = (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;
+    MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+    MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, MOP_EINVAL, "workspace must be 16-byte aligned");
+    ewl::edgewise_fwd_kernel<<<ewl::grid_size(p), 256, smem, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
