@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 1
+#define MOP_ABI_VERSION 2
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -92,6 +92,11 @@ typedef struct MopEdgewiseParams {
   const float* mid3_b;  /* [hidden] */
   const float* conv2_w; /* [4,hidden]                                    :255 */
   const float* conv2_b; /* [4] */
+  float* row_stats;     /* [B,H,N,2] fp32, optional: per row of the mixed score map its (integer) base-2 reference exponent and
+                           the sum of the bf16-rounded probabilities.  Written by mop_edgewise_fwd when non-NULL; the
+                           tcgen05 backward for N != 64 needs it as an input */
+  float* y_base;        /* [B,N,H,dk] fp32, optional, same life cycle as row_stats: A V_1 (the output without the chain
+                           value term) in full precision, from which the backward forms rowsum(dA . A) */
   /* backward only */
   const void* dy;       /* [B,N,H,dk] `dtype` */
   void* dqkv;           /* [B,N,Vp,3,H,dk] `dtype`, fully overwritten */
@@ -105,6 +110,9 @@ typedef struct MopEdgewiseParams {
 } MopEdgewiseParams;
 
 size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);
+/* 1 if mop_edgewise_fwd with these params would run the kernel whose backward wants `row_stats` and `y_base`: allocate
+ * them, pass them to the forward and hand them back to the backward; 0 otherwise (both may be NULL) */
+int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p);
 /* bytes of workspace needed by mop_edgewise_fwd (backward=0) / mop_edgewise_bwd (backward=1) */
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward);
 int mop_edgewise_fwd(MopEdgewiseParams* p, void* cuda_stream);

@@ -31,7 +31,6 @@ using namespace tc;
 using ewtc::fast_exp2;
 using ewtc::fast_log2;
 using ewtc::fast_rcp;
-using ewtc::fast_sigmoid;
 using ewtc::kLn2;
 using ewtc::kLog2e;
 using ewtc::kMaxQ;
@@ -71,6 +70,11 @@ static_assert(kOffKsP + 2 * kMaxV * kKsP <= kBufA, "final-stage aliases overflow
 constexpr int kPt = 128 * 16 * (kPanel / 8);             // 8192
 static_assert(2 * kPt <= kKt, "P panels overflow the K tile");
 
+// sigmoid from ex2 + rcp (relative error ~1e-7).  tanh.approx (2^-11) is not enough here: the column-factor gradients of the
+// gate head are residuals of row sums of D g(1-g) that cancel to ~1 % of their terms, and forward and backward must use the
+// same gate values for the rows of D to sum to zero.
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.f + fast_exp2(-kLog2e * x)); }
+
 __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
 // column sums over the 32 rows of a warp: v[e] is this lane's value of column e (16 columns).  After the
@@ -101,6 +105,7 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane, int* co
 }
 
 // 16 fp32 -> 2 x (8 bf16), optionally scaled
+// (callers zero v[] for padded rows themselves: 0 * NaN would not be zero)
 __device__ __forceinline__ void pack16(const float* v, float sc, uint4& lo, uint4& hi) {
   lo.x = pack_bf16(v[0] * sc, v[1] * sc); lo.y = pack_bf16(v[2] * sc, v[3] * sc);
   lo.z = pack_bf16(v[4] * sc, v[5] * sc); lo.w = pack_bf16(v[6] * sc, v[7] * sc);
@@ -283,13 +288,14 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
           tmem_st_32x32b_x16(tl + 16 * c, v);
         }
         tmem_st_wait();
-        const float inv_l = row_ok ? 1.f / l : 0.f;   // padded rows become zero rows of A_k
+        const float inv_l = 1.f / l;
         for (int c = 0; c < KS; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
           uint4 lo, hi;
           pack16(v, inv_l, lo, hi);
+          if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);   // padded rows are zero rows of A_k
           if (row < kRA) {
             *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
             *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
@@ -481,10 +487,17 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
             tmem_st_32x32b_x8(tlS + 8 * sub, val);   // park the mixed scores in the (consumed) columns of S_0
           }
           tmem_st_wait();
-          // online softmax: rescale the running P V_1 accumulator when this row's maximum moved
-          const float m_new = fmaxf(m_run, pmax);
-          const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
-          const float sc = (m_run == -INFINITY) ? 0.f : fast_exp2(fmaf(m_run, kLog2e, -mb));
+          // online softmax in base 2 with an INTEGER reference exponent per row: rescaling by exact powers of two
+          // commutes with the bf16 rounding of P, and the row sum is taken over the ROUNDED probabilities, so that
+          // y_base = (sum_j P_ij V_1j) / l_i is exactly the softmax-weighted mean the backward differentiates
+          // (its D = A (dA - dY . y_base) then has zero row sums, which the gate-head gradients rely on).
+          const float m_new = fmaxf(m_run, ceilf(pmax * kLog2e));
+          const float mb = (m_new == -INFINITY) ? 0.f : m_new;
+          float sc = 0.f;
+          if (m_run != -INFINITY) {
+            const int diff = max((int)(m_run - m_new), -126);
+            sc = __int_as_float((127 + diff) << 23);
+          }
           const bool need = pn > 0 && m_new > m_run;
           if (__any_sync(0xffffffffu, need)) {
             const float scl = need ? sc : 1.f;
@@ -506,18 +519,16 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
           tmem_ld_wait();
           float ps = 0.f;
 #pragma unroll
-          for (int e = 0; e < kPanel; ++e) {
-            smix[e] = fast_exp2(fmaf(smix[e], kLog2e, -mb));   // exp2(-inf) = 0 for padded columns / rows
-            ps += smix[e];
+          for (int c = 0; c < kPanel / 8; ++c) {
+            uint32_t u[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              u[e2] = pack_bf16(fast_exp2(fmaf(smix[8 * c + 2 * e2], kLog2e, -mb)), fast_exp2(fmaf(smix[8 * c + 2 * e2 + 1], kLog2e, -mb)));
+              ps += __uint_as_float(u[e2] << 16) + __uint_as_float(u[e2] & 0xffff0000u);   // the rounded values (exp2(-inf) = 0)
+            }
+            *reinterpret_cast<uint4*>(Pt + c * (128 * 16) + t * 16) = make_uint4(u[0], u[1], u[2], u[3]);
           }
           l_run += ps;
-#pragma unroll
-          for (int c = 0; c < kPanel / 8; ++c) {
-            uint4 u;
-            u.x = pack_bf16(smix[8 * c], smix[8 * c + 1]); u.y = pack_bf16(smix[8 * c + 2], smix[8 * c + 3]);
-            u.z = pack_bf16(smix[8 * c + 4], smix[8 * c + 5]); u.w = pack_bf16(smix[8 * c + 6], smix[8 * c + 7]);
-            *reinterpret_cast<uint4*>(Pt + c * (128 * 16) + t * 16) = u;
-          }
         } else {
 #pragma unroll
           for (int c = 0; c < kPanel / 8; ++c) *reinterpret_cast<uint4*>(Pt + c * (128 * 16) + t * 16) = make_uint4(0, 0, 0, 0);
@@ -548,6 +559,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
       mma_wait();
       if (warp_on) {
         const float il = 1.f / l_run;
+        if (p.row_stats && row_ok) *reinterpret_cast<float2*>(p.row_stats + (((size_t)pb * H + ph) * N + row) * 2) = make_float2(m_run, l_run);
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((size_t)pb * N + row) * H + ph) * dk;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -560,6 +572,11 @@ __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams 
             for (int h8 = 0; h8 < 2; ++h8) {
               const int d0 = 16 * c + 8 * h8;
               if (d0 < dk) {
+                if (p.y_base) {
+                  float* yb = p.y_base + (((size_t)pb * N + row) * H + ph) * dk + d0;
+                  *reinterpret_cast<float4*>(yb) = make_float4(oa[8 * h8] * il, oa[8 * h8 + 1] * il, oa[8 * h8 + 2] * il, oa[8 * h8 + 3] * il);
+                  *reinterpret_cast<float4*>(yb + 4) = make_float4(oa[8 * h8 + 4] * il, oa[8 * h8 + 5] * il, oa[8 * h8 + 6] * il, oa[8 * h8 + 7] * il);
+                }
                 uint4 u;
                 u.x = pack_bf16(fmaf(oa[8 * h8 + 0], il, of[8 * h8 + 0]), fmaf(oa[8 * h8 + 1], il, of[8 * h8 + 1]));
                 u.y = pack_bf16(fmaf(oa[8 * h8 + 2], il, of[8 * h8 + 2]), fmaf(oa[8 * h8 + 3], il, of[8 * h8 + 3]));

@@ -1,0 +1,1007 @@
+// Edgewise (Mixture-of-Products) attention backward on tcgen05 / TMEM for token counts up to 200 (ViT-B/16: N = 196).
+//
+// Same execution model as the forward (edgewise_tc_large.cuh): one persistent CTA of 256 threads per SM, one
+// (batch, head) problem at a time, M=128 row blocks, one thread per row of every fp32 accumulator.  The backward
+// touches ~25 N x N maps per problem, far more than fits on chip, so every map that is needed again later is kept
+// as a bf16 tile image in a per-CTA scratch region of the caller's workspace (27 slots x 86.5 KB; written by the
+// owning threads or by cp.async.bulk, read back by cp.async.bulk straight into the operand buffer).  Nothing in
+// the scratch is shared between CTAs and nothing survives the launch.
+//
+// Phases per problem (executable specification: oracle/edgewise_manual.py):
+//   1  forward recompute: pass R and pass F of the forward, keeping A_k, the suffix products A_{V-1}..A_k, the
+//      prefix products A_0..A_k, F and R; gate factors a (registers) and b (shared);
+//   2  mixed-map backward, flash style over 32-column panels: score panels + dA = dY V_1^T panel by MMA, the mix is
+//      recomputed in registers, A = exp2(mix - lse) with the row statistics saved by the forward,
+//      D = A (dA - delta), delta = dY . (A V_1) with A V_1 in fp32 from the forward; keeps A, the four gate pre-activation gradients, the direct
+//      part of dS_k and D g_chain / (F + eps); the row-factor gradients da are fp32 register sums;
+//   3  column-factor gradients db = sum_t dG_t^T a (MMA), gate-head parameter partials, feature-mean gradients;
+//   4  value gradients dV = (A^T dY) vs_1 + (F^T dY) w vs_V, v_scale partials, chain_value_logit partial;
+//   5  chain seeds and sweeps.  For the F chain (k = V-1..1):  X' = X A_k^T,  dA_k = P_{k-1}^T X,
+//      C = A_k (dA_k - rowsum(dA_k A_k)); same for the R chain (k = 0..V-2) with the suffix products;
+//   6  every contribution C to dS_k (chain links, direct part + rank-1 feature terms) goes straight through
+//      T = C K, U = C^T Q and is accumulated into fp32 dQ / dK rows (softmax backward is linear, so the
+//      contributions never have to be summed as maps).
+#pragma once
+#include "edgewise_tc_large.cuh"
+
+namespace mop {
+namespace ewl {
+
+// scratch slots (kBufA bytes each)
+constexpr int kSlotA = 0;       // A_k, k = 0..4
+constexpr int kSlotSfx = 5;     // suffix product A_{V-1}..A_k for k = 1..3 at kSlotSfx + k - 1
+constexpr int kSlotR = 8;       // R = A_{V-1}..A_0
+constexpr int kSlotPfx = 9;     // prefix product A_0..A_k for k = 1..3 at kSlotPfx + k - 1
+constexpr int kSlotF = 12;      // F = A_0..A_{V-1}
+constexpr int kSlotAmix = 13;   // A = softmax(mix)
+constexpr int kSlotDG = 14;     // gate pre-activation gradients, 4 maps
+constexpr int kSlotDS = 18;     // direct part of dS_k, 5 maps
+constexpr int kSlotHf = 23;     // D g_chain / (F + eps)
+constexpr int kSlotXN = 24;     // next running product of a sweep (X tile image, kBufX bytes)
+constexpr int kSlotAcc = 25;    // fp32 dQ rows [208][64] (slot 25) and dK rows (slot 26)
+constexpr int kBwdSlots = 27;
+
+struct __align__(128) SmemBwd {
+  unsigned char X[kBufX];
+  unsigned char A[kBufA];
+  unsigned char Q[kQt];
+  unsigned char K[kKt];
+  float colsum[kMaxV + 2][kNmax];  // phase 1: column sums of S_k, log F, log R.  Phase 3 on: rows 0..4 = column part
+                                   // of the rank-1 feature gradient of S_k, row 5 / 6 = dkappa of log F / log R
+  float cvec[kMaxV][64];
+  float vs1[64], vsL[64];
+  float zsum[kMaxV][64];          // sum_n (dS_k K)[n,d] Q[n,d]
+  float vsum[2][64];              // sum_j dV_1[j,d] V[j,d], sum_j (F^T dY)[j,d] V[j,d]
+  float amean[kMaxQ];             // mean over tokens of the row gate factors a[q][.]
+  uint64_t bar[2];
+  uint64_t ldbar;
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(SmemBwd) <= 232448, "backward shared memory over the 227 KB limit");
+
+// phase-3 staging inside X: dY tile | a (bf16, one masked copy per gate) | da, db rows
+constexpr int kOffDy = 0;                          // kQt bytes (R = 200)
+constexpr int kAbf = kRA * 16 * 2;                 // 6656: [208 x 16] bf16
+constexpr int kOffAbf = kQt;                       // 4 x kAbf
+constexpr int kOffDab = kOffAbf + 4 * kAbf;        // float da[16][208], db[16][208]
+static_assert(kOffDab + 2 * 16 * kNmax * 4 <= kBufX, "phase-3 staging overflows the X buffer");
+
+// column sums over the 32 rows of a warp for 16 columns, added to dst[col] (shared memory)
+__device__ __forceinline__ void colsum16_to(float* dst, const float* v, int lane) {
+  int col;
+  const float cs = warp_colsum16(v, lane, &col);
+  if ((lane & 1) == 0) atomicAdd(dst + col, cs);
+}
+
+__device__ __forceinline__ void unpack8(uint4 u, float* f) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
+  const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;
+  const int N = p.N, V = p.V, r = p.gate_rank, C = 2 * V + 2, dk = p.dk, H = p.H;
+  const int KS = (N + 15) >> 4, NN = KS * 16;
+  const int cfull = N >> 4;
+  const int dks = (dk + 15) >> 4;
+  const int row = 128 * wg + t;
+  const bool row_ok = row < N;
+  const bool blk_on = 128 * wg < N;
+  const bool warp_on = 128 * wg + 32 * warp4 < N;
+  const float invN = 1.f / (float)N;
+  const uint32_t map_bytes = (uint32_t)(2 * KS) * (kRA * 16);
+  const uint32_t xmap_bytes = (uint32_t)(2 * KS) * (kRX * 16);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(p.workspace) + (size_t)blockIdx.x * kBwdSlots * kBufA;
+  auto slot = [&](int s) -> unsigned char* { return scratch + (size_t)s * kBufA; };
+
+  if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.ldbar, 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = sm.tmem_slot;
+  const uint32_t tD = tbase + 256u * (uint32_t)wg;
+  const uint32_t tl = tD + ((uint32_t)(32 * warp4) << 16);
+  uint32_t phase = 0, ldphase = 0;
+  const float w = 1.f / (1.f + __expf(-p.chain_value_logit[0]));
+  const float bn = p.beta_not / (float)max(1, V - 1);
+  const float sscale = rsqrtf((float)dk);
+  const uint32_t sX = smem_u32(sm.X), sA = smem_u32(sm.A), sQ = smem_u32(sm.Q), sK = smem_u32(sm.K);
+
+  auto mma_wait = [&]() { mbar_wait(&sm.bar[wg], phase); phase ^= 1; tc_fence_after(); };
+  auto commit = [&]() { mma_commit(&sm.bar[wg]); };
+  // generic-proxy writes (shared and global) -> visible to the async proxy (MMA operand reads, bulk copies); CTA barrier
+  auto publish_cta = [&]() { fence_async_all(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
+  auto publish_wg = [&]() { fence_async_smem(); tc_fence_before(); wg_sync(wg); tc_fence_after(); };
+  auto sync_cta = [&]() { tc_fence_before(); __syncthreads(); tc_fence_after(); };
+  // bulk load of a scratch map into the A buffer (or an X image into the X buffer); every thread waits
+  auto load_start = [&](void* dst, const void* src, uint32_t bytes) {
+    if (tid == kSpillThread) { mbar_expect_tx(&sm.ldbar, bytes); bulk_g2s(dst, src, bytes, &sm.ldbar); }
+  };
+  auto load_wait = [&]() { mbar_wait(&sm.ldbar, ldphase); ldphase ^= 1; };
+  // D[rows of this block, NN] = Xtile[rows] * (A buffer, K index = its rows)          (forward chain step)
+  auto mma_x_a = [&]() {
+    const uint32_t id = idesc_bf16(128, NN, 0, 1);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_mnmajor(sA, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+  };
+  // D[rows, m] = sum_j Xtile[rows, j] * Abuf[m, j]                                      (X A_k^T)
+  auto mma_x_at = [&]() {
+    const uint32_t id = idesc_bf16(128, NN, 0, 0);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(sA, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+  };
+  // D[m in this block, j] = sum_i Abuf[i, m] * Xtile[i, j]                              (P^T X)
+  auto mma_at_x = [&]() {
+    const uint32_t id = idesc_bf16(128, NN, 1, 1);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD, desc_mnmajor(sA + (16 * wg) * (kRA * 16), kRA, 16 * ks), desc_mnmajor(sX, kRX, 16 * ks), id, ks > 0 ? 1u : 0u);
+  };
+  // D[m in this block, 0..ncols) at column dcol = sum_i Abuf[i, m] * tile[i, :]         (map^T times a [tokens x n] tile)
+  auto mma_at_tile = [&](uint32_t dcol, uint32_t tile, uint32_t R, uint32_t ncols, bool acc) {
+    const uint32_t id = idesc_bf16(128, ncols, 1, 1);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD + dcol, desc_mnmajor(sA + (16 * wg) * (kRA * 16), kRA, 16 * ks), desc_mnmajor(tile, R, 16 * ks), id, (acc || ks > 0) ? 1u : 0u);
+  };
+  // D[rows of this block, 0..64) at column dcol = Abuf[rows, :] * tile (tile rows = tokens)
+  auto mma_a_tile = [&](uint32_t dcol, uint32_t tile, uint32_t R) {
+    const uint32_t id = idesc_bf16(128, 64, 0, 1);
+    for (int ks = 0; ks < KS; ++ks)
+      mma_ss(tD + dcol, desc_kmajor(sA + 128 * wg * 16, kRA, 16 * ks), desc_mnmajor(tile, R, 16 * ks), id, ks > 0 ? 1u : 0u);
+  };
+
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
+  __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(p.dqkv);
+  const size_t hd = (size_t)H * dk;
+  const int G = p.B * H;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int pb = g / H, ph = g % H;
+    auto in_row = [&](int n) { return qkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };
+    auto out_row = [&](int n) { return dqkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };
+    auto tok_row = [&](const void* base, int n) { return reinterpret_cast<const __nv_bfloat16*>(base) + (((size_t)pb * N + n) * H + ph) * dk; };
+    // row image of a scratch map (R = 208 layout): chunk c of this thread's row
+    auto map_chunk = [&](int s, int c) -> unsigned char* { return slot(s) + (size_t)c * (kRA * 16) + row * 16; };
+    // =================================================================================================
+    // stage 0
+    // =================================================================================================
+    for (int idx = tid; idx < V * 64; idx += 256) {
+      const int i = idx >> 6, d = idx & 63;
+      float c = 0.f;
+      if (d < dk) c = sscale * p.q_scale[((size_t)i * H + ph) * dk + d] * p.k_scale[((size_t)i * H + ph) * dk + d];
+      sm.cvec[i][d] = c;
+      sm.zsum[i][d] = 0.f;
+    }
+    if (tid < 64) {
+      const int d = tid;
+      float a = 0.f, b = 0.f;
+      if (d < dk) { a = p.v_scale[((size_t)0 * H + ph) * dk + d]; b = p.v_scale[((size_t)(V - 1) * H + ph) * dk + d]; }
+      sm.vs1[d] = a;
+      sm.vsL[d] = w * b;
+      sm.vsum[0][d] = 0.f;
+      sm.vsum[1][d] = 0.f;
+      if (d < kMaxQ) sm.amean[d] = 0.f;
+    }
+    for (int idx = tid; idx < (kMaxV + 2) * kNmax; idx += 256) (&sm.colsum[0][0])[idx] = 0.f;
+    uint4 kraw[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      kraw[ch] = q;
+      if (tid < N && ch * 8 < dk) {
+        q = *reinterpret_cast<const uint4*>(in_row(tid) + ch * 8);
+        kraw[ch] = *reinterpret_cast<const uint4*>(in_row(tid) + hd + ch * 8);
+      }
+      if (tid < kRX) *reinterpret_cast<uint4*>(sm.Q + ch * (kRX * 16) + tid * 16) = q;
+    }
+    __syncthreads();
+    float rho[kMaxV], rhoF = 0.f, rhoR = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) rho[i] = 0.f;
+    // accumulator -> bf16 row of X and / or of a scratch map, and / or log statistics
+    auto chain_epilogue = [&](bool store_x, int gslot, bool logs, int cslot, float& rowmean) {
+      float ls = 0.f;
+      for (int c = 0; c < KS; ++c) {
+        float v[16];
+        tmem_ld_32x32b_x16(tl + 16 * c, v);
+        tmem_ld_wait();
+        uint4 lo, hi;
+        pack16(v, 1.f, lo, hi);
+        if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
+        if (store_x && row < kRX) {
+          *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
+          *reinterpret_cast<uint4*>(sm.X + (2 * c + 1) * (kRX * 16) + row * 16) = hi;
+        }
+        if (gslot >= 0 && row < kRA) {
+          *reinterpret_cast<uint4*>(map_chunk(gslot, 2 * c)) = lo;
+          *reinterpret_cast<uint4*>(map_chunk(gslot, 2 * c + 1)) = hi;
+        }
+        if (logs) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const bool ok = row_ok && 16 * c + e < N;
+            v[e] = ok ? kLn2 * fast_log2(v[e] + p.eps) : 0.f;
+            ls += v[e];
+          }
+          colsum16_to(&sm.colsum[cslot][16 * c], v, lane);
+        }
+      }
+      if (logs) rowmean = ls * invN;
+    };
+    // =================================================================================================
+    // phase 1a: pass R (views V-1 .. 0)
+    // =================================================================================================
+    for (int idx = 0; idx < V; ++idx) {
+      const int k = V - 1 - idx;
+      const bool first = idx == 0, last = idx == V - 1;
+      if (tid < kRA) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = scale_chunk(kraw[ch], &sm.cvec[k][ch * 8]);
+      }
+      if (tid == kSpillThread && !first) bulk_wait_read();
+      publish_cta();
+      if (blk_on) {
+        if (t == 0) {
+          const uint32_t id = idesc_bf16(128, NN, 0, 0);
+          for (int ks = 0; ks < dks; ++ks)
+            mma_ss(tD, desc_kmajor(sQ + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(sK, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+          commit();
+        }
+        mma_wait();
+      }
+      if (warp_on) {
+        float mx = -INFINITY, rs = 0.f;
+        for (int c = 0; c < KS; ++c) {
+          float v[16];
+          tmem_ld_32x32b_x16(tl + 16 * c, v);
+          tmem_ld_wait();
+          if (c < cfull) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { mx = fmaxf(mx, v[e]); rs += v[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (16 * c + e < N) { mx = fmaxf(mx, v[e]); rs += v[e]; } else v[e] = 0.f;
+            }
+          }
+          if (!row_ok) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          }
+          colsum16_to(&sm.colsum[k][16 * c], v, lane);
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i)
+          if (i == k) rho[i] = rs * invN;
+        float l = 0.f;
+        const float mb = mx * kLog2e;
+        for (int c = 0; c < KS; ++c) {
+          float v[16];
+          tmem_ld_32x32b_x16(tl + 16 * c, v);
+          tmem_ld_wait();
+          if (c < cfull) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = fast_exp2(fmaf(v[e], kLog2e, -mb)); l += v[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = (16 * c + e < N) ? fast_exp2(fmaf(v[e], kLog2e, -mb)) : 0.f; l += v[e]; }
+          }
+          tmem_st_32x32b_x16(tl + 16 * c, v);
+        }
+        tmem_st_wait();
+        const float inv_l = 1.f / l;
+        for (int c = 0; c < KS; ++c) {
+          float v[16];
+          tmem_ld_32x32b_x16(tl + 16 * c, v);
+          tmem_ld_wait();
+          uint4 lo, hi;
+          pack16(v, inv_l, lo, hi);
+          if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
+          if (row < kRA) {
+            *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
+            *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
+          }
+          if (first && row < kRX) {
+            *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
+            *reinterpret_cast<uint4*>(sm.X + (2 * c + 1) * (kRX * 16) + row * 16) = hi;
+          }
+        }
+      } else if (row < kRA) {
+        for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
+      }
+      publish_cta();
+      if (tid == kSpillThread) bulk_s2g(slot(kSlotA + k), sm.A, map_bytes);
+      if (first) continue;
+      if (blk_on) {
+        if (t == 0) { mma_x_a(); commit(); }
+        mma_wait();
+      }
+      if (warp_on) chain_epilogue(!last, last ? kSlotR : kSlotSfx + k - 1, last, V + 1, rhoR);
+      if (last && row < kRX) {
+        for (int c = 0; c < 2 * KS; ++c)
+          *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) =
+              row < kRA ? *reinterpret_cast<const uint4*>(sm.A + c * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    // =================================================================================================
+    // phase 1b: pass F (views 1 .. V-1)
+    // =================================================================================================
+    publish_cta();
+    if (tid == kSpillThread) { bulk_wait_all(); fence_async_all(); }
+    load_start(sm.A, slot(kSlotA + 1), map_bytes);
+    for (int k = 1; k < V; ++k) {
+      const bool last = k == V - 1;
+      load_wait();
+      if (blk_on) {
+        if (t == 0) { mma_x_a(); commit(); }
+        mma_wait();
+      }
+      if (!last) {
+        sync_cta();
+        load_start(sm.A, slot(kSlotA + k + 1), map_bytes);
+      }
+      if (warp_on) chain_epilogue(true, last ? kSlotF : kSlotPfx + k - 1, last, V, rhoF);
+      if (!last) publish_cta();
+    }
+    publish_cta();   // F in X and in its slot; colsum final; A and K buffers free
+    // =================================================================================================
+    // gate factors; delta = dY . (y - F w V_V)
+    // =================================================================================================
+    float* bfac = reinterpret_cast<float*>(sm.A + kOffBfac);
+    unsigned char* Vt = sm.A + kOffVt;
+    unsigned char* KsP = sm.A + kOffKsP + wg * (kMaxV * kKsP);
+    auto load_values = [&](unsigned char* dst, const float* vscale) {
+      if (tid < kRA) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 vv = make_uint4(0, 0, 0, 0);
+          if (tid < N && ch * 8 < dk) vv = scale_chunk(*reinterpret_cast<const uint4*>(in_row(tid) + 2 * hd + ch * 8), &vscale[ch * 8]);
+          *reinterpret_cast<uint4*>(dst + ch * (kRA * 16) + tid * 16) = vv;
+        }
+      }
+    };
+    float afac[kMaxQ];
+    float fr[2 * kMaxV + 2], fc[2 * kMaxV + 2];
+    {
+#pragma unroll
+      for (int c = 0; c < kMaxV; ++c) {
+        const float kap = (c < V && row < kNmax) ? sm.colsum[c][row] * invN : 0.f;
+        fr[c] = rho[c]; fr[kMaxV + c] = kap;
+        fc[c] = kap;    fc[kMaxV + c] = rho[c];
+      }
+      const float kapF = row < kNmax ? sm.colsum[V][row] * invN : 0.f, kapR = row < kNmax ? sm.colsum[V + 1][row] * invN : 0.f;
+      fr[2 * kMaxV] = rhoF; fr[2 * kMaxV + 1] = rhoR;
+      fc[2 * kMaxV] = kapF; fc[2 * kMaxV + 1] = kapR;
+#pragma unroll
+      for (int qq = 0; qq < kMaxQ; ++qq) {
+        const int tg = qq >> 2, kk = qq & 3, q = tg * r + kk;
+        float a = 0.f, b = 0.f;
+        if (kk < r && row_ok) {
+          a = __ldg(p.row_b + q);
+          b = __ldg(p.col_b + q);
+#pragma unroll
+          for (int c = 0; c < kMaxV; ++c)
+            if (c < V) {
+              a = fmaf(__ldg(p.row_w + q * C + c), fr[c], a);
+              a = fmaf(__ldg(p.row_w + q * C + V + c), fr[kMaxV + c], a);
+              b = fmaf(__ldg(p.col_w + q * C + c), fc[c], b);
+              b = fmaf(__ldg(p.col_w + q * C + V + c), fc[kMaxV + c], b);
+            }
+          a = fmaf(__ldg(p.row_w + q * C + 2 * V), fr[2 * kMaxV], a);
+          a = fmaf(__ldg(p.row_w + q * C + 2 * V + 1), fr[2 * kMaxV + 1], a);
+          b = fmaf(__ldg(p.col_w + q * C + 2 * V), fc[2 * kMaxV], b);
+          b = fmaf(__ldg(p.col_w + q * C + 2 * V + 1), fc[2 * kMaxV + 1], b);
+        }
+        afac[qq] = a;
+        if (row < kNmax) bfac[row * 16 + qq] = b;
+        const float asum = warp_sum(a);   // a = 0 for padded rows
+        if (lane == 0 && asum != 0.f) atomicAdd(&sm.amean[qq], asum);
+      }
+    }
+    // exact (fp32) column sums of the four gate pre-activation gradients, accumulated in phase 2: [4][208] in the K region
+    float* cs_s = reinterpret_cast<float*>(sm.K);
+    for (int idx = tid; idx < 4 * kNmax; idx += 256) cs_s[idx] = 0.f;
+    publish_cta();
+    // delta = rowsum(dA . A) = dY . (A V_1), with A V_1 in fp32 from the forward
+    float delta = 0.f, lse2 = 0.f, inv_lmix = 0.f;
+    if (row_ok) {
+      const __nv_bfloat16* dyr = tok_row(p.dy, row);
+      const float* yb = p.y_base + (((size_t)pb * N + row) * H + ph) * dk;
+      for (int d0 = 0; d0 < dk; d0 += 8) {
+        float dv[8];
+        unpack8(*reinterpret_cast<const uint4*>(dyr + d0), dv);
+        const float4 y0 = *reinterpret_cast<const float4*>(yb + d0), y1 = *reinterpret_cast<const float4*>(yb + d0 + 4);
+        delta = fmaf(dv[0], y0.x, fmaf(dv[1], y0.y, fmaf(dv[2], y0.z, fmaf(dv[3], y0.w, delta))));
+        delta = fmaf(dv[4], y1.x, fmaf(dv[5], y1.y, fmaf(dv[6], y1.z, fmaf(dv[7], y1.w, delta))));
+      }
+      const float2 st2 = *reinterpret_cast<const float2*>(p.row_stats + (((size_t)pb * H + ph) * N + row) * 2);
+      lse2 = st2.x;          // integer reference exponent (base 2) of this row of the mixed map
+      inv_lmix = 1.f / st2.y;   // 1 / sum of the bf16-rounded exp2(mix - reference)
+    }
+    sync_cta();   // X (F) and the value tile are free
+    // dY tile (A operand of dA = dY V_1^T, B operand of the value-gradient MMAs), V_1 tile
+    unsigned char* dYt = sm.X + kOffDy;
+    if (tid < kRX) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tid < N && ch * 8 < dk) v = *reinterpret_cast<const uint4*>(tok_row(p.dy, tid) + ch * 8);
+        *reinterpret_cast<uint4*>(dYt + ch * (kRX * 16) + tid * 16) = v;
+      }
+    }
+    load_values(Vt, sm.vs1);
+    publish_cta();
+    // =================================================================================================
+    // phase 2: mixed-map backward over 32-column panels
+    // =================================================================================================
+    float da[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) da[q] = 0.f;
+    const uint32_t tS = tD, tdA = tD + 160;
+    const uint32_t tlS = tl, tldA = tl + 160;
+    if (blk_on) {
+      const int npanels = (N + kPanel - 1) / kPanel;
+      uint4 raw[2];
+      auto fetch_panel = [&](int j0) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int item = t + 128 * it, jj = item & 31, ch = item >> 5, j = j0 + jj;
+          raw[it] = make_uint4(0, 0, 0, 0);
+          if (j < N && ch * 8 < dk) raw[it] = *reinterpret_cast<const uint4*>(in_row(j) + hd + ch * 8);
+        }
+      };
+      fetch_panel(0);
+      for (int pn = 0; pn < npanels; ++pn) {
+        const int j0 = pn * kPanel;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int item = t + 128 * it, jj = item & 31, ch = item >> 5;
+          for (int k = 0; k < V; ++k)
+            *reinterpret_cast<uint4*>(KsP + k * kKsP + ch * (kPanel * 16) + jj * 16) = scale_chunk(raw[it], &sm.cvec[k][ch * 8]);
+        }
+        publish_wg();
+        if (t == 0) {
+          const uint32_t id = idesc_bf16(128, kPanel, 0, 0);
+          for (int k = 0; k < V; ++k)
+            for (int ks = 0; ks < dks; ++ks)
+              mma_ss(tS + 32 * k, desc_kmajor(sQ + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(smem_u32(KsP) + k * kKsP, kPanel, 16 * ks), id, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < dks; ++ks)   // dA panel = dY V_1[panel]^T
+            mma_ss(tdA, desc_kmajor(smem_u32(dYt) + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(smem_u32(Vt) + j0 * 16, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+          commit();
+        }
+        if (pn + 1 < npanels) fetch_panel(j0 + kPanel);
+        mma_wait();
+        if (warp_on) {
+#pragma unroll 1
+          for (int sub = 0; sub < kPanel / 8; ++sub) {
+            const int jc = j0 + 8 * sub;
+            if (jc >= NN) break;
+            float sv[kMaxV][8], dav[8];
+#pragma unroll
+            for (int i = 0; i < kMaxV; ++i)
+              if (i < V) tmem_ld_32x32b_x8(tlS + 32 * i + 8 * sub, sv[i]);
+            tmem_ld_32x32b_x8(tldA + 8 * sub, dav);
+            tmem_ld_wait();
+            if (!row_ok) {   // padded rows hold whatever the over-read operand rows produced: make them exact zeros
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                dav[e] = 0.f;
+#pragma unroll
+                for (int i = 0; i < kMaxV; ++i) sv[i][e] = 0.f;
+              }
+            }
+            float fv[8];
+            unpack8(row < kRA ? ldcg16(map_chunk(kSlotF, jc >> 3)) : make_uint4(0, 0, 0, 0), fv);
+            float o_am[8], o_hf[8], o_dg[4][8], o_ds[kMaxV][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = jc + e;
+              const bool ok = j < N && row_ok;
+              float s0 = sv[0][e], sum = s0, mxv = s0;
+#pragma unroll
+              for (int i = 1; i < kMaxV; ++i)
+                if (i < V) { sum += sv[i][e]; mxv = fmaxf(mxv, sv[i][e]); }
+              float ex[kMaxV], se = 0.f;
+#pragma unroll
+              for (int i = 0; i < kMaxV; ++i)
+                if (i < V) { ex[i] = fast_exp2((sv[i][e] - mxv) * kLog2e); se += ex[i]; }
+              const float inv_se = fast_rcp(se);
+              const float lse = mxv + kLn2 * fast_log2(se);
+              const float U = sum - s0, O = lse - s0;
+              const float fe = fv[e] + p.eps, lf = kLn2 * fast_log2(fe);
+              float z[4], bq[kMaxQ];
+              const float4* bp = reinterpret_cast<const float4*>(bfac + (j < kNmax ? j : kNmax - 1) * 16);
+#pragma unroll
+              for (int tg = 0; tg < 4; ++tg) {
+                const float4 b4 = bp[tg];
+                bq[4 * tg] = b4.x; bq[4 * tg + 1] = b4.y; bq[4 * tg + 2] = b4.z; bq[4 * tg + 3] = b4.w;
+                z[tg] = fmaf(afac[4 * tg], b4.x, fmaf(afac[4 * tg + 1], b4.y, fmaf(afac[4 * tg + 2], b4.z, afac[4 * tg + 3] * b4.w)));
+              }
+              const float g0 = fast_sigmoid(z[0]), g1 = fast_sigmoid(z[1]), g2 = fast_sigmoid(z[2]), g3 = fast_sigmoid(z[3]);
+              const float mixv = s0 + g0 * U + g1 * O - g2 * bn * U + g3 * lf;
+              const float am = ok ? __bfloat162float(__float2bfloat16_rn(fast_exp2(fmaf(mixv, kLog2e, -lse2)))) * inv_lmix : 0.f;
+              const float d = ok ? am * (dav[e] - delta) : 0.f;
+              o_am[e] = am;
+              const float dg0 = d * U * g0 * (1.f - g0), dg1 = d * O * g1 * (1.f - g1), dg2 = -bn * d * U * g2 * (1.f - g2), dg3 = d * lf * g3 * (1.f - g3);
+              o_dg[0][e] = dg0; o_dg[1][e] = dg1; o_dg[2][e] = dg2; o_dg[3][e] = dg3;
+#pragma unroll
+              for (int q = 0; q < kMaxQ; ++q) {
+                const float dgq = (q >> 2) == 0 ? dg0 : (q >> 2) == 1 ? dg1 : (q >> 2) == 2 ? dg2 : dg3;
+                da[q] = fmaf(dgq, bq[q], da[q]);
+              }
+              o_hf[e] = d * g3 * fast_rcp(fe);
+              const float e1 = d * g1, e0 = d * (g0 - g2 * bn);
+#pragma unroll
+              for (int i = 0; i < kMaxV; ++i)
+                if (i < V) {
+                  const float pi = ex[i] * inv_se;
+                  o_ds[i][e] = (i == 0) ? (d - e1 + e1 * pi) : (e0 + e1 * pi);
+                }
+            }
+            {
+              // column sums over this warp's rows: gates (0,1) and (2,3) share one 16-column butterfly each
+              float pr[16];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { pr[e] = o_dg[0][e]; pr[8 + e] = o_dg[1][e]; }
+              int col;
+              float csum = warp_colsum16(pr, lane, &col);
+              if ((lane & 1) == 0) atomicAdd(&cs_s[(col >> 3) * kNmax + jc + (col & 7)], csum);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { pr[e] = o_dg[2][e]; pr[8 + e] = o_dg[3][e]; }
+              csum = warp_colsum16(pr, lane, &col);
+              if ((lane & 1) == 0) atomicAdd(&cs_s[(2 + (col >> 3)) * kNmax + jc + (col & 7)], csum);
+            }
+            if (row < kRA) {
+              const int ch = jc >> 3;
+              *reinterpret_cast<uint4*>(map_chunk(kSlotAmix, ch)) = pack8(o_am);
+              *reinterpret_cast<uint4*>(map_chunk(kSlotHf, ch)) = pack8(o_hf);
+#pragma unroll
+              for (int tg = 0; tg < 4; ++tg) *reinterpret_cast<uint4*>(map_chunk(kSlotDG + tg, ch)) = pack8(o_dg[tg]);
+#pragma unroll
+              for (int i = 0; i < kMaxV; ++i)
+                if (i < V) *reinterpret_cast<uint4*>(map_chunk(kSlotDS + i, ch)) = pack8(o_ds[i]);
+            }
+          }
+        }
+      }
+    }
+    sync_cta();   // phase-2 MMAs complete: A buffer (value tile, key panels, b factors) and the dY tile region are reusable
+    // =================================================================================================
+    // phase 3: db = sum_t dG_t^T a (MMA), head-parameter partials, feature-mean gradients
+    // =================================================================================================
+    float* da_s = reinterpret_cast<float*>(sm.X + kOffDab);          // [16][208]
+    float* db_s = da_s + 16 * kNmax;                                  // [16][208]
+    float* fr_s = reinterpret_cast<float*>(sm.K);                     // [12][208] row-projection features
+    float* fc_s = fr_s + (2 * kMaxV + 2) * kNmax;                     // [12][208] column-projection features
+    static_assert(2 * (2 * kMaxV + 2) * kNmax * 4 <= kKt, "feature staging overflows the K tile");
+    float csr[4];   // column sums of dG_t at column `row`
+#pragma unroll
+    for (int tg = 0; tg < 4; ++tg) csr[tg] = row < kNmax ? cs_s[tg * kNmax + row] : 0.f;
+    __syncthreads();   // cs read before the K region is reused for the feature staging
+    if (row < kNmax) {
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q) {
+        da_s[q * kNmax + row] = row_ok ? da[q] : 0.f;
+        // bf16 image of a, one copy per gate with the other gates' columns zeroed: [208 rows][16 cols], R = 208
+        // centred: db = mean(a) * colsum(dG_t) (exact, fp32) + dG_t^T (a - mean(a)) (MMA); the column sums of dG_t cancel
+        // heavily once summed over columns, which bf16-rounded operands would not reproduce
+        const __nv_bfloat16 av = __float2bfloat16_rn(row_ok ? afac[q] - sm.amean[q] * invN : 0.f);
+#pragma unroll
+        for (int tg = 0; tg < 4; ++tg)
+          *reinterpret_cast<__nv_bfloat16*>(sm.X + kOffAbf + tg * kAbf + tile_off(kRA, row, q)) = (q >> 2) == tg ? av : __float2bfloat16_rn(0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 2 * kMaxV + 2; ++c) { fr_s[c * kNmax + row] = row_ok ? fr[c] : 0.f; fc_s[c * kNmax + row] = row_ok ? fc[c] : 0.f; }
+    }
+    publish_cta();
+    for (int tg = 0; tg < 4; ++tg) {
+      load_start(sm.A, slot(kSlotDG + tg), map_bytes);
+      load_wait();
+      if (blk_on) {
+        if (t == 0) { mma_at_tile(0, sX + kOffAbf + tg * kAbf, kRA, 16, tg > 0); commit(); }
+        mma_wait();
+      }
+      sync_cta();   // both warpgroups' MMAs have read the map
+    }
+    float db[kMaxQ];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q) db[q] = 0.f;
+    if (warp_on) {
+      tmem_ld_32x32b_x16(tl, db);
+      tmem_ld_wait();
+    }
+    if (row < kNmax) {
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q) { db[q] = row_ok ? fmaf(sm.amean[q] * invN, csr[q >> 2], db[q]) : 0.f; db_s[q * kNmax + row] = db[q]; }
+    }
+    // feature-mean gradients of this thread's token (as a row i and as a column j)
+    float drho[2 * kMaxV + 2], dkap[2 * kMaxV + 2];
+#pragma unroll
+    for (int c = 0; c < 2 * kMaxV + 2; ++c) { drho[c] = 0.f; dkap[c] = 0.f; }
+    if (row_ok) {
+#pragma unroll
+      for (int qq = 0; qq < kMaxQ; ++qq) {
+        const int tg = qq >> 2, kk = qq & 3, q = tg * r + kk;
+        if (kk < r) {
+#pragma unroll
+          for (int c = 0; c < kMaxV; ++c)
+            if (c < V) {
+              drho[c] = fmaf(__ldg(p.row_w + q * C + c), da[qq], drho[c]);
+              drho[kMaxV + c] = fmaf(__ldg(p.row_w + q * C + V + c), da[qq], drho[kMaxV + c]);
+              dkap[c] = fmaf(__ldg(p.col_w + q * C + c), db[qq], dkap[c]);
+              dkap[kMaxV + c] = fmaf(__ldg(p.col_w + q * C + V + c), db[qq], dkap[kMaxV + c]);
+            }
+          drho[2 * kMaxV] = fmaf(__ldg(p.row_w + q * C + 2 * V), da[qq], drho[2 * kMaxV]);
+          drho[2 * kMaxV + 1] = fmaf(__ldg(p.row_w + q * C + 2 * V + 1), da[qq], drho[2 * kMaxV + 1]);
+          dkap[2 * kMaxV] = fmaf(__ldg(p.col_w + q * C + 2 * V), db[qq], dkap[2 * kMaxV]);
+          dkap[2 * kMaxV + 1] = fmaf(__ldg(p.col_w + q * C + 2 * V + 1), db[qq], dkap[2 * kMaxV + 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2 * kMaxV + 2; ++c) { drho[c] *= invN; dkap[c] *= invN; }
+    }
+    float* cprime_s = &sm.colsum[0][0];
+    float* dkapF_s = &sm.colsum[kMaxV][0];
+    float* dkapR_s = &sm.colsum[kMaxV + 1][0];
+    // dS_k[i,j] += rterm_k[i] + cprime_k[j]:  channel k is S_k, channel V+k is S_k^T (row/column roles swapped)
+    float rterm[kMaxV];
+#pragma unroll
+    for (int k = 0; k < kMaxV; ++k) {
+      rterm[k] = drho[k] + dkap[kMaxV + k];
+      if (row < kNmax) cprime_s[k * kNmax + row] = dkap[k] + drho[kMaxV + k];
+    }
+    const float drhoF = drho[2 * kMaxV], drhoR = drho[2 * kMaxV + 1];
+    if (row < kNmax) { dkapF_s[row] = dkap[2 * kMaxV]; dkapR_s[row] = dkap[2 * kMaxV + 1]; }
+    __syncthreads();
+    {
+      // gate-head parameter partials: row_w [4r][C], row_b [4r], col_w, col_b
+      const int nW = 4 * r * C, nP = nW + 4 * r;
+      float* dh = p.dhead_part + (size_t)g * 2 * nP;
+      for (int idx = tid; idx < 2 * nP; idx += 256) {
+        const int half = idx / nP, rem = idx % nP;
+        const float* dv = half ? db_s : da_s;
+        const float* ft = half ? fc_s : fr_s;
+        float s = 0.f;
+        if (rem < nW) {
+          const int q = rem / C, c = rem % C, qq = 4 * (q / r) + (q % r);
+          const int cc = c < V ? c : c < 2 * V ? kMaxV + (c - V) : 2 * kMaxV + (c - 2 * V);
+          for (int i = 0; i < N; ++i) s = fmaf(dv[qq * kNmax + i], ft[cc * kNmax + i], s);
+        } else {
+          const int q = rem - nW, qq = 4 * (q / r) + (q % r);
+          for (int i = 0; i < N; ++i) s += dv[qq * kNmax + i];
+        }
+        dh[idx] = s;
+      }
+    }
+    sync_cta();
+    // =================================================================================================
+    // phase 4: dV = (A^T dY) vs_1 + (F^T dY) w vs_V ; v_scale partials ; chain_value_logit partial
+    // =================================================================================================
+    load_start(sm.A, slot(kSlotAmix), map_bytes);
+    load_wait();
+    if (blk_on) {
+      if (t == 0) { mma_at_tile(0, smem_u32(dYt), kRX, 64, false); commit(); }
+      mma_wait();
+    }
+    sync_cta();
+    load_start(sm.A, slot(kSlotF), map_bytes);
+    load_wait();
+    if (blk_on) {
+      if (t == 0) { mma_at_tile(64, smem_u32(dYt), kRX, 64, false); commit(); }
+      mma_wait();
+      if (warp_on) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float d1[16], dl[16], p1[16], pl[16];
+          tmem_ld_32x32b_x16(tl + 16 * c, d1);
+          tmem_ld_32x32b_x16(tl + 64 + 16 * c, dl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int d0 = 16 * c + 8 * h8;
+            float vv[8], o[8];
+            unpack8((row_ok && d0 < dk) ? *reinterpret_cast<const uint4*>(in_row(row) + 2 * hd + d0) : make_uint4(0, 0, 0, 0), vv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float a1 = d1[8 * h8 + e], al = dl[8 * h8 + e];
+              o[e] = a1 * sm.vs1[d0 + e] + al * sm.vsL[d0 + e];
+              p1[8 * h8 + e] = row_ok ? a1 * vv[e] : 0.f;
+              pl[8 * h8 + e] = row_ok ? al * vv[e] : 0.f;
+            }
+            if (row_ok && d0 < dk) *reinterpret_cast<uint4*>(out_row(row) + 2 * hd + d0) = pack8(o);
+          }
+          colsum16_to(&sm.vsum[0][16 * c], p1, lane);
+          colsum16_to(&sm.vsum[1][16 * c], pl, lane);
+        }
+      }
+    }
+    sync_cta();
+    if (tid < 32) {
+      float s = 0.f;
+      for (int d = tid; d < dk; d += 32) s = fmaf(sm.vsL[d], sm.vsum[1][d], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (tid == 0) p.dlogit_part[g] = (1.f - w) * s;
+    }
+    if (p.dscale_part) {
+      float* ds = p.dscale_part + (size_t)g * 3 * V * dk + (size_t)2 * V * dk;
+      for (int idx = tid; idx < V * dk; idx += 256) {
+        const int k = idx / dk, d = idx % dk;
+        float val = 0.f;
+        if (k == 0) val = sm.vsum[0][d];
+        if (k == V - 1) val += w * sm.vsum[1][d];
+        ds[idx] = val;
+      }
+    }
+    // =================================================================================================
+    // phase 5 / 6: chain seeds, sweeps and contributions
+    // =================================================================================================
+    // value tile w V_V (B operand of the seed MMA) in the K region; later the unscaled key tile lives there
+    load_values(sm.K, sm.vsL);
+    publish_cta();
+    if (blk_on) {
+      if (t == 0) {   // dY (w V_V)^T -> [rows, NN]
+        const uint32_t id = idesc_bf16(128, NN, 0, 0);
+        for (int ks = 0; ks < dks; ++ks)
+          mma_ss(tD, desc_kmajor(smem_u32(dYt) + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(sK, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
+        commit();
+      }
+      mma_wait();
+    }
+    sync_cta();   // dY tile and value tile are dead: X may be overwritten, K region gets the unscaled keys
+    if (tid < kRA) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 kk = make_uint4(0, 0, 0, 0);
+        if (tid < N && ch * 8 < dk) kk = *reinterpret_cast<const uint4*>(in_row(tid) + hd + ch * 8);
+        *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = kk;
+      }
+    }
+    // seed of the F sweep: X = D g_chain/(F+eps) + dY (w V_V)^T + (drho_F[i] + dkap_F[j]) / (F + eps)
+    if (warp_on) {
+      for (int c = 0; c < KS; ++c) {
+        float v[16], f8[8], h8v[8];
+        tmem_ld_32x32b_x16(tl + 16 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          unpack8(row < kRA ? ldcg16(map_chunk(kSlotF, 2 * c + hh)) : make_uint4(0, 0, 0, 0), f8);
+          unpack8(row < kRA ? ldcg16(map_chunk(kSlotHf, 2 * c + hh)) : make_uint4(0, 0, 0, 0), h8v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = 16 * c + 8 * hh + e;
+            const float x = v[8 * hh + e] + h8v[e] + (drhoF + dkapF_s[j < kNmax ? j : 0]) * fast_rcp(f8[e] + p.eps);
+            v[8 * hh + e] = (row_ok && j < N) ? x : 0.f;
+          }
+        }
+        if (row < kRX) {
+          uint4 lo, hi;
+          pack16(v, 1.f, lo, hi);
+          *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
+          *reinterpret_cast<uint4*>(sm.X + (2 * c + 1) * (kRX * 16) + row * 16) = hi;
+        }
+      }
+    }
+    bool acc_started = false;   // dQ / dK rows in the scratch hold valid partial sums
+    float* dq_acc = reinterpret_cast<float*>(slot(kSlotAcc)) + (size_t)row * 64;
+    float* dk_acc = reinterpret_cast<float*>(slot(kSlotAcc + 1)) + (size_t)row * 64;
+    // C (bf16, all rows, in the A buffer) is one additive part of dS_k:  T = C K -> dQ, scale sums ; U = C^T Q -> dK
+    auto contribute = [&](int k) {
+      publish_cta();   // C rows written by their owners
+      if (blk_on) {
+        if (t == 0) {
+          mma_a_tile(0, sK, kRA);
+          mma_at_tile(64, sQ, kRX, 64, false);
+          commit();
+        }
+        mma_wait();
+        if (warp_on) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float tv[16], uv[16], zq[16];
+            tmem_ld_32x32b_x16(tl + 16 * c, tv);
+            tmem_ld_32x32b_x16(tl + 64 + 16 * c, uv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int d0 = 16 * c + 8 * h8;
+              float qv[8];
+              unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.Q + (d0 >> 3) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), qv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) zq[8 * h8 + e] = row_ok ? tv[8 * h8 + e] * qv[e] : 0.f;
+              if (row_ok && d0 < dk) {
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+                if (acc_started) {
+                  a0 = __ldcg(reinterpret_cast<const float4*>(dq_acc + d0)); a1 = __ldcg(reinterpret_cast<const float4*>(dq_acc + d0 + 4));
+                  b0 = __ldcg(reinterpret_cast<const float4*>(dk_acc + d0)); b1 = __ldcg(reinterpret_cast<const float4*>(dk_acc + d0 + 4));
+                }
+                const float* cv = &sm.cvec[k][d0];
+                a0.x = fmaf(tv[8 * h8 + 0], cv[0], a0.x); a0.y = fmaf(tv[8 * h8 + 1], cv[1], a0.y);
+                a0.z = fmaf(tv[8 * h8 + 2], cv[2], a0.z); a0.w = fmaf(tv[8 * h8 + 3], cv[3], a0.w);
+                a1.x = fmaf(tv[8 * h8 + 4], cv[4], a1.x); a1.y = fmaf(tv[8 * h8 + 5], cv[5], a1.y);
+                a1.z = fmaf(tv[8 * h8 + 6], cv[6], a1.z); a1.w = fmaf(tv[8 * h8 + 7], cv[7], a1.w);
+                b0.x = fmaf(uv[8 * h8 + 0], cv[0], b0.x); b0.y = fmaf(uv[8 * h8 + 1], cv[1], b0.y);
+                b0.z = fmaf(uv[8 * h8 + 2], cv[2], b0.z); b0.w = fmaf(uv[8 * h8 + 3], cv[3], b0.w);
+                b1.x = fmaf(uv[8 * h8 + 4], cv[4], b1.x); b1.y = fmaf(uv[8 * h8 + 5], cv[5], b1.y);
+                b1.z = fmaf(uv[8 * h8 + 6], cv[6], b1.z); b1.w = fmaf(uv[8 * h8 + 7], cv[7], b1.w);
+                *reinterpret_cast<float4*>(dq_acc + d0) = a0; *reinterpret_cast<float4*>(dq_acc + d0 + 4) = a1;
+                *reinterpret_cast<float4*>(dk_acc + d0) = b0; *reinterpret_cast<float4*>(dk_acc + d0 + 4) = b1;
+              }
+            }
+            colsum16_to(&sm.zsum[k][16 * c], zq, lane);
+          }
+        }
+      }
+      acc_started = true;
+      sync_cta();   // the A buffer may be refilled
+    };
+    // C[m,:] = Ak[m,:] * (x[m,:] - sum_j x[m,j] Ak[m,j]) for this thread's row m, x taken from the accumulator
+    // (from_tmem) or from the X tile; Ak from its scratch slot.  Written as bf16 into the A buffer.
+    auto softmax_bwd_row = [&](int aslot, bool from_tmem) {
+      if (!warp_on) {
+        if (row < kRA) for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
+        return;
+      }
+      float dot = 0.f;
+      for (int c = 0; c < KS; ++c) {
+        float v[16], a8[8];
+        if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
+          unpack8(row < kRA ? ldcg16(map_chunk(aslot, 2 * c + hh)) : make_uint4(0, 0, 0, 0), a8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dot = fmaf(v[8 * hh + e], a8[e], dot);
+        }
+      }
+      for (int c = 0; c < KS; ++c) {
+        float v[16], a8[8];
+        if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
+          unpack8(row < kRA ? ldcg16(map_chunk(aslot, 2 * c + hh)) : make_uint4(0, 0, 0, 0), a8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * hh + e] = row_ok ? a8[e] * (v[8 * hh + e] - dot) : 0.f;
+        }
+        if (row < kRA) {
+          uint4 lo, hi;
+          pack16(v, 1.f, lo, hi);
+          *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
+          *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
+        }
+      }
+    };
+    // one sweep: X holds the seed.  order[s] = view visited at step s (V-1 steps), pslot(s) = scratch slot of the
+    // partial product multiplying X from the left (transposed); last_view = view of the final link (dA += X).
+    auto sweep = [&](bool fchain) {
+      for (int s = 0; s < V - 1; ++s) {
+        const int k = fchain ? V - 1 - s : s;
+        int pslot;
+        if (fchain) pslot = (k - 1 == 0) ? kSlotA + 0 : kSlotPfx + (k - 1) - 1;                 // P_{k-1}
+        else pslot = (k + 1 == V - 1) ? kSlotA + V - 1 : kSlotSfx + (k + 1) - 1;               // A_{V-1}..A_{k+1}
+        publish_cta();   // X rows (seed or reloaded image) visible; A buffer free
+        load_start(sm.A, slot(kSlotA + k), map_bytes);
+        load_wait();
+        if (blk_on) {
+          if (t == 0) { mma_x_at(); commit(); }     // X' = X A_k^T
+          mma_wait();
+          if (warp_on) {
+            for (int c = 0; c < KS; ++c) {
+              float v[16];
+              tmem_ld_32x32b_x16(tl + 16 * c, v);
+              tmem_ld_wait();
+              if (row < kRX) {
+                uint4 lo, hi;
+                pack16(v, 1.f, lo, hi);
+                if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c) * (kRX * 16) + row * 16) = lo;
+                *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c + 1) * (kRX * 16) + row * 16) = hi;
+              }
+            }
+          }
+        }
+        sync_cta();      // both warpgroups' MMAs have read A_k
+        load_start(sm.A, slot(pslot), map_bytes);
+        load_wait();
+        if (blk_on) {
+          if (t == 0) { mma_at_x(); commit(); }     // dA_k part = P^T X
+          mma_wait();
+        }
+        sync_cta();      // A buffer (P) free: it receives C
+        softmax_bwd_row(kSlotA + k, true);
+        contribute(k);   // (publishes; leaves the A buffer free)
+        // X <- X'
+        publish_cta();   // X' rows in the scratch visible to the bulk copy; nobody reads X any more
+        load_start(sm.X, slot(kSlotXN), xmap_bytes);
+        load_wait();
+      }
+      // final link
+      const int kl = fchain ? 0 : V - 1;
+      sync_cta();
+      softmax_bwd_row(kSlotA + kl, false);
+      contribute(kl);
+    };
+    sweep(true);
+    // seed of the R sweep: X = (drho_R[i] + dkap_R[j]) / (R + eps)
+    if (row < kRX) {
+      for (int c = 0; c < 2 * KS; ++c) {
+        float r8[8];
+        unpack8(row < kRA ? ldcg16(map_chunk(kSlotR, c)) : make_uint4(0, 0, 0, 0), r8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = 8 * c + e;
+          r8[e] = (row_ok && j < N) ? (drhoR + dkapR_s[j < kNmax ? j : 0]) * fast_rcp(r8[e] + p.eps) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) = pack8(r8);
+      }
+    }
+    sweep(false);
+    // direct parts + rank-1 feature terms
+    for (int k = 0; k < V; ++k) {
+      load_start(sm.A, slot(kSlotDS + k), map_bytes);
+      load_wait();
+      if (row_ok) {
+        float rt = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i)
+          if (i == k) rt = rterm[i];
+        for (int c = 0; c < 2 * KS; ++c) {
+          float v8[8];
+          unsigned char* ptr = sm.A + c * (kRA * 16) + row * 16;
+          unpack8(*reinterpret_cast<const uint4*>(ptr), v8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * c + e;
+            v8[e] = j < N ? v8[e] + rt + cprime_s[k * kNmax + j] : 0.f;
+          }
+          *reinterpret_cast<uint4*>(ptr) = pack8(v8);
+        }
+      }
+      contribute(k);
+    }
+    // =================================================================================================
+    // outputs: dQ, dK rows; q/k scale partials
+    // =================================================================================================
+    if (row_ok) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c * 8 < dk) {
+          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(dq_acc + 8 * c)), a1 = __ldcg(reinterpret_cast<const float4*>(dq_acc + 8 * c + 4));
+          const float4 b0 = __ldcg(reinterpret_cast<const float4*>(dk_acc + 8 * c)), b1 = __ldcg(reinterpret_cast<const float4*>(dk_acc + 8 * c + 4));
+          const float qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, ka[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          *reinterpret_cast<uint4*>(out_row(row) + 8 * c) = pack8(qa);
+          *reinterpret_cast<uint4*>(out_row(row) + hd + 8 * c) = pack8(ka);
+        }
+      }
+    }
+    if (p.dscale_part) {
+      float* ds = p.dscale_part + (size_t)g * 3 * V * dk;
+      for (int idx = tid; idx < V * dk; idx += 256) {
+        const int k = idx / dk, d = idx % dk;
+        const float z = sscale * sm.zsum[k][d];
+        const size_t pi = ((size_t)k * H + ph) * dk + d;
+        ds[idx] = p.k_scale[pi] * z;
+        ds[(size_t)V * dk + idx] = p.q_scale[pi] * z;
+      }
+    }
+    sync_cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<512>(tbase);
+}
+
+inline bool supported_bwd(const MopEdgewiseParams* p) { return supported(p) && p->row_stats != nullptr && p->y_base != nullptr; }
+
+}  // namespace ewl
+}  // namespace mop

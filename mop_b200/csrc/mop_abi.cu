@@ -9,6 +9,7 @@
 #include "edgewise_tc.cuh"
 #include "edgewise_tc_bwd2.cuh"
 #include "edgewise_tc_large.cuh"
+#include "edgewise_tc_large_bwd.cuh"
 #include "quartet_simt.cuh"
 #include "sdpa_simt.cuh"
 #include "sdpa_tc.cuh"
@@ -106,10 +107,18 @@ size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
   return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3);
 }
 
+int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  return (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) ? 1 : 0;
+}
+
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {
   if (check_edgewise(p, false) != MOP_OK) return 0;
-  if (!backward && p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p))
-    return (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;   // per-CTA spill slots of the per-view softmax maps
+  if (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) {
+    // per-CTA scratch slots of bf16 map images (forward: the V per-view softmax maps; backward: see edgewise_tc_large_bwd.cuh)
+    if (!backward) return (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;
+    if (p->row_stats && p->y_base) return (size_t)ewl::grid_size(p) * ewl::kBwdSlots * ewl::kBufA;
+  }
   ew::Layout L = edgewise_layout(p, backward ? 1 : 0);
   return (size_t)edgewise_grid(p) * L.total * sizeof(float);
 }
@@ -120,23 +129,26 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_ok = ewtc::supported(p);
-  const bool large_ok = !tc_ok && !bwd && ewl::supported(p);   // forward for token counts up to 200 (ViT-B/16: 196)
+  // token counts up to 200 (ViT-B/16: 196); the backward needs the row statistics saved by the forward
+  const bool large_ok = !tc_ok && (bwd ? ewl::supported_bwd(p) : ewl::supported(p));
   MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && (tc_ok || large_ok)), MOP_EUNSUPPORTED,
               "impl %d not available for this shape (tcgen05 path: bf16, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4; "
               "N=64 forward+backward, N<=200 forward)", p->impl);
   if (large_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem = sizeof(ewl::Smem) + 128;
+    const size_t smem = sizeof(ewl::Smem) + 128, smem_b = sizeof(ewl::SmemBwd) + 128;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOP_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
       configured_dev = dev;
     }
-    const size_t need = (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;
+    const size_t need = (size_t)ewl::grid_size(p) * (bwd ? ewl::kBwdSlots : ewtc::kMaxV) * ewl::kBufA;
     MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
     MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, MOP_EINVAL, "workspace must be 16-byte aligned");
-    ewl::edgewise_fwd_kernel<<<ewl::grid_size(p), 256, smem, st>>>(*p);
+    if (bwd) ewl::edgewise_bwd_kernel<<<ewl::grid_size(p), 256, smem_b, st>>>(*p);
+    else ewl::edgewise_fwd_kernel<<<ewl::grid_size(p), 256, smem, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

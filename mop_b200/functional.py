@@ -122,6 +122,12 @@ class _Edgewise(torch.autograd.Function):
             p = _lib.new_params(_lib.EdgewiseParams)
             _fill_edgewise(p, qkv_c, scales, logit32, head32, cfg)
             p.y = _ptr(y)
+            # the tcgen05 kernels for N != 64 hand the row statistics of the mixed map and A V_1 (fp32) to their backward
+            stats = ybase = None
+            if lib.mop_edgewise_needs_row_stats(C.byref(p)) and any(ctx.needs_input_grad):
+                stats = torch.empty(B, H, N, 2, dtype=torch.float32, device=qkv_c.device)
+                ybase = torch.empty(B, N, H, dk, dtype=torch.float32, device=qkv_c.device)
+                p.row_stats, p.y_base = _ptr(stats), _ptr(ybase)
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 0)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv_c.device)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
@@ -134,7 +140,8 @@ class _Edgewise(torch.autograd.Function):
         ctx.head_shapes = [h.shape for h in head]
         ctx.in_dtypes = [None if t is None else t.dtype for t in (q_scale, k_scale, v_scale, logit, *head)]
         ctx.scale_shape = None if q_scale is None else q_scale.shape
-        ctx.save_for_backward(qkv_c, logit32, *(scales or ()), *head32)
+        ctx.has_stats = stats is not None
+        ctx.save_for_backward(qkv_c, logit32, *(scales or ()), *head32, *((ybase, stats) if stats is not None else ()))
         return y
 
     @staticmethod
@@ -142,6 +149,10 @@ class _Edgewise(torch.autograd.Function):
         lib = _lib.load()
         cfg = ctx.cfg
         saved = ctx.saved_tensors
+        ybase = stats = None
+        if ctx.has_stats:
+            ybase, stats = saved[-2], saved[-1]
+            saved = saved[:-2]
         qkv_c, logit32 = saved[0], saved[1]
         scales = tuple(saved[2:5]) if ctx.has_scales else None
         head32 = tuple(saved[5:] if ctx.has_scales else saved[2:])
@@ -153,8 +164,9 @@ class _Edgewise(torch.autograd.Function):
         with torch.cuda.device(dev):
             p = _lib.new_params(_lib.EdgewiseParams)
             _fill_edgewise(p, qkv_c, scales, logit32, head32, cfg)
-            y_dummy = dqkv  # forward output is not needed by the backward kernels
-            p.y = _ptr(y_dummy)
+            p.y = _ptr(dqkv)  # the forward output is not needed by the backward kernels
+            if stats is not None:
+                p.row_stats, p.y_base = _ptr(stats), _ptr(ybase)
             nhead = lib.mop_edgewise_head_param_count(C.byref(p))
             G = B * H
             dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev)
