@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         }
       };
       fetch_panel(0);
+      uint4 fnext = row < kRA ? ldcg16(map_chunk(kSlotF, 0)) : make_uint4(0, 0, 0, 0);
       for (int pn = 0; pn < npanels; ++pn) {
         const int j0 = pn * kPanel;
 #pragma unroll
@@ -500,7 +501,8 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
               }
             }
             float fv[8];
-            unpack8(row < kRA ? ldcg16(map_chunk(kSlotF, jc >> 3)) : make_uint4(0, 0, 0, 0), fv);
+            unpack8(fnext, fv);
+            if (jc + 8 < NN && row < kRA) fnext = ldcg16(map_chunk(kSlotF, (jc + 8) >> 3));   // next chunk of this row of F
             float o_am[8], o_hf[8], o_dg[4][8], o_ds[kMaxV][8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -768,14 +770,25 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
     }
     // seed of the F sweep: X = D g_chain/(F+eps) + dY (w V_V)^T + (drho_F[i] + dkap_F[j]) / (F + eps)
     if (warp_on) {
+      uint4 pf[2][2];   // [F | Hf][half] of the next 16 columns
+      auto fetch_fh = [&](int c) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          pf[0][hh] = (row < kRA && c < KS) ? ldcg16(map_chunk(kSlotF, 2 * c + hh)) : make_uint4(0, 0, 0, 0);
+          pf[1][hh] = (row < kRA && c < KS) ? ldcg16(map_chunk(kSlotHf, 2 * c + hh)) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      fetch_fh(0);
       for (int c = 0; c < KS; ++c) {
         float v[16], f8[8], h8v[8];
         tmem_ld_32x32b_x16(tl + 16 * c, v);
         tmem_ld_wait();
+        const uint4 cf0 = pf[0][0], cf1 = pf[0][1], ch0 = pf[1][0], ch1 = pf[1][1];
+        fetch_fh(c + 1);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          unpack8(row < kRA ? ldcg16(map_chunk(kSlotF, 2 * c + hh)) : make_uint4(0, 0, 0, 0), f8);
-          unpack8(row < kRA ? ldcg16(map_chunk(kSlotHf, 2 * c + hh)) : make_uint4(0, 0, 0, 0), h8v);
+          unpack8(hh ? cf1 : cf0, f8);
+          unpack8(hh ? ch1 : ch0, h8v);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = 16 * c + 8 * hh + e;
@@ -805,52 +818,59 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         }
         mma_wait();
         if (warp_on) {
+          // T part: dQ rows (fp32 partial sums live in the scratch; all loads are issued before the first use)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float tv[16], uv[16], zq[16];
-            tmem_ld_32x32b_x16(tl + 16 * c, tv);
-            tmem_ld_32x32b_x16(tl + 64 + 16 * c, uv);
-            tmem_ld_wait();
+          for (int part = 0; part < 2; ++part) {
+            float* acc = part ? dk_acc : dq_acc;
+            float4 av[16];
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const int d0 = 16 * c + 8 * h8;
-              float qv[8];
-              unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.Q + (d0 >> 3) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), qv);
+            for (int i = 0; i < 16; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (acc_started && row_ok) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) zq[8 * h8 + e] = row_ok ? tv[8 * h8 + e] * qv[e] : 0.f;
-              if (row_ok && d0 < dk) {
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
-                if (acc_started) {
-                  a0 = __ldcg(reinterpret_cast<const float4*>(dq_acc + d0)); a1 = __ldcg(reinterpret_cast<const float4*>(dq_acc + d0 + 4));
-                  b0 = __ldcg(reinterpret_cast<const float4*>(dk_acc + d0)); b1 = __ldcg(reinterpret_cast<const float4*>(dk_acc + d0 + 4));
+              for (int i = 0; i < 16; ++i)
+                if (4 * i < dk) av[i] = __ldcg(reinterpret_cast<const float4*>(acc + 4 * i));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float tv[16];
+              tmem_ld_32x32b_x16(tl + 64 * part + 16 * c, tv);
+              tmem_ld_wait();
+              const float* cv = &sm.cvec[k][16 * c];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                av[4 * c + i].x = fmaf(tv[4 * i + 0], cv[4 * i + 0], av[4 * c + i].x);
+                av[4 * c + i].y = fmaf(tv[4 * i + 1], cv[4 * i + 1], av[4 * c + i].y);
+                av[4 * c + i].z = fmaf(tv[4 * i + 2], cv[4 * i + 2], av[4 * c + i].z);
+                av[4 * c + i].w = fmaf(tv[4 * i + 3], cv[4 * i + 3], av[4 * c + i].w);
+              }
+              if (part == 0) {
+                float zq[16], qv[8];
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                  unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.Q + (2 * c + h8) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), qv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) zq[8 * h8 + e] = row_ok ? tv[8 * h8 + e] * qv[e] : 0.f;
                 }
-                const float* cv = &sm.cvec[k][d0];
-                a0.x = fmaf(tv[8 * h8 + 0], cv[0], a0.x); a0.y = fmaf(tv[8 * h8 + 1], cv[1], a0.y);
-                a0.z = fmaf(tv[8 * h8 + 2], cv[2], a0.z); a0.w = fmaf(tv[8 * h8 + 3], cv[3], a0.w);
-                a1.x = fmaf(tv[8 * h8 + 4], cv[4], a1.x); a1.y = fmaf(tv[8 * h8 + 5], cv[5], a1.y);
-                a1.z = fmaf(tv[8 * h8 + 6], cv[6], a1.z); a1.w = fmaf(tv[8 * h8 + 7], cv[7], a1.w);
-                b0.x = fmaf(uv[8 * h8 + 0], cv[0], b0.x); b0.y = fmaf(uv[8 * h8 + 1], cv[1], b0.y);
-                b0.z = fmaf(uv[8 * h8 + 2], cv[2], b0.z); b0.w = fmaf(uv[8 * h8 + 3], cv[3], b0.w);
-                b1.x = fmaf(uv[8 * h8 + 4], cv[4], b1.x); b1.y = fmaf(uv[8 * h8 + 5], cv[5], b1.y);
-                b1.z = fmaf(uv[8 * h8 + 6], cv[6], b1.z); b1.w = fmaf(uv[8 * h8 + 7], cv[7], b1.w);
-                *reinterpret_cast<float4*>(dq_acc + d0) = a0; *reinterpret_cast<float4*>(dq_acc + d0 + 4) = a1;
-                *reinterpret_cast<float4*>(dk_acc + d0) = b0; *reinterpret_cast<float4*>(dk_acc + d0 + 4) = b1;
+                colsum16_to(&sm.zsum[k][16 * c], zq, lane);
               }
             }
-            colsum16_to(&sm.zsum[k][16 * c], zq, lane);
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (4 * i < dk) *reinterpret_cast<float4*>(acc + 4 * i) = av[i];
+            }
           }
         }
       }
       acc_started = true;
       sync_cta();   // the A buffer may be refilled
     };
-    // C[m,:] = Ak[m,:] * (x[m,:] - sum_j x[m,j] Ak[m,j]) for this thread's row m, x taken from the accumulator
-    // (from_tmem) or from the X tile; Ak from its scratch slot.  Written as bf16 into the A buffer.
-    auto softmax_bwd_row = [&](int aslot, bool from_tmem) {
-      if (!warp_on) {
-        if (row < kRA) for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
-        return;
-      }
+    // C[m,:] = Ak[m,:] * (x[m,:] - sum_j x[m,j] Ak[m,j]) for this thread's row m.  A_k sits in the A buffer (bulk loaded)
+    // and is overwritten in place by C (bf16); x comes from the accumulator (from_tmem) or from the X tile.
+    // Rows >= N of A_k are zero, so C keeps them zero.
+    auto softmax_bwd_row = [&](bool from_tmem) {
+      if (!warp_on) return;   // (warp-uniform: the TMEM loads below are warp-collective)
+      const bool has_row = row < kRA;
       float dot = 0.f;
       for (int c = 0; c < KS; ++c) {
         float v[16], a8[8];
@@ -858,7 +878,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
-          unpack8(row < kRA ? ldcg16(map_chunk(aslot, 2 * c + hh)) : make_uint4(0, 0, 0, 0), a8);
+          unpack8(has_row ? *reinterpret_cast<const uint4*>(sm.A + (2 * c + hh) * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0), a8);
 #pragma unroll
           for (int e = 0; e < 8; ++e) dot = fmaf(v[8 * hh + e], a8[e], dot);
         }
@@ -868,16 +888,12 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          unsigned char* ap = sm.A + (2 * c + hh) * (kRA * 16) + row * 16;
           if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
-          unpack8(row < kRA ? ldcg16(map_chunk(aslot, 2 * c + hh)) : make_uint4(0, 0, 0, 0), a8);
+          unpack8(has_row ? *reinterpret_cast<const uint4*>(ap) : make_uint4(0, 0, 0, 0), a8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 * hh + e] = row_ok ? a8[e] * (v[8 * hh + e] - dot) : 0.f;
-        }
-        if (row < kRA) {
-          uint4 lo, hi;
-          pack16(v, 1.f, lo, hi);
-          *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
-          *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
+          for (int e = 0; e < 8; ++e) a8[e] = row_ok ? a8[e] * (v[8 * hh + e] - dot) : 0.f;
+          if (has_row) *reinterpret_cast<uint4*>(ap) = pack8(a8);
         }
       }
     };
@@ -917,8 +933,10 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
           if (t == 0) { mma_at_x(); commit(); }     // dA_k part = P^T X
           mma_wait();
         }
-        sync_cta();      // A buffer (P) free: it receives C
-        softmax_bwd_row(kSlotA + k, true);
+        sync_cta();      // A buffer (P) free: A_k comes back and is turned into C in place
+        load_start(sm.A, slot(kSlotA + k), map_bytes);
+        load_wait();
+        softmax_bwd_row(true);
         contribute(k);   // (publishes; leaves the A buffer free)
         // X <- X'
         publish_cta();   // X' rows in the scratch visible to the bulk copy; nobody reads X any more
@@ -928,15 +946,21 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       // final link
       const int kl = fchain ? 0 : V - 1;
       sync_cta();
-      softmax_bwd_row(kSlotA + kl, false);
+      load_start(sm.A, slot(kSlotA + kl), map_bytes);
+      load_wait();
+      softmax_bwd_row(false);
       contribute(kl);
     };
     sweep(true);
     // seed of the R sweep: X = (drho_R[i] + dkap_R[j]) / (R + eps)
     if (row < kRX) {
+      uint4 rnext[2];
+      rnext[0] = ldcg16(map_chunk(kSlotR, 0));
+      rnext[1] = ldcg16(map_chunk(kSlotR, 1));
       for (int c = 0; c < 2 * KS; ++c) {
         float r8[8];
-        unpack8(row < kRA ? ldcg16(map_chunk(kSlotR, c)) : make_uint4(0, 0, 0, 0), r8);
+        unpack8(rnext[c & 1], r8);
+        if (c + 2 < 2 * KS) rnext[c & 1] = ldcg16(map_chunk(kSlotR, c + 2));
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int j = 8 * c + e;

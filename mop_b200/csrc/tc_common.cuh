@@ -22,10 +22,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap instead.
+// Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap after ~2 s of SM clock instead.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  const long long t0 = clock64();
+  for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -35,6 +36,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return;
+    if (clock64() - t0 > 4000000000LL) break;
   }
   printf("mop_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
