@@ -11,6 +11,7 @@
 #include "edgewise_tc_large.cuh"
 #include "edgewise_tc_large_bwd.cuh"
 #include "quartet_simt.cuh"
+#include "quartet_tc.cuh"
 #include "sdpa_simt.cuh"
 #include "sdpa_tc.cuh"
 #include "tc_selftest.cuh"
@@ -345,11 +346,45 @@ static int quartet_run(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   p->impl_used = MOP_IMPL_SIMT;
   return MOP_OK;
 }
+// tcgen05 path: prep -> fwd  |  prep -> bwd_dq -> gmat -> bwd_dkdv -> finish  (quartet_tc.cuh)
+static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
+  const qtc::Ws w = qtc::layout(p, bwd ? 1 : 0);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
+  const int BH = p->B * p->H;
+  // the backward kernels own all 512 TMEM columns of their SM: ask for more than half of the shared memory
+  const size_t smem_f = sizeof(qtc::SmemF) + 128, one_per_sm = 117 * 1024;
+  const size_t smem_q = sizeof(qtc::SmemQ) + 128 > one_per_sm ? sizeof(qtc::SmemQ) + 128 : one_per_sm;
+  const size_t smem_k = sizeof(qtc::SmemK) + 128 > one_per_sm ? sizeof(qtc::SmemK) + 128 : one_per_sm;
+  int rc;
+  qtc::prep_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  if (!bwd) {
+    if ((rc = allow_smem(qtc::fwd_kernel, smem_f))) return rc;
+    qtc::fwd_kernel<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws);
+  } else {
+    if ((rc = allow_smem(qtc::bwd_dq_kernel, smem_q))) return rc;
+    if ((rc = allow_smem(qtc::bwd_dkdv_kernel, smem_k))) return rc;
+    qtc::bwd_dq_kernel<<<BH * w.nqb, 128, smem_q, st>>>(*p, w, ws);
+    qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+    qtc::bwd_dkdv_kernel<<<BH * w.nqb, 128, smem_k, st>>>(*p, w, ws);
+    qtc::finish_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_TCGEN05;
+  return MOP_OK;
+}
 static int quartet_launch(MopQuartetParams* p, void* stream, bool bwd) {
   int rc = check_quartet(p, bwd);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT, MOP_EUNSUPPORTED, "impl %d not available", p->impl);
+  const bool tc_ok = qtc::supported(p);
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
+              "impl %d not available (tcgen05 path: bf16, dk%%8==0, dk<=64, 16-byte aligned tensors)", p->impl);
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t need_tc = qtc::layout(p, bwd ? 1 : 0).total;
+    MOP_REQUIRE(p->workspace && p->workspace_bytes >= need_tc, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need_tc);
+    MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 255) == 0, MOP_EINVAL, "workspace must be 256-byte aligned");
+    return quartet_run_tc(p, (cudaStream_t)stream, bwd);
+  }
   const size_t need = quartet::layout(p, bwd ? 1 : 0).total * sizeof(float);
   MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
   return p->dtype == MOP_F32 ? quartet_run<float>(p, (cudaStream_t)stream, bwd) : quartet_run<__nv_bfloat16>(p, (cudaStream_t)stream, bwd);
@@ -358,6 +393,7 @@ static int quartet_launch(MopQuartetParams* p, void* stream, bool bwd) {
 extern "C" {
 size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward) {
   if (check_quartet(p, false) != MOP_OK) return 0;
+  if (p->impl != MOP_IMPL_SIMT && qtc::supported(p)) return qtc::layout(p, backward).total;
   return quartet::layout(p, backward).total * sizeof(float);
 }
 int mop_quartet_fwd(MopQuartetParams* p, void* stream) { return quartet_launch(p, stream, false); }

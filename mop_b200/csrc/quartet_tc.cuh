@@ -1,0 +1,787 @@
+// GPT "Quartet" causal attention on tcgen05 / TMEM (bf16 operands, fp32 accumulation and statistics).
+//
+// Replaces quartet_attn_patch.py:88-121 for bf16 activations with dk <= 64 (dk % 8 == 0): two score maps, each
+// z-scored per row over the FULL row with the unbiased std, mixed as (1-m) n1 + m gamma n1 n2, causal fill,
+// optional additive mask, softmax, PV (`use_quartet = 0`: the single z-scored map).  Same algebra as the fp32-mode
+// kernels (quartet_simt.cuh): with kc_j = k_j - mean_j k_j the centred score is
+// c_ij = s q_i . kc_j, and sigma_i^2 = s^2 q_i^T (Kc^T Kc) q_i / (T-1), so the forward needs only the CAUSAL half of
+// both score maps plus a dk x dk Gram matrix per (batch, head, map); the backward adds two Gram-type corrections.
+//
+// Kernels (M=128 accumulators, one thread per accumulator row = tcgen05.ld 32x32b):
+//   prep      per (b,h,map): kc (bf16, the operand the MMAs see), G = Kc^T Kc from that rounded kc (as bf16 hi + lo tiles)
+//   fwd       per (b,h,128 queries): sigma_i^2 = s^2 q_i.(G q_i)/(T-1) with G q by MMA; then stream 64-key tiles (cp.async, double
+//             buffered) up to the diagonal: S1, S2 by MMA, mix + online softmax in
+//             registers (thread per query row), P V accumulated in TMEM
+//   bwd_dq    per (b,h,128 queries): S1, S2, dP = dO V^T by MMA; W1, W2 (bf16) -> dQ1 += W1 Kc1, dQ2 += W2 Kc2 in TMEM;
+//             row coefficients g_i, the Gram correction and the two scalar partials
+//   gmat      per (b,h,map): M = sum_i g_i q_i q_i^T
+//   bwd_dkdv  per (b,h,128 keys), transposed tiles (thread per key row, per-query statistics broadcast from shared
+//             memory): dV += P^T dO, dKc1 += W1^T Q, dKc2 += W2^T Q2 in TMEM, then the M correction
+//   finish    dk = dkc - mean_j dkc; scalar partials
+// Every output is written by exactly one CTA (no atomics); all buffers are the caller's.
+#pragma once
+#include "quartet_simt.cuh"
+#include "tc_common.cuh"
+
+namespace mop {
+namespace qtc {
+
+using namespace tc;
+using quartet::at;
+using quartet::load_mix;
+using quartet::Mix;
+
+constexpr int kT128 = 128 * 16 * 8;   // [128 x 64] bf16 tile image, R = 128
+constexpr int kT64 = 64 * 16 * 8;     // [64 x 64] bf16 tile image, R = 64
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct Ws {  // byte offsets into the workspace
+  size_t kc, sig, gram, gvec, mmat, dkc, spart, total;
+  int nm, nqb;
+};
+__host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
+  Ws w;
+  const size_t BH = (size_t)p->B * p->H, T = p->T;
+  w.nm = p->use_quartet ? 2 : 1;
+  w.nqb = (p->T + 127) / 128;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+  w.kc = take(w.nm * BH * T * 64 * 2);       // bf16 [nm][BH][T][64] (columns >= dk are zero)
+  w.sig = take(w.nm * BH * T * 4);           // fp32 [nm][BH][T]
+  w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
+  w.gvec = w.mmat = w.dkc = w.spart = 0;
+  if (backward) {
+    w.gvec = take(w.nm * BH * T * 4);
+    w.mmat = take(w.nm * BH * 2 * kT64);     // bf16 hi / lo tile images of sum_i g_i q_i q_i^T
+    w.dkc = take(w.nm * BH * T * 64 * 4);    // fp32 [nm][BH][T][64]
+    w.spart = take(BH * w.nqb * 2 * 4);
+  }
+  w.total = o;
+  return w;
+}
+
+__device__ __forceinline__ void publish() {
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+__device__ __forceinline__ void unpack8(uint4 u, float* f) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// fp32 64x64 matrix (shared) -> two bf16 chunk-major tile images hi, lo with hi + lo = G to ~2^-17 (global, 2 x 8 KB).
+// The symmetric matrices Kc^T Kc and sum g q q^T enter the quadratic forms through two MMAs each (X hi + X lo).
+__device__ inline void write_hilo_tiles(const float* G, unsigned char* dst) {
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += blockDim.x) {
+    const int r = idx & 63, ch = idx >> 6;
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = G[r * 64 + ch * 8 + e];
+      hi[e] = __bfloat162float(__float2bfloat16_rn(g));
+      lo[e] = g - hi[e];
+    }
+    *reinterpret_cast<uint4*>(dst + ch * 1024 + r * 16) = pack8(hi);
+    *reinterpret_cast<uint4*>(dst + kT64 + ch * 1024 + r * 16) = pack8(lo);
+  }
+}
+// 8 KB tile image global -> shared (plain copy)
+__device__ __forceinline__ void copy_tile64(unsigned char* dst, const unsigned char* src) {
+  for (int idx = threadIdx.x; idx < kT64 / 16; idx += blockDim.x) *reinterpret_cast<uint4*>(dst + idx * 16) = *reinterpret_cast<const uint4*>(src + idx * 16);
+}
+// Z[128 x 64] at TMEM column dcol = X (Mhi + Mlo): X a [128 x 64] K-major tile, M symmetric (tile images in shared memory)
+__device__ __forceinline__ void mma_x_sym(uint32_t d_tmem, uint32_t xtile, uint32_t mhi, uint32_t mlo) {
+  const uint32_t id = idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_kmajor(xtile, 128, 16 * ks), desc_kmajor(mhi, 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_kmajor(xtile, 128, 16 * ks), desc_kmajor(mlo, 64, 16 * ks), id, 1u);
+}
+
+// rows [row0, row0 + R) of a [.., T, H, dk] bf16 activation (token stride `stride` elements) -> chunk-major tile, zero fill
+template <int R>
+__device__ __forceinline__ void load_act_tile(unsigned char* tile, const __nv_bfloat16* base, size_t stride, int row0, int T, int dk) {
+  for (int idx = threadIdx.x; idx < R * 8; idx += blockDim.x) {
+    const int r = idx % R, ch = idx / R, n = row0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < T && ch * 8 < dk) v = *reinterpret_cast<const uint4*>(base + (size_t)n * stride + ch * 8);
+    *reinterpret_cast<uint4*>(tile + ch * (R * 16) + r * 16) = v;
+  }
+}
+
+// G[64][64] (shared, fp32) = sum_t wgt[t] * x_t x_t^T over the rows of a bf16 matrix with row stride `stride`
+// (columns >= dk read as zero).  256 threads; `stage` is 64*64 floats of shared memory.
+__device__ inline void weighted_gram(float* G, float* stage, const __nv_bfloat16* x, size_t stride, const float* wgt, int T, int dk) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 64) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 8; idx += 256) {
+      const int r = idx >> 3, ch = idx & 7, t = t0 + r;
+      float f[8];
+      unpack8((t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(x + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) stage[r * 64 + ch * 8 + e] = f[e];
+    }
+    __syncthreads();
+    const int rows = min(64, T - t0);
+    for (int r = 0; r < rows; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(stage + r * 64 + 4 * ty);
+      float4 b = *reinterpret_cast<const float4*>(stage + r * 64 + 4 * tx);
+      if (wgt) { const float g = wgt[t0 + r]; b.x *= g; b.y *= g; b.z *= g; b.w *= g; }
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) G[(4 * ty + i) * 64 + 4 * tx + j] = acc[i][j];
+  __syncthreads();
+}
+
+// grid: B*H*nm, 256 threads
+__global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ __align__(16) float G[64 * 64];
+  __shared__ __align__(16) float stage[64 * 64];
+  __shared__ float part[4][64];
+  __shared__ float kbar[64];
+  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(map ? p.k2 : p.k) + at(p, b, 0, h);
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(map ? p.q2 : p.q) + at(p, b, 0, h);
+  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(ws + w.kc) + ((size_t)map * BH + bh) * T * 64;
+  {
+    const int d = tid & 63, sl = tid >> 6;
+    float s = 0.f;
+    if (d < dk)
+      for (int t = sl; t < T; t += 4) s += __bfloat162float(k[(size_t)t * stride + d]);
+    part[sl][d] = s;
+  }
+  __syncthreads();
+  if (tid < 64) kbar[tid] = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) / (float)T;
+  __syncthreads();
+  for (int idx = tid; idx < T * 8; idx += 256) {
+    const int t = idx >> 3, ch = idx & 7;
+    float f[8];
+    unpack8(ch * 8 < dk ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (ch * 8 + e < dk) ? f[e] - kbar[ch * 8 + e] : 0.f;
+    *reinterpret_cast<uint4*>(kc + (size_t)t * 64 + ch * 8) = pack8(f);
+  }
+  __syncthreads();   // this CTA's kc rows are visible to all of its threads
+  weighted_gram(G, stage, kc, 64, nullptr, T, 64);
+  write_hilo_tiles(G, ws + w.gram + ((size_t)map * BH + bh) * 2 * kT64);
+}
+
+// mixed score of one element from the raw MMA dot products (natural units); masks applied by the caller
+__device__ __forceinline__ float mix_n(const Mix& x, float n1, float n2) { return x.quart ? n1 * ((1.f - x.m) + x.m * x.gam * n2) : n1; }
+
+// 16-byte global -> shared copy without registers (zero fill when !valid); completion tracked by cp.async groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int R>
+__device__ __forceinline__ void load_act_tile_async(unsigned char* tile, const __nv_bfloat16* base, size_t stride, int row0, int T, int dk) {
+  for (int idx = threadIdx.x; idx < R * 8; idx += blockDim.x) {
+    const int r = idx % R, ch = idx / R, n = row0 + r;
+    const bool ok = n < T && ch * 8 < dk;
+    cp_async16(tile + ch * (R * 16) + r * 16, base + (size_t)(ok ? n : 0) * stride + (ok ? ch * 8 : 0), ok);
+  }
+}
+
+struct __align__(128) SmemF {
+  unsigned char Q[kT128], Q2[kT128], P[kT128];
+  unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
+  uint64_t bar;
+  uint32_t tmem_slot;
+};
+
+// grid: B*H*nqb, 128 threads; two CTAs per SM (256 TMEM columns each: S1 | S2 | O)
+__global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nqb = w.nqb;
+  // heavy (late) query blocks first: the causal work per block grows with its index
+  const int qb = nqb - 1 - (int)(blockIdx.x / ((unsigned)p.B * p.H)), bh = blockIdx.x % (p.B * p.H), b = bh / p.H, h = bh % p.H;
+  const int q0 = qb * 128, gi = q0 + tid;
+  const bool row_ok = gi < T;
+  const int dks = (dk + 15) >> 4;
+  const Mix mx = load_mix(p);
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  if (warp == 0) tmem_alloc<256>(&sm.tmem_slot);
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
+  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
+  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
+  load_act_tile<128>(sm.Q, reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h), stride, q0, T, dk);
+  if (mx.quart) load_act_tile<128>(sm.Q2, reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h), stride, q0, T, dk);
+  // the Gram tiles (hi, lo per map) borrow the second key / value buffers for the sigma prologue
+  copy_tile64(sm.K1[1], ws + w.gram + (size_t)bh * 2 * kT64);
+  copy_tile64(sm.K2[1], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
+  if (mx.quart) {
+    copy_tile64(sm.V[1], ws + w.gram + (BH + bh) * 2 * kT64);
+    copy_tile64(sm.P, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
+  }
+  auto fetch = [&](int buf, int k0) {
+    load_act_tile_async<64>(sm.K1[buf], kc1, 64, k0, T, 64);
+    if (mx.quart) load_act_tile_async<64>(sm.K2[buf], kc2, 64, k0, T, 64);
+    load_act_tile_async<64>(sm.V[buf], vbase, stride, k0, T, dk);
+    cp_async_commit();
+  };
+  fetch(0, 0);
+  publish();
+  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
+  uint32_t phase = 0;
+  // ---- sigma_i = s sqrt(q_i . (G q_i) / (T-1)),  G q by MMA (G = hi + lo)
+  if (tid == 0) {
+    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1[1]), smem_u32(sm.K2[1]));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V[1]), smem_u32(sm.P));
+    mma_commit(&sm.bar);
+  }
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  float quad1 = 0.f, quad2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float z1[16], z2[16], x[8];
+    tmem_ld_32x32b_x16(tl + 16 * c, z1);
+    if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, z2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      unpack8(*reinterpret_cast<const uint4*>(sm.Q + (2 * c + hh) * (128 * 16) + tid * 16), x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) quad1 = fmaf(z1[8 * hh + e], x[e], quad1);
+      if (mx.quart) {
+        unpack8(*reinterpret_cast<const uint4*>(sm.Q2 + (2 * c + hh) * (128 * 16) + tid * 16), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) quad2 = fmaf(z2[8 * hh + e], x[e], quad2);
+      }
+    }
+  }
+  const float s1v = p.scale * sqrtf(fmaxf(quad1, 0.f) / (float)(T - 1)), s2v = mx.quart ? p.scale * sqrtf(fmaxf(quad2, 0.f) / (float)(T - 1)) : 0.f;
+  const float a1 = p.scale / (s1v + mx.eps), a2 = mx.quart ? p.scale / (s2v + mx.eps) : 0.f;
+  tc_fence_before();
+  __syncthreads();   // the Gram tiles are dead: their buffers may receive key / value tiles
+  float m_run = -INFINITY, l_run = 0.f;
+  const int k_end = min(T, q0 + 128);
+  const int ntiles = (k_end + 63) >> 6;
+  for (int it = 0; it < ntiles; ++it) {
+    const int k0 = it * 64, buf = it & 1;
+    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // P V of tile it-1: its buffers and P are free
+    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 0);
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+      if (mx.quart)
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+      mma_commit(&sm.bar);
+    }
+    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+    float sc[64];
+    float tmax = -INFINITY;
+    const bool need_mask = (k0 + 63 > q0) || (k0 + 64 > T);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v1[16], v2[16];
+      tmem_ld_32x32b_x16(tl + 16 * c, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int gj = k0 + 16 * c + e;
+        float s = mix_n(mx, v1[e] * a1, mx.quart ? v2[e] * a2 : 0.f);
+        if (need_mask && (gj > gi || gj >= T)) s = -INFINITY;
+        if (p.add_mask && row_ok && gj < T) s += p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+        sc[16 * c + e] = s;
+        tmax = fmaxf(tmax, s);
+      }
+    }
+    const float m_new = fmaxf(m_run, tmax);
+    const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
+    const float corr = (m_run == -INFINITY) ? 0.f : ex2(fmaf(m_run, kLog2e, -mb));
+    const bool need = it > 0 && m_new > m_run;
+    if (__any_sync(0xffffffffu, need)) {
+      const float scl = need ? corr : 1.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float o[16];
+        tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] *= scl;
+        tmem_st_32x32b_x16(tl + 128 + 16 * c, o);
+      }
+      tmem_st_wait();
+    }
+    l_run *= corr;
+    m_run = m_new;
+    float ps = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { pv[e] = ex2(fmaf(sc[8 * c + e], kLog2e, -mb)); ps += pv[e]; }
+      *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
+    }
+    l_run += ps;
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.P), 128, 16 * ks), desc_mnmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&sm.bar);
+    }
+  }
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float o[16];
+    tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] *= il;
+    if (row_ok) {
+      if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
+      if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
+    }
+  }
+  if (p.stats && row_ok) {
+    float* st = p.stats + (((size_t)b * p.H + h) * T + gi) * 3;
+    st[0] = s1v; st[1] = s2v; st[2] = m_run + kLn2 * lg2(l_run);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tb);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+struct __align__(128) SmemQ {
+  unsigned char Q[kT128], Q2[kT128], dO[kT128], K1[kT64], K2[kT64], V[kT64], W1[kT128], W2[kT128];
+  float red[8];
+  uint64_t bar;
+  uint32_t tmem_slot;
+};
+
+// Per-element backward of the mix given the raw dot products; returns the probability and writes dn1, dn2.
+struct ElemOut { float pr, dn1, dn2, c1, c2; };
+__device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, float dp, float scale, float i1, float i2, float lse, float dlt,
+                                            bool masked, float addm, float* sc0, float* sc1) {
+  ElemOut o;
+  o.c1 = r1 * scale; o.c2 = r2 * scale;
+  const float n1 = o.c1 * i1, n2 = o.c2 * i2;
+  const float s = mix_n(mx, n1, n2) + addm;
+  o.pr = masked ? 0.f : ex2((s - lse) * kLog2e);
+  const float D = o.pr * (dp - dlt);
+  o.dn1 = D; o.dn2 = 0.f;
+  if (mx.quart) {
+    o.dn1 = D * ((1.f - mx.m) + mx.m * mx.gam * n2);
+    o.dn2 = D * (mx.m * mx.gam * n1);
+    *sc0 += D * (-n1 + mx.gam * n1 * n2);
+    *sc1 += D * (mx.m * n1 * n2);
+  }
+  return o;
+}
+
+// grid: B*H*nqb, 128 threads, one CTA per SM (TMEM: S1 | S2 | dP | dQ1 | dQ2)
+__global__ void __launch_bounds__(128, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, dk = p.dk, T = p.T, nqb = w.nqb;
+  const int qb = blockIdx.x % nqb, bh = blockIdx.x / nqb, b = bh / p.H, h = bh % p.H;
+  const int q0 = qb * 128, gi = q0 + tid;
+  const bool row_ok = gi < T;
+  const int dks = (dk + 15) >> 4;
+  const Mix mx = load_mix(p);
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  if (warp == 0) tmem_alloc<512>(&sm.tmem_slot);
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
+  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
+  load_act_tile<128>(sm.Q, reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h), stride, q0, T, dk);
+  if (mx.quart) load_act_tile<128>(sm.Q2, reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h), stride, q0, T, dk);
+  load_act_tile<128>(sm.dO, reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h), stride, q0, T, dk);
+  // per-row statistics
+  const float* st = p.stats + (((size_t)b * p.H + h) * T + (row_ok ? gi : T - 1)) * 3;
+  const float s1v = st[0], s2v = st[1], lse = st[2];
+  const float i1 = 1.f / (s1v + mx.eps), i2 = mx.quart ? 1.f / (s2v + mx.eps) : 0.f;
+  float dlt = 0.f;
+  if (row_ok) {
+    const __nv_bfloat16* yr = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, gi, h);
+    const __nv_bfloat16* dr = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, gi, h);
+    for (int d0 = 0; d0 < dk; d0 += 8) {
+      float a[8], c[8];
+      unpack8(*reinterpret_cast<const uint4*>(yr + d0), a);
+      unpack8(*reinterpret_cast<const uint4*>(dr + d0), c);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dlt = fmaf(a[e], c[e], dlt);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
+  uint32_t phase = 0;
+  float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
+  const int k_end = min(T, q0 + 128);
+  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
+  for (int k0 = 0; k0 < k_end; k0 += 64) {
+    if (k0 > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+    load_act_tile<64>(sm.K1, kc1, 64, k0, T, 64);
+    if (mx.quart) load_act_tile<64>(sm.K2, kc2, 64, k0, T, 64);
+    load_act_tile<64>(sm.V, vbase, stride, k0, T, dk);
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 0);
+      for (int ks = 0; ks < dks; ++ks) {
+        mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.dO), 128, 16 * ks), desc_kmajor(smem_u32(sm.V), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+      }
+      mma_commit(&sm.bar);
+    }
+    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v1[16], v2[16], dp[16], w1[16], w2[16];
+      tmem_ld_32x32b_x16(tl + 16 * c, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
+      tmem_ld_32x32b_x16(tl + 128 + 16 * c, dp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int gj = k0 + 16 * c + e;
+        const bool masked = gj > gi || gj >= T || !row_ok;
+        float addm = 0.f;
+        if (p.add_mask && !masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+        const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, lse, dlt, masked, addm, &sc0, &sc1);
+        g1 = fmaf(o.dn1, o.c1, g1);
+        g2 = fmaf(o.dn2, o.c2, g2);
+        w1[e] = o.dn1 * i1;
+        w2[e] = o.dn2 * i2;
+      }
+      *reinterpret_cast<uint4*>(sm.W1 + (2 * c) * (128 * 16) + tid * 16) = pack8(w1);
+      *reinterpret_cast<uint4*>(sm.W1 + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w1 + 8);
+      if (mx.quart) {
+        *reinterpret_cast<uint4*>(sm.W2 + (2 * c) * (128 * 16) + tid * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2 + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w2 + 8);
+      }
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K1), 64, 16 * ks), id, (k0 > 0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K2), 64, 16 * ks), id, (k0 > 0 || ks > 0) ? 1u : 0u);
+      }
+      mma_commit(&sm.bar);
+    }
+  }
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  // row coefficients, Gram correction, outputs
+  const float Tm1 = (float)(T - 1);
+  const float gg1 = row_ok ? g1 / ((s1v + mx.eps) * (s1v + mx.eps) * Tm1 * s1v) : 0.f;
+  const float gg2 = (row_ok && mx.quart) ? g2 / ((s2v + mx.eps) * (s2v + mx.eps) * Tm1 * s2v) : 0.f;
+  // G q by MMA: the Gram tiles (hi, lo per map) go to the dead key / value / W buffers; Z1 -> columns [0,64), Z2 -> [64,128)
+  __syncthreads();
+  copy_tile64(sm.K1, ws + w.gram + (size_t)bh * 2 * kT64);
+  copy_tile64(sm.K2, ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
+  if (mx.quart) {
+    copy_tile64(sm.V, ws + w.gram + (BH + bh) * 2 * kT64);
+    copy_tile64(sm.W1, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
+  }
+  publish();
+  if (tid == 0) {
+    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1), smem_u32(sm.K2));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V), smem_u32(sm.W1));
+    mma_commit(&sm.bar);
+  }
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  for (int map = 0; map < w.nm; ++map) {
+    const float gv = map ? gg2 : gg1;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(map ? p.dq2 : p.dq) + at(p, b, row_ok ? gi : 0, h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc[16], wv[16];
+      tmem_ld_32x32b_x16(tl + (map ? 256 : 192) + 16 * c, acc);
+      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + 16 * c, wv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = p.scale * acc[e] - p.scale * p.scale * gv * wv[e];
+      if (row_ok) {
+        if (16 * c < dk) *reinterpret_cast<uint4*>(out + 16 * c) = pack8(acc);
+        if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(out + 16 * c + 8) = pack8(acc + 8);
+      }
+    }
+    if (row_ok) (reinterpret_cast<float*>(ws + w.gvec) + ((size_t)map * BH + bh) * T)[gi] = gv;
+  }
+  // scalar partials of this query block
+  sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
+  if (lane == 0) { sm.red[warp] = sc0; sm.red[4 + warp] = sc1; }
+  __syncthreads();
+  if (tid == 0) {
+    float* sp = reinterpret_cast<float*>(ws + w.spart) + (size_t)blockIdx.x * 2;
+    sp[0] = mx.m * (1.f - mx.m) * (sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3]);
+    sp[1] = sm.red[4] + sm.red[5] + sm.red[6] + sm.red[7];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tb);
+}
+
+// grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T
+__global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ __align__(16) float G[64 * 64];
+  __shared__ __align__(16) float stage[64 * 64];
+  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H;
+  const size_t BH = (size_t)p.B * p.H;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(map ? p.q2 : p.q) + at(p, b, 0, h);
+  const float* gv = reinterpret_cast<const float*>(ws + w.gvec) + ((size_t)map * BH + bh) * p.T;
+  weighted_gram(G, stage, q, (size_t)p.H * p.dk, gv, p.T, p.dk);
+  write_hilo_tiles(G, ws + w.mmat + ((size_t)map * BH + bh) * 2 * kT64);
+}
+
+struct __align__(128) SmemK {
+  unsigned char K1[kT128], K2[kT128], V[kT128], Q[kT64], Q2[kT64], dO[kT64], PT[kT128], W1T[kT128], W2T[kT128];
+  float i1s[64], i2s[64], lses[64], dlts[64];
+  uint64_t bar;
+  uint32_t tmem_slot;
+};
+
+// grid: B*H*nqb (128 keys per CTA), 128 threads (thread per key), one CTA per SM
+// TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)
+__global__ void __launch_bounds__(128, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nkb = w.nqb;
+  const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;
+  const int k0 = kb * 128, gj = k0 + tid;
+  const bool key_ok = gj < T;
+  const int dks = (dk + 15) >> 4;
+  const Mix mx = load_mix(p);
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  if (warp == 0) tmem_alloc<512>(&sm.tmem_slot);
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
+  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
+  load_act_tile<128>(sm.K1, kc1, 64, k0, T, 64);
+  if (mx.quart) load_act_tile<128>(sm.K2, kc2, 64, k0, T, 64);
+  load_act_tile<128>(sm.V, reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h), stride, k0, T, dk);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
+  uint32_t phase = 0;
+  float dum0 = 0.f, dum1 = 0.f;
+  bool first = true;
+  const __nv_bfloat16* qbase = reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h);
+  const __nv_bfloat16* q2base = mx.quart ? reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h) : nullptr;
+  const __nv_bfloat16* dybase = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h);
+  const __nv_bfloat16* ybase = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, 0, h);
+  for (int q0 = k0; q0 < T; q0 += 64) {   // queries i >= j only (k0 is a multiple of 64)
+    if (!first) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+    load_act_tile<64>(sm.Q, qbase, stride, q0, T, dk);
+    if (mx.quart) load_act_tile<64>(sm.Q2, q2base, stride, q0, T, dk);
+    load_act_tile<64>(sm.dO, dybase, stride, q0, T, dk);
+    if (tid < 64) {
+      const int i = q0 + tid, ic = min(i, T - 1);
+      const float* st = p.stats + (((size_t)b * p.H + h) * T + ic) * 3;
+      sm.i1s[tid] = 1.f / (st[0] + mx.eps);
+      sm.i2s[tid] = mx.quart ? 1.f / (st[1] + mx.eps) : 0.f;
+      sm.lses[tid] = st[2];
+      float dl = 0.f;
+      if (i < T)
+        for (int d0 = 0; d0 < dk; d0 += 8) {
+          float a[8], c[8];
+          unpack8(*reinterpret_cast<const uint4*>(ybase + (size_t)i * stride + d0), a);
+          unpack8(*reinterpret_cast<const uint4*>(dybase + (size_t)i * stride + d0), c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dl = fmaf(a[e], c[e], dl);
+        }
+      sm.dlts[tid] = dl;
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 0);
+      for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
+        mma_ss(tb, desc_kmajor(smem_u32(sm.K1), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.K2), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q2), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.V), 128, 16 * ks), desc_kmajor(smem_u32(sm.dO), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+      }
+      mma_commit(&sm.bar);
+    }
+    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v1[16], v2[16], dp[16], pt[16], w1[16], w2[16];
+      tmem_ld_32x32b_x16(tl + 16 * c, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
+      tmem_ld_32x32b_x16(tl + 128 + 16 * c, dp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = 16 * c + e, gi = q0 + col;
+        const bool masked = gj > gi || gi >= T || !key_ok;
+        float addm = 0.f;
+        if (p.add_mask && !masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+        const float i1 = sm.i1s[col], i2 = sm.i2s[col];
+        const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, sm.lses[col], sm.dlts[col], masked, addm, &dum0, &dum1);
+        pt[e] = o.pr;
+        w1[e] = o.dn1 * i1;
+        w2[e] = o.dn2 * i2;
+      }
+      *reinterpret_cast<uint4*>(sm.PT + (2 * c) * (128 * 16) + tid * 16) = pack8(pt);
+      *reinterpret_cast<uint4*>(sm.PT + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(pt + 8);
+      *reinterpret_cast<uint4*>(sm.W1T + (2 * c) * (128 * 16) + tid * 16) = pack8(w1);
+      *reinterpret_cast<uint4*>(sm.W1T + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w1 + 8);
+      if (mx.quart) {
+        *reinterpret_cast<uint4*>(sm.W2T + (2 * c) * (128 * 16) + tid * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2T + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w2 + 8);
+      }
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(128, 64, 0, 1);
+      const uint32_t acc0 = first ? 0u : 1u;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.dO), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q2), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+      }
+      mma_commit(&sm.bar);
+    }
+    first = false;
+  }
+  if (!first) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+  // dV
+  __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + at(p, b, key_ok ? gj : 0, h);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc[16];
+    if (first) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    } else {
+      tmem_ld_32x32b_x16(tl + 192 + 16 * c, acc);
+      tmem_ld_wait();
+    }
+    if (key_ok) {
+      if (16 * c < dk) *reinterpret_cast<uint4*>(dv + 16 * c) = pack8(acc);
+      if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(dv + 16 * c + 8) = pack8(acc + 8);
+    }
+  }
+  // dkc = s W^T q - s^2 M kc   (fp32; centred by finish_kernel)
+  // M kc by MMA: the M tiles (hi, lo per map) go to the dead query / dO / PT buffers; Z1 -> columns [0,64), Z2 -> [64,128)
+  __syncthreads();
+  copy_tile64(sm.Q, ws + w.mmat + (size_t)bh * 2 * kT64);
+  copy_tile64(sm.Q2, ws + w.mmat + (size_t)bh * 2 * kT64 + kT64);
+  if (mx.quart) {
+    copy_tile64(sm.dO, ws + w.mmat + (BH + bh) * 2 * kT64);
+    copy_tile64(sm.PT, ws + w.mmat + (BH + bh) * 2 * kT64 + kT64);
+  }
+  publish();
+  if (tid == 0) {
+    mma_x_sym(tb, smem_u32(sm.K1), smem_u32(sm.Q), smem_u32(sm.Q2));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.K2), smem_u32(sm.dO), smem_u32(sm.PT));
+    mma_commit(&sm.bar);
+  }
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  for (int map = 0; map < w.nm; ++map) {
+    float* out = reinterpret_cast<float*>(ws + w.dkc) + (((size_t)map * BH + bh) * T + (key_ok ? gj : 0)) * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc[16], wv[16];
+      if (first) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      } else {
+        tmem_ld_32x32b_x16(tl + (map ? 320 : 256) + 16 * c, acc);
+      }
+      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + 16 * c, wv);
+      tmem_ld_wait();
+      if (key_ok) {
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4)
+          *reinterpret_cast<float4*>(out + 16 * c + 4 * e4) =
+              make_float4(p.scale * acc[4 * e4] - p.scale * p.scale * wv[4 * e4], p.scale * acc[4 * e4 + 1] - p.scale * p.scale * wv[4 * e4 + 1],
+                          p.scale * acc[4 * e4 + 2] - p.scale * p.scale * wv[4 * e4 + 2], p.scale * acc[4 * e4 + 3] - p.scale * p.scale * wv[4 * e4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tb);
+}
+
+// grid: B*H*nm, 256 threads.  dk = dkc - mean_j dkc ; map 0 also reduces the scalar partials of its (b,h)
+__global__ void __launch_bounds__(256) finish_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ float part[4][64];
+  __shared__ float mean[64];
+  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
+  const size_t BH = (size_t)p.B * p.H;
+  const float* dkc = reinterpret_cast<const float*>(ws + w.dkc) + ((size_t)map * BH + bh) * T * 64;
+  {
+    const int d = tid & 63, sl = tid >> 6;
+    float s = 0.f;
+    for (int t = sl; t < T; t += 4) s += dkc[(size_t)t * 64 + d];
+    part[sl][d] = s;
+  }
+  __syncthreads();
+  if (tid < 64) mean[tid] = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) / (float)T;
+  __syncthreads();
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(map ? p.dk2 : p.dk_) + at(p, b, 0, h);
+  const size_t stride = (size_t)p.H * dk;
+  for (int idx = tid; idx < T * 8; idx += 256) {
+    const int t = idx >> 3, ch = idx & 7;
+    if (ch * 8 >= dk) continue;
+    const float4 a = *reinterpret_cast<const float4*>(dkc + (size_t)t * 64 + ch * 8), c = *reinterpret_cast<const float4*>(dkc + (size_t)t * 64 + ch * 8 + 4);
+    const float f[8] = {a.x - mean[ch * 8], a.y - mean[ch * 8 + 1], a.z - mean[ch * 8 + 2], a.w - mean[ch * 8 + 3],
+                        c.x - mean[ch * 8 + 4], c.y - mean[ch * 8 + 5], c.z - mean[ch * 8 + 6], c.w - mean[ch * 8 + 7]};
+    *reinterpret_cast<uint4*>(out + (size_t)t * stride + ch * 8) = pack8(f);
+  }
+  if (map == 0 && tid < 2 && p.dscalar_part) {
+    float s = 0.f;
+    const float* sp = reinterpret_cast<const float*>(ws + w.spart) + (size_t)bh * w.nqb * 2;
+    for (int c = 0; c < w.nqb; ++c) s += sp[c * 2 + tid];
+    p.dscalar_part[(size_t)bh * 2 + tid] = s;
+  }
+}
+
+inline bool supported(const MopQuartetParams* p) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return p->dtype == MOP_BF16 && p->dk % 8 == 0 && p->dk <= 64 && p->T >= 2 && al16(p->q) && al16(p->k) && al16(p->v) &&
+         (!p->use_quartet || (al16(p->q2) && al16(p->k2)));
+}
+
+}  // namespace qtc
+}  // namespace mop
