@@ -357,15 +357,16 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   const size_t smem_k = sizeof(qtc::SmemK) + 128 > one_per_sm ? sizeof(qtc::SmemK) + 128 : one_per_sm;
   int rc;
   qtc::prep_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  const bool hm = p->add_mask != nullptr;
   if (!bwd) {
-    if ((rc = allow_smem(qtc::fwd_kernel, smem_f))) return rc;
-    qtc::fwd_kernel<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws);
+    if ((rc = allow_smem(hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>, smem_f))) return rc;
+    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws);
   } else {
-    if ((rc = allow_smem(qtc::bwd_dq_kernel, smem_q))) return rc;
-    if ((rc = allow_smem(qtc::bwd_dkdv_kernel, smem_k))) return rc;
-    qtc::bwd_dq_kernel<<<BH * w.nqb, 128, smem_q, st>>>(*p, w, ws);
+    if ((rc = allow_smem(hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>, smem_q))) return rc;
+    if ((rc = allow_smem(hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>, smem_k))) return rc;
+    (hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>)<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws);
     qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
-    qtc::bwd_dkdv_kernel<<<BH * w.nqb, 128, smem_k, st>>>(*p, w, ws);
+    (hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>)<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws);
     qtc::finish_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
   }
   MOP_CHECK_CUDA(cudaGetLastError());

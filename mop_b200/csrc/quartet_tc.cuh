@@ -40,7 +40,7 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 struct Ws {  // byte offsets into the workspace
-  size_t kc, sig, gram, gvec, mmat, dkc, spart, total;
+  size_t kc, sig, gram, gvec, mmat, dkc, spart, delta, total;
   int nm, nqb;
 };
 __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
@@ -53,12 +53,13 @@ __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
   w.kc = take(w.nm * BH * T * 64 * 2);       // bf16 [nm][BH][T][64] (columns >= dk are zero)
   w.sig = take(w.nm * BH * T * 4);           // fp32 [nm][BH][T]
   w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
-  w.gvec = w.mmat = w.dkc = w.spart = 0;
+  w.gvec = w.mmat = w.dkc = w.spart = w.delta = 0;
   if (backward) {
     w.gvec = take(w.nm * BH * T * 4);
     w.mmat = take(w.nm * BH * 2 * kT64);     // bf16 hi / lo tile images of sum_i g_i q_i q_i^T
     w.dkc = take(w.nm * BH * T * 64 * 4);    // fp32 [nm][BH][T][64]
     w.spart = take(BH * w.nqb * 2 * 4);
+    w.delta = take(BH * T * 4);              // fp32 [BH][T]: dO . y per query (bwd_dq -> bwd_dkdv)
   }
   w.total = o;
   return w;
@@ -220,6 +221,7 @@ struct __align__(128) SmemF {
 };
 
 // grid: B*H*nqb, 128 threads; two CTAs per SM (256 TMEM columns each: S1 | S2 | O)
+template <bool HAS_MASK>
 __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
@@ -311,15 +313,23 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int gj = k0 + 16 * c + e;
-        float s = mix_n(mx, v1[e] * a1, mx.quart ? v2[e] * a2 : 0.f);
-        if (need_mask && (gj > gi || gj >= T)) s = -INFINITY;
-        if (p.add_mask && row_ok && gj < T) s += p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
-        sc[16 * c + e] = s;
-        tmax = fmaxf(tmax, s);
+      for (int e = 0; e < 16; ++e) sc[16 * c + e] = mix_n(mx, v1[e] * a1, mx.quart ? v2[e] * a2 : 0.f);
+    }
+    if (need_mask) {   // tiles on the diagonal / past the end only (uniform branch)
+#pragma unroll
+      for (int e = 0; e < 64; ++e)
+        if (k0 + e > gi || k0 + e >= T) sc[e] = -INFINITY;
+    }
+    if constexpr (HAS_MASK) {
+      if (row_ok) {
+        const float* am = p.add_mask + (int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)k0 * p.am_sk;
+#pragma unroll 8
+        for (int e = 0; e < 64; ++e)
+          if (k0 + e < T) sc[e] += am[(int64_t)e * p.am_sk];
       }
     }
+#pragma unroll
+    for (int e = 0; e < 64; ++e) tmax = fmaxf(tmax, sc[e]);
     const float m_new = fmaxf(m_run, tmax);
     const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
     const float corr = (m_run == -INFINITY) ? 0.f : ex2(fmaf(m_run, kLog2e, -mb));
@@ -385,8 +395,10 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
 // backward
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(128) SmemQ {
-  unsigned char Q[kT128], Q2[kT128], dO[kT128], K1[kT64], K2[kT64], V[kT64], W1[kT128], W2[kT128];
-  float red[8];
+  unsigned char Q[kT128], Q2[kT128], dO[kT128], W1[kT128], W2[kT128];
+  unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
+  float gx[2][2][128];   // [warpgroup][map][row]: row-coefficient partial sums
+  float red[16];
   uint64_t bar;
   uint32_t tmem_slot;
 };
@@ -411,25 +423,36 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
   return o;
 }
 
-// grid: B*H*nqb, 128 threads, one CTA per SM (TMEM: S1 | S2 | dP | dQ1 | dQ2)
-__global__ void __launch_bounds__(128, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+// grid: B*H*nqb, 256 threads (two warpgroups split the 64 columns of every tile), one CTA per SM
+// TMEM: S1 | S2 | dP | dQ1 | dQ2 (64 columns each)
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, dk = p.dk, T = p.T, nqb = w.nqb;
-  const int qb = blockIdx.x % nqb, bh = blockIdx.x / nqb, b = bh / p.H, h = bh % p.H;
-  const int q0 = qb * 128, gi = q0 + tid;
+  const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31, dk = p.dk, T = p.T, nqb = w.nqb;
+  const int qb = nqb - 1 - (int)(blockIdx.x / ((unsigned)p.B * p.H)), bh = blockIdx.x % (p.B * p.H), b = bh / p.H, h = bh % p.H;
+  const int q0 = qb * 128, gi = q0 + t;
   const bool row_ok = gi < T;
   const int dks = (dk + 15) >> 4;
+  const int c0 = 32 * wg;   // this warpgroup's columns inside a 64-key tile
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
-  if (warp == 0) tmem_alloc<512>(&sm.tmem_slot);
+  if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
   const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
   const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
+  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
+  auto fetch = [&](int buf, int k0) {
+    load_act_tile_async<64>(sm.K1[buf], kc1, 64, k0, T, 64);
+    if (mx.quart) load_act_tile_async<64>(sm.K2[buf], kc2, 64, k0, T, 64);
+    load_act_tile_async<64>(sm.V[buf], vbase, stride, k0, T, dk);
+    cp_async_commit();
+  };
+  fetch(0, 0);
   load_act_tile<128>(sm.Q, reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h), stride, q0, T, dk);
   if (mx.quart) load_act_tile<128>(sm.Q2, reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h), stride, q0, T, dk);
   load_act_tile<128>(sm.dO, reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h), stride, q0, T, dk);
-  // per-row statistics
+  // per-row statistics (both warpgroups need them)
   const float* st = p.stats + (((size_t)b * p.H + h) * T + (row_ok ? gi : T - 1)) * 3;
   const float s1v = st[0], s2v = st[1], lse = st[2];
   const float i1 = 1.f / (s1v + mx.eps), i2 = mx.quart ? 1.f / (s2v + mx.eps) : 0.f;
@@ -444,55 +467,58 @@ __global__ void __launch_bounds__(128, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
 #pragma unroll
       for (int e = 0; e < 8; ++e) dlt = fmaf(a[e], c[e], dlt);
     }
+    if (wg == 0) (reinterpret_cast<float*>(ws + w.delta) + (size_t)bh * T)[gi] = dlt;   // for bwd_dkdv
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
+  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
   const int k_end = min(T, q0 + 128);
-  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
-  for (int k0 = 0; k0 < k_end; k0 += 64) {
-    if (k0 > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
-    load_act_tile<64>(sm.K1, kc1, 64, k0, T, 64);
-    if (mx.quart) load_act_tile<64>(sm.K2, kc2, 64, k0, T, 64);
-    load_act_tile<64>(sm.V, vbase, stride, k0, T, dk);
+  const int ntiles = (k_end + 63) >> 6;
+  for (int it = 0; it < ntiles; ++it) {
+    const int k0 = it * 64, buf = it & 1;
+    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // dQ MMAs of tile it-1: its buffers and W are free
+    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
     publish();
     if (tid == 0) {
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {
-        mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.dO), 128, 16 * ks), desc_kmajor(smem_u32(sm.V), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.dO), 128, 16 * ks), desc_kmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int col = c0 + 16 * c;
       float v1[16], v2[16], dp[16], w1[16], w2[16];
-      tmem_ld_32x32b_x16(tl + 16 * c, v1);
-      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
-      tmem_ld_32x32b_x16(tl + 128 + 16 * c, dp);
+      tmem_ld_32x32b_x16(tl + col, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + col, v2);
+      tmem_ld_32x32b_x16(tl + 128 + col, dp);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int gj = k0 + 16 * c + e;
+        const int gj = k0 + col + e;
         const bool masked = gj > gi || gj >= T || !row_ok;
         float addm = 0.f;
-        if (p.add_mask && !masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+        if constexpr (HAS_MASK)
+          if (!masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
         const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, lse, dlt, masked, addm, &sc0, &sc1);
         g1 = fmaf(o.dn1, o.c1, g1);
         g2 = fmaf(o.dn2, o.c2, g2);
         w1[e] = o.dn1 * i1;
         w2[e] = o.dn2 * i2;
       }
-      *reinterpret_cast<uint4*>(sm.W1 + (2 * c) * (128 * 16) + tid * 16) = pack8(w1);
-      *reinterpret_cast<uint4*>(sm.W1 + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w1 + 8);
+      const int ch = col >> 3;
+      *reinterpret_cast<uint4*>(sm.W1 + ch * (128 * 16) + t * 16) = pack8(w1);
+      *reinterpret_cast<uint4*>(sm.W1 + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
       if (mx.quart) {
-        *reinterpret_cast<uint4*>(sm.W2 + (2 * c) * (128 * 16) + tid * 16) = pack8(w2);
-        *reinterpret_cast<uint4*>(sm.W2 + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w2 + 8);
+        *reinterpret_cast<uint4*>(sm.W2 + ch * (128 * 16) + t * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2 + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
       }
     }
     publish();
@@ -500,62 +526,67 @@ __global__ void __launch_bounds__(128, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K1), 64, 16 * ks), id, (k0 > 0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K2), 64, 16 * ks), id, (k0 > 0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-  // row coefficients, Gram correction, outputs
-  const float Tm1 = (float)(T - 1);
-  const float gg1 = row_ok ? g1 / ((s1v + mx.eps) * (s1v + mx.eps) * Tm1 * s1v) : 0.f;
-  const float gg2 = (row_ok && mx.quart) ? g2 / ((s2v + mx.eps) * (s2v + mx.eps) * Tm1 * s2v) : 0.f;
+  // row coefficients: combine the two column halves
+  sm.gx[wg][0][t] = g1;
+  sm.gx[wg][1][t] = g2;
   // G q by MMA: the Gram tiles (hi, lo per map) go to the dead key / value / W buffers; Z1 -> columns [0,64), Z2 -> [64,128)
-  __syncthreads();
-  copy_tile64(sm.K1, ws + w.gram + (size_t)bh * 2 * kT64);
-  copy_tile64(sm.K2, ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
+  copy_tile64(sm.K1[0], ws + w.gram + (size_t)bh * 2 * kT64);
+  copy_tile64(sm.K2[0], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
   if (mx.quart) {
-    copy_tile64(sm.V, ws + w.gram + (BH + bh) * 2 * kT64);
+    copy_tile64(sm.V[0], ws + w.gram + (BH + bh) * 2 * kT64);
     copy_tile64(sm.W1, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
   }
   publish();
   if (tid == 0) {
-    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1), smem_u32(sm.K2));
-    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V), smem_u32(sm.W1));
+    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1[0]), smem_u32(sm.K2[0]));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V[0]), smem_u32(sm.W1));
     mma_commit(&sm.bar);
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  const float Tm1 = (float)(T - 1);
+  const float g1t = sm.gx[0][0][t] + sm.gx[1][0][t], g2t = sm.gx[0][1][t] + sm.gx[1][1][t];
+  const float gg1 = row_ok ? g1t / ((s1v + mx.eps) * (s1v + mx.eps) * Tm1 * s1v) : 0.f;
+  const float gg2 = (row_ok && mx.quart) ? g2t / ((s2v + mx.eps) * (s2v + mx.eps) * Tm1 * s2v) : 0.f;
   for (int map = 0; map < w.nm; ++map) {
     const float gv = map ? gg2 : gg1;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(map ? p.dq2 : p.dq) + at(p, b, row_ok ? gi : 0, h);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {   // this warpgroup's 32 output columns
+      const int col = c0 + 16 * c;
       float acc[16], wv[16];
-      tmem_ld_32x32b_x16(tl + (map ? 256 : 192) + 16 * c, acc);
-      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + 16 * c, wv);
+      tmem_ld_32x32b_x16(tl + (map ? 256 : 192) + col, acc);
+      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + col, wv);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[e] = p.scale * acc[e] - p.scale * p.scale * gv * wv[e];
       if (row_ok) {
-        if (16 * c < dk) *reinterpret_cast<uint4*>(out + 16 * c) = pack8(acc);
-        if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(out + 16 * c + 8) = pack8(acc + 8);
+        if (col < dk) *reinterpret_cast<uint4*>(out + col) = pack8(acc);
+        if (col + 8 < dk) *reinterpret_cast<uint4*>(out + col + 8) = pack8(acc + 8);
       }
     }
-    if (row_ok) (reinterpret_cast<float*>(ws + w.gvec) + ((size_t)map * BH + bh) * T)[gi] = gv;
+    if (row_ok && wg == 0) (reinterpret_cast<float*>(ws + w.gvec) + ((size_t)map * BH + bh) * T)[gi] = gv;
   }
   // scalar partials of this query block
   sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
-  if (lane == 0) { sm.red[warp] = sc0; sm.red[4 + warp] = sc1; }
+  if (lane == 0) { sm.red[tid >> 5] = sc0; sm.red[8 + (tid >> 5)] = sc1; }
   __syncthreads();
   if (tid == 0) {
-    float* sp = reinterpret_cast<float*>(ws + w.spart) + (size_t)blockIdx.x * 2;
-    sp[0] = mx.m * (1.f - mx.m) * (sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3]);
-    sp[1] = sm.red[4] + sm.red[5] + sm.red[6] + sm.red[7];
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sm.red[i]; c += sm.red[8 + i]; }
+    float* sp = reinterpret_cast<float*>(ws + w.spart) + ((size_t)bh * nqb + qb) * 2;
+    sp[0] = mx.m * (1.f - mx.m) * a;
+    sp[1] = c;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tb);
+  if (tid < 32) tmem_dealloc<512>(tb);
 }
 
 // grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T
@@ -571,168 +602,170 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
 }
 
 struct __align__(128) SmemK {
-  unsigned char K1[kT128], K2[kT128], V[kT128], Q[kT64], Q2[kT64], dO[kT64], PT[kT128], W1T[kT128], W2T[kT128];
-  float i1s[64], i2s[64], lses[64], dlts[64];
+  unsigned char K1[kT128], K2[kT128], V[kT128], PT[kT128], W1T[kT128], W2T[kT128];
+  unsigned char Q[2][kT64], Q2[2][kT64], dO[2][kT64];   // double buffered query-side tiles
+  float vec[2][4][64];                                   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta
   uint64_t bar;
   uint32_t tmem_slot;
 };
 
-// grid: B*H*nqb (128 keys per CTA), 128 threads (thread per key), one CTA per SM
-// TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)
-__global__ void __launch_bounds__(128, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// grid: B*H*nqb (128 keys per CTA), 256 threads (thread per key row; two warpgroups split the 64 query columns of every
+// tile), one CTA per SM.  TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nkb = w.nqb;
-  const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;
-  const int k0 = kb * 128, gj = k0 + tid;
+  const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, T = p.T, nkb = w.nqb;
+  const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;   // early key blocks (most work) first
+  const int k0 = kb * 128, gj = k0 + t;
   const bool key_ok = gj < T;
   const int dks = (dk + 15) >> 4;
+  const int c0 = 32 * wg;
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
-  if (warp == 0) tmem_alloc<512>(&sm.tmem_slot);
+  if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
   const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
   const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
+  const __nv_bfloat16* qbase = reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h);
+  const __nv_bfloat16* q2base = mx.quart ? reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h) : nullptr;
+  const __nv_bfloat16* dybase = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h);
+  const float* stats = p.stats + ((size_t)b * p.H + h) * T * 3;
+  const float* delta = reinterpret_cast<const float*>(ws + w.delta) + (size_t)bh * T;
+  auto fetch = [&](int buf, int q0) {
+    load_act_tile_async<64>(sm.Q[buf], qbase, stride, q0, T, dk);
+    if (mx.quart) load_act_tile_async<64>(sm.Q2[buf], q2base, stride, q0, T, dk);
+    load_act_tile_async<64>(sm.dO[buf], dybase, stride, q0, T, dk);
+    if (tid < 64) {
+      const int i = min(q0 + tid, T - 1);
+      cp_async4(&sm.vec[buf][0][tid], stats + (size_t)i * 3);
+      cp_async4(&sm.vec[buf][1][tid], stats + (size_t)i * 3 + 1);
+      cp_async4(&sm.vec[buf][2][tid], stats + (size_t)i * 3 + 2);
+      cp_async4(&sm.vec[buf][3][tid], delta + i);
+    }
+    cp_async_commit();
+  };
+  fetch(0, k0);
   load_act_tile<128>(sm.K1, kc1, 64, k0, T, 64);
   if (mx.quart) load_act_tile<128>(sm.K2, kc2, 64, k0, T, 64);
   load_act_tile<128>(sm.V, reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h), stride, k0, T, dk);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
+  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float dum0 = 0.f, dum1 = 0.f;
-  bool first = true;
-  const __nv_bfloat16* qbase = reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h);
-  const __nv_bfloat16* q2base = mx.quart ? reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h) : nullptr;
-  const __nv_bfloat16* dybase = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h);
-  const __nv_bfloat16* ybase = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, 0, h);
-  for (int q0 = k0; q0 < T; q0 += 64) {   // queries i >= j only (k0 is a multiple of 64)
-    if (!first) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
-    load_act_tile<64>(sm.Q, qbase, stride, q0, T, dk);
-    if (mx.quart) load_act_tile<64>(sm.Q2, q2base, stride, q0, T, dk);
-    load_act_tile<64>(sm.dO, dybase, stride, q0, T, dk);
-    if (tid < 64) {
-      const int i = q0 + tid, ic = min(i, T - 1);
-      const float* st = p.stats + (((size_t)b * p.H + h) * T + ic) * 3;
-      sm.i1s[tid] = 1.f / (st[0] + mx.eps);
-      sm.i2s[tid] = mx.quart ? 1.f / (st[1] + mx.eps) : 0.f;
-      sm.lses[tid] = st[2];
-      float dl = 0.f;
-      if (i < T)
-        for (int d0 = 0; d0 < dk; d0 += 8) {
-          float a[8], c[8];
-          unpack8(*reinterpret_cast<const uint4*>(ybase + (size_t)i * stride + d0), a);
-          unpack8(*reinterpret_cast<const uint4*>(dybase + (size_t)i * stride + d0), c);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) dl = fmaf(a[e], c[e], dl);
-        }
-      sm.dlts[tid] = dl;
+  const int ntiles = (T - k0 + 63) >> 6;   // queries i >= j only (k0 is a multiple of 64)
+  for (int it = 0; it < ntiles; ++it) {
+    const int q0 = k0 + it * 64, buf = it & 1;
+    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // output MMAs of tile it-1 have read their tiles
+    if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();
+    if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place
+      sm.vec[buf][0][tid] = 1.f / (sm.vec[buf][0][tid] + mx.eps);
+      sm.vec[buf][1][tid] = mx.quart ? 1.f / (sm.vec[buf][1][tid] + mx.eps) : 0.f;
     }
     publish();
     if (tid == 0) {
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
-        mma_ss(tb, desc_kmajor(smem_u32(sm.K1), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.K2), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q2), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.V), 128, 16 * ks), desc_kmajor(smem_u32(sm.dO), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_kmajor(smem_u32(sm.K1), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.K2), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.V), 128, 16 * ks), desc_kmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int colb = c0 + 16 * c;
       float v1[16], v2[16], dp[16], pt[16], w1[16], w2[16];
-      tmem_ld_32x32b_x16(tl + 16 * c, v1);
-      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
-      tmem_ld_32x32b_x16(tl + 128 + 16 * c, dp);
+      tmem_ld_32x32b_x16(tl + colb, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + colb, v2);
+      tmem_ld_32x32b_x16(tl + 128 + colb, dp);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int col = 16 * c + e, gi = q0 + col;
+        const int col = colb + e, gi = q0 + col;
         const bool masked = gj > gi || gi >= T || !key_ok;
         float addm = 0.f;
-        if (p.add_mask && !masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
-        const float i1 = sm.i1s[col], i2 = sm.i2s[col];
-        const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, sm.lses[col], sm.dlts[col], masked, addm, &dum0, &dum1);
+        if constexpr (HAS_MASK)
+          if (!masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+        const float i1 = sm.vec[buf][0][col], i2 = sm.vec[buf][1][col];
+        const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, sm.vec[buf][2][col], sm.vec[buf][3][col], masked, addm, &dum0, &dum1);
         pt[e] = o.pr;
         w1[e] = o.dn1 * i1;
         w2[e] = o.dn2 * i2;
       }
-      *reinterpret_cast<uint4*>(sm.PT + (2 * c) * (128 * 16) + tid * 16) = pack8(pt);
-      *reinterpret_cast<uint4*>(sm.PT + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(pt + 8);
-      *reinterpret_cast<uint4*>(sm.W1T + (2 * c) * (128 * 16) + tid * 16) = pack8(w1);
-      *reinterpret_cast<uint4*>(sm.W1T + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w1 + 8);
+      const int ch = colb >> 3;
+      *reinterpret_cast<uint4*>(sm.PT + ch * (128 * 16) + t * 16) = pack8(pt);
+      *reinterpret_cast<uint4*>(sm.PT + (ch + 1) * (128 * 16) + t * 16) = pack8(pt + 8);
+      *reinterpret_cast<uint4*>(sm.W1T + ch * (128 * 16) + t * 16) = pack8(w1);
+      *reinterpret_cast<uint4*>(sm.W1T + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
       if (mx.quart) {
-        *reinterpret_cast<uint4*>(sm.W2T + (2 * c) * (128 * 16) + tid * 16) = pack8(w2);
-        *reinterpret_cast<uint4*>(sm.W2T + (2 * c + 1) * (128 * 16) + tid * 16) = pack8(w2 + 8);
+        *reinterpret_cast<uint4*>(sm.W2T + ch * (128 * 16) + t * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2T + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
       }
     }
     publish();
     if (tid == 0) {
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
-      const uint32_t acc0 = first ? 0u : 1u;
+      const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.dO), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q2), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q2[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
-    first = false;
   }
-  if (!first) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
-  // dV
+  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  // dV: this warpgroup's 32 columns
   __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + at(p, b, key_ok ? gj : 0, h);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
+    const int col = c0 + 16 * c;
     float acc[16];
-    if (first) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-    } else {
-      tmem_ld_32x32b_x16(tl + 192 + 16 * c, acc);
-      tmem_ld_wait();
-    }
+    tmem_ld_32x32b_x16(tl + 192 + col, acc);
+    tmem_ld_wait();
     if (key_ok) {
-      if (16 * c < dk) *reinterpret_cast<uint4*>(dv + 16 * c) = pack8(acc);
-      if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(dv + 16 * c + 8) = pack8(acc + 8);
+      if (col < dk) *reinterpret_cast<uint4*>(dv + col) = pack8(acc);
+      if (col + 8 < dk) *reinterpret_cast<uint4*>(dv + col + 8) = pack8(acc + 8);
     }
   }
-  // dkc = s W^T q - s^2 M kc   (fp32; centred by finish_kernel)
-  // M kc by MMA: the M tiles (hi, lo per map) go to the dead query / dO / PT buffers; Z1 -> columns [0,64), Z2 -> [64,128)
+  // M kc by MMA: the M tiles (hi, lo per map) go to the dead query / dO buffers; Z1 -> columns [0,64), Z2 -> [64,128)
   __syncthreads();
-  copy_tile64(sm.Q, ws + w.mmat + (size_t)bh * 2 * kT64);
-  copy_tile64(sm.Q2, ws + w.mmat + (size_t)bh * 2 * kT64 + kT64);
+  copy_tile64(sm.Q[0], ws + w.mmat + (size_t)bh * 2 * kT64);
+  copy_tile64(sm.Q[1], ws + w.mmat + (size_t)bh * 2 * kT64 + kT64);
   if (mx.quart) {
-    copy_tile64(sm.dO, ws + w.mmat + (BH + bh) * 2 * kT64);
-    copy_tile64(sm.PT, ws + w.mmat + (BH + bh) * 2 * kT64 + kT64);
+    copy_tile64(sm.dO[0], ws + w.mmat + (BH + bh) * 2 * kT64);
+    copy_tile64(sm.dO[1], ws + w.mmat + (BH + bh) * 2 * kT64 + kT64);
   }
   publish();
   if (tid == 0) {
-    mma_x_sym(tb, smem_u32(sm.K1), smem_u32(sm.Q), smem_u32(sm.Q2));
-    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.K2), smem_u32(sm.dO), smem_u32(sm.PT));
+    mma_x_sym(tb, smem_u32(sm.K1), smem_u32(sm.Q[0]), smem_u32(sm.Q[1]));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.K2), smem_u32(sm.dO[0]), smem_u32(sm.dO[1]));
     mma_commit(&sm.bar);
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
   for (int map = 0; map < w.nm; ++map) {
     float* out = reinterpret_cast<float*>(ws + w.dkc) + (((size_t)map * BH + bh) * T + (key_ok ? gj : 0)) * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int col = c0 + 16 * c;
       float acc[16], wv[16];
-      if (first) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-      } else {
-        tmem_ld_32x32b_x16(tl + (map ? 320 : 256) + 16 * c, acc);
-      }
-      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + 16 * c, wv);
+      tmem_ld_32x32b_x16(tl + (map ? 320 : 256) + col, acc);
+      tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + col, wv);
       tmem_ld_wait();
       if (key_ok) {
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4)
-          *reinterpret_cast<float4*>(out + 16 * c + 4 * e4) =
+          *reinterpret_cast<float4*>(out + col + 4 * e4) =
               make_float4(p.scale * acc[4 * e4] - p.scale * p.scale * wv[4 * e4], p.scale * acc[4 * e4 + 1] - p.scale * p.scale * wv[4 * e4 + 1],
                           p.scale * acc[4 * e4 + 2] - p.scale * p.scale * wv[4 * e4 + 2], p.scale * acc[4 * e4 + 3] - p.scale * p.scale * wv[4 * e4 + 3]);
       }
@@ -740,7 +773,7 @@ __global__ void __launch_bounds__(128, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tb);
+  if (tid < 32) tmem_dealloc<512>(tb);
 }
 
 // grid: B*H*nm, 256 threads.  dk = dkc - mean_j dkc ; map 0 also reduces the scalar partials of its (b,h)
