@@ -82,13 +82,13 @@ def edgewise_case(name, B, H, N, dk, V, r, impl, iters, flush, dtype=torch.bfloa
                 fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9)
 
 
-def quartet_case(name, B, H, T, dk, iters, flush, dtype=torch.bfloat16):
+def quartet_case(name, B, H, T, dk, impl, iters, flush, dtype=torch.bfloat16):
     ts = [torch.randn(B, T, H, dk, device="cuda", dtype=dtype, requires_grad=True) for _ in range(5)]
     mix = torch.tensor([-5.0], device="cuda", requires_grad=True)
     gam = torch.tensor([1.0], device="cuda", requires_grad=True)
     dy = torch.randn(B, T, H, dk, device="cuda", dtype=dtype)
     fl = B * H * 3 * T * T * dk
-    call = lambda: mop_b200.quartet_attention(ts[0], ts[1], ts[2], ts[3], ts[4], mix, gam)
+    call = lambda: mop_b200.quartet_attention(ts[0], ts[1], ts[2], ts[3], ts[4], mix, gam, impl=impl)
 
     def fb():
         call().backward(dy)
@@ -108,14 +108,17 @@ def main():
     pk, src = peak()
     rows = []
     rows.append(edgewise_case("M1/M2 Edgewise E (config 1/2 core)", 256, 4, 64, 56, 5, 4, None, a.iters, flush))
+    rows.append(edgewise_case("M3 Edgewise ViT-B/16 core", 256, 12, 196, 64, 5, 4, "tcgen05", max(3, a.iters // 2), flush))
+    rows.append(quartet_case("M4 Quartet GPT-1024 (B=16)", 16, 12, 1024, 64, "tcgen05", a.iters, flush))
+    rows.append(quartet_case("M4 Quartet GPT-4096 (B=4)", 4, 12, 4096, 64, "tcgen05", a.iters, flush))
     rows.append(sdpa_case("M1 MSA model A (config 1)", 256, 4, 64, 56, False, "tcgen05", a.iters, flush))
     rows.append(sdpa_case("M3 ViT-B/16 plain attention", 256, 12, 196, 64, False, "tcgen05", a.iters, flush))
     rows.append(sdpa_case("M5 Whisper encoder self-attention", 8, 16, 1500, 64, False, "tcgen05", a.iters, flush))
     rows.append(sdpa_case("GPT-1024 causal plain attention", 16, 12, 1024, 64, True, "tcgen05", a.iters, flush))
     if not a.quick:
-        rows.append(sdpa_case("M3 ViT-B/16 plain attention", 32, 12, 196, 64, False, "simt", max(3, a.iters // 4), flush))
-        rows.append(edgewise_case("M3 Edgewise ViT-B/16 core (fp32-mode kernels)", 8, 12, 196, 64, 5, 4, "simt", 3, flush))
-        rows.append(quartet_case("M4 Quartet T=1024 (fp32-mode kernels)", 2, 12, 1024, 64, 3, flush))
+        # the fp32-mode (CUDA-core) kernels on the same bf16 storage, reduced batch: what the tcgen05 paths replace
+        rows.append(edgewise_case("M3 Edgewise ViT-B/16 core (fp32-mode kernels, B=8)", 8, 12, 196, 64, 5, 4, "simt", 3, flush))
+        rows.append(quartet_case("M4 Quartet GPT-1024 (fp32-mode kernels, B=2)", 2, 12, 1024, 64, "simt", 3, flush))
     for r in rows:
         r["frac_of_bf16_peak_fwd_bwd"] = r["fwd_bwd_tflops"] / pk
         r["peak"] = f"{pk} TFLOP/s ({src})"
