@@ -121,77 +121,106 @@ __device__ __forceinline__ void load_act_tile(unsigned char* tile, const __nv_bf
   }
 }
 
-// G[64][64] (shared, fp32) = sum_t wgt[t] * x_t x_t^T over the rows of a bf16 matrix with row stride `stride`
-// (columns >= dk read as zero).  256 threads; `stage` is 64*64 floats of shared memory.
-__device__ inline void weighted_gram(float* G, float* stage, const __nv_bfloat16* x, size_t stride, const float* wgt, int T, int dk) {
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  float acc[4][4];
+// ---- 64 x 64 Gram-type matrices on the tensor core ----------------------------------------------------------
+// G = sum over 64-row chunks of A_chunk^T B_chunk with M = N = 64 (MN-major operands: the chunk's rows are the K
+// index), accumulated in TMEM (M=64 accumulator: lanes 0-15 of each sub-partition, read as 16x256b fragments).
+// The caller stages each chunk's operand tiles (chunk-major, R = 64) into one of kGramBufs shared buffers.
+constexpr int kGramBufs = 2;
+struct GramPipe {
+  uint64_t bar[kGramBufs];
+  uint32_t tmem_slot;
+  uint32_t phase_bits;   // per-thread copy kept in a register by the caller
+};
+// after the last chunk: accumulator -> fp32 G[64][64] in shared memory (threads 0..127)
+__device__ inline void gram_readout(uint32_t tb, float* G) {
+  if (threadIdx.x < 128) {
+    const Frag f;
+    float v[32];
+    tmem_ld_16x256b_x8(tb + ((uint32_t)(32 * f.warp) << 16), v);
+    tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += 64) {
-    __syncthreads();
-    for (int idx = tid; idx < 64 * 8; idx += 256) {
-      const int r = idx >> 3, ch = idx & 7, t = t0 + r;
-      float f[8];
-      unpack8((t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(x + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) stage[r * 64 + ch * 8 + e] = f[e];
-    }
-    __syncthreads();
-    const int rows = min(64, T - t0);
-    for (int r = 0; r < rows; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(stage + r * 64 + 4 * ty);
-      float4 b = *reinterpret_cast<const float4*>(stage + r * 64 + 4 * tx);
-      if (wgt) { const float g = wgt[t0 + r]; b.x *= g; b.y *= g; b.z *= g; b.w *= g; }
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    for (int n = 0; n < 8; ++n) {
+      G[f.row_lo * 64 + f.col(n)] = v[4 * n];
+      G[f.row_lo * 64 + f.col(n) + 1] = v[4 * n + 1];
+      G[f.row_hi * 64 + f.col(n)] = v[4 * n + 2];
+      G[f.row_hi * 64 + f.col(n) + 1] = v[4 * n + 3];
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) G[(4 * ty + i) * 64 + 4 * tx + j] = acc[i][j];
-  __syncthreads();
 }
 
-// grid: B*H*nm, 256 threads
+// grid: B*H*nm, 256 threads.  kbar, kc = bf16(k - kbar) (written to the workspace and staged for the MMA),
+// G = Kc^T Kc from that rounded kc -> bf16 hi / lo tile images.
 __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ __align__(128) unsigned char tiles[kGramBufs][kT64];
   __shared__ __align__(16) float G[64 * 64];
-  __shared__ __align__(16) float stage[64 * 64];
-  __shared__ float part[4][64];
+  __shared__ float part[32][64];
   __shared__ float kbar[64];
+  __shared__ GramPipe gp;
   const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(map ? p.k2 : p.k) + at(p, b, 0, h);
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(map ? p.q2 : p.q) + at(p, b, 0, h);
   __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(ws + w.kc) + ((size_t)map * BH + bh) * T * 64;
+  if (tid < 32) tmem_alloc<64>(&gp.tmem_slot);
+  if (tid == 0) { for (int i = 0; i < kGramBufs; ++i) mbar_init(&gp.bar[i], 1); fence_mbar_init(); }
+  const int r0 = tid >> 3, ch = tid & 7;   // this thread: rows r0, r0 + 32, ... and the 8 columns of chunk ch
   {
-    const int d = tid & 63, sl = tid >> 6;
-    float s = 0.f;
-    if (d < dk)
-      for (int t = sl; t < T; t += 4) s += __bfloat162float(k[(size_t)t * stride + d]);
-    part[sl][d] = s;
-  }
-  __syncthreads();
-  if (tid < 64) kbar[tid] = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) / (float)T;
-  __syncthreads();
-  for (int idx = tid; idx < T * 8; idx += 256) {
-    const int t = idx >> 3, ch = idx & 7;
-    float f[8];
-    unpack8(ch * 8 < dk ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
+    float s[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = (ch * 8 + e < dk) ? f[e] - kbar[ch * 8 + e] : 0.f;
-    *reinterpret_cast<uint4*>(kc + (size_t)t * 64 + ch * 8) = pack8(f);
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    if (ch * 8 < dk)
+      for (int t = r0; t < T; t += 32) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[r0][ch * 8 + e] = s[e];
   }
-  __syncthreads();   // this CTA's kc rows are visible to all of its threads
-  weighted_gram(G, stage, kc, 64, nullptr, T, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 64) {
+    float s = 0.f;
+    for (int i = 0; i < 32; ++i) s += part[i][tid];
+    kbar[tid] = s / (float)T;
+  }
+  __syncthreads();
+  const uint32_t tb = gp.tmem_slot;
+  uint32_t phases = 0;
+  const int nchunks = (T + 63) >> 6;
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c % kGramBufs;
+    if (c >= kGramBufs) { mbar_wait(&gp.bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; }   // the MMAs that read this buffer are done
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = r0 + 32 * it, t = c * 64 + r;
+      float f[8];
+      unpack8((t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (t < T && ch * 8 + e < dk) ? f[e] - kbar[ch * 8 + e] : 0.f;
+      const uint4 u = pack8(f);
+      if (t < T) *reinterpret_cast<uint4*>(kc + (size_t)t * 64 + ch * 8) = u;
+      *reinterpret_cast<uint4*>(tiles[buf] + ch * 1024 + r * 16) = u;
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(64, 64, 1, 1), tl = smem_u32(tiles[buf]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(tl, 64, 16 * ks), desc_mnmajor(tl, 64, 16 * ks), id, (c > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&gp.bar[buf]);
+    }
+  }
+  {   // the last commit covers every MMA issued before it
+    const int buf = (nchunks - 1) % kGramBufs;
+    mbar_wait(&gp.bar[buf], (phases >> buf) & 1u);
+    tc_fence_after();
+  }
+  gram_readout(tb, G);
+  tc_fence_before();
+  __syncthreads();
   write_hilo_tiles(G, ws + w.gram + ((size_t)map * BH + bh) * 2 * kT64);
+  if (tid < 32) tmem_dealloc<64>(tb);
 }
 
 // mixed score of one element from the raw MMA dot products (natural units); masks applied by the caller
@@ -589,16 +618,63 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   if (tid < 32) tmem_dealloc<512>(tb);
 }
 
-// grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T
+// grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T = (g q)^T q on the tensor core, g q split into bf16 hi + lo
 __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
-  __shared__ __align__(16) float G[64 * 64];
-  __shared__ __align__(16) float stage[64 * 64];
-  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H;
-  const size_t BH = (size_t)p.B * p.H;
+  __shared__ __align__(128) unsigned char tiles[1][3][kT64];   // [g q hi | g q lo | q] (single buffer: several CTAs share an SM)
+  __shared__ GramPipe gp;
+  float* G = reinterpret_cast<float*>(&tiles[0][0][0]);        // 16 KB: read out once every MMA has completed
+  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(map ? p.q2 : p.q) + at(p, b, 0, h);
-  const float* gv = reinterpret_cast<const float*>(ws + w.gvec) + ((size_t)map * BH + bh) * p.T;
-  weighted_gram(G, stage, q, (size_t)p.H * p.dk, gv, p.T, p.dk);
+  const float* gv = reinterpret_cast<const float*>(ws + w.gvec) + ((size_t)map * BH + bh) * T;
+  if (tid < 32) tmem_alloc<64>(&gp.tmem_slot);
+  if (tid == 0) { mbar_init(&gp.bar[0], 1); mbar_init(&gp.bar[1], 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = gp.tmem_slot;
+  const int r0 = tid >> 3, ch = tid & 7;
+  uint32_t phases = 0;
+  const int nchunks = (T + 63) >> 6;
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = 0;
+    if (c >= 1) { mbar_wait(&gp.bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = r0 + 32 * it, t = c * 64 + r;
+      const bool ok = t < T && ch * 8 < dk;
+      const uint4 raw = ok ? *reinterpret_cast<const uint4*>(q + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+      const float g = t < T ? gv[t] : 0.f;
+      float f[8], hi[8], lo[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = g * f[e];
+        hi[e] = __bfloat162float(__float2bfloat16_rn(x));
+        lo[e] = x - hi[e];
+      }
+      *reinterpret_cast<uint4*>(tiles[buf][0] + ch * 1024 + r * 16) = pack8(hi);
+      *reinterpret_cast<uint4*>(tiles[buf][1] + ch * 1024 + r * 16) = pack8(lo);
+      *reinterpret_cast<uint4*>(tiles[buf][2] + ch * 1024 + r * 16) = raw;
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(64, 64, 1, 1);
+      const uint32_t th = smem_u32(tiles[buf][0]), tlo = smem_u32(tiles[buf][1]), tq = smem_u32(tiles[buf][2]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(th, 64, 16 * ks), desc_mnmajor(tq, 64, 16 * ks), id, (c > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(tlo, 64, 16 * ks), desc_mnmajor(tq, 64, 16 * ks), id, 1u);
+      mma_commit(&gp.bar[buf]);
+    }
+  }
+  mbar_wait(&gp.bar[0], phases & 1u);
+  tc_fence_after();
+  gram_readout(tb, G);
+  tc_fence_before();
+  __syncthreads();
   write_hilo_tiles(G, ws + w.mmat + ((size_t)map * BH + bh) * 2 * kT64);
+  if (tid < 32) tmem_dealloc<64>(tb);
 }
 
 struct __align__(128) SmemK {
