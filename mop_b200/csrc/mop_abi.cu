@@ -12,8 +12,8 @@
 #include "edgewise_tc_large_bwd.cuh"
 #include "quartet_simt.cuh"
 #include "quartet_tc.cuh"
+#include "sdpa_tc2.cuh"
 #include "sdpa_simt.cuh"
-#include "sdpa_tc.cuh"
 #include "tc_selftest.cuh"
 
 namespace mop {
@@ -231,15 +231,16 @@ int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
   int rc = check_sdpa(p, false);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  const bool tc_ok = sdpatc::supported(p);
+  const bool tc_ok = sdpa2::supported(p);
   MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
               "impl %d not available (tcgen05 path: bf16, dk%%8==0, dk<=64, 16-byte aligned rows)", p->impl);
   const int grid = p->B * p->H * ((p->Nq + sdpa::TQ - 1) / sdpa::TQ);
   cudaStream_t st = (cudaStream_t)stream;
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem_tc = sizeof(sdpatc::SmemFwd) + 1024;
-    if ((rc = allow_smem(sdpatc::fwd_kernel, smem_tc))) return rc;
-    sdpatc::fwd_kernel<<<grid, 128, smem_tc, st>>>(*p);
+    const size_t smem_tc = sizeof(sdpa2::SmemF) + 128;
+    const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
+    if ((rc = allow_smem(extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>, smem_tc))) return rc;
+    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 128, smem_tc, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
@@ -261,7 +262,7 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
   int rc = check_sdpa(p, true);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  const bool tc_ok = sdpatc::supported(p);
+  const bool tc_ok = sdpa2::supported(p);
   MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && tc_ok), MOP_EUNSUPPORTED,
               "impl %d not available (tcgen05 path: bf16, dk%%8==0, dk<=64, 16-byte aligned rows)", p->impl);
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
@@ -269,13 +270,12 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
     MOP_REQUIRE(p->workspace && p->workspace_bytes >= need_tc, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need_tc);
     float* delta = reinterpret_cast<float*>(p->workspace);
     cudaStream_t st2 = (cudaStream_t)stream;
-    const size_t smem_tc = sizeof(sdpatc::SmemBwd) + 1024;
-    if ((rc = allow_smem(sdpatc::bwd_dkdv_kernel, smem_tc))) return rc;
-    if ((rc = allow_smem(sdpatc::bwd_dq_kernel, smem_tc))) return rc;
-    const int rows = p->B * p->Nq * p->H;
-    sdpatc::delta_kernel<<<(rows + 7) / 8, 256, 0, st2>>>(*p, delta);
-    sdpatc::bwd_dkdv_kernel<<<p->B * p->H * ((p->Nk + 63) / 64), 128, smem_tc, st2>>>(*p, delta);
-    sdpatc::bwd_dq_kernel<<<p->B * p->H * ((p->Nq + 63) / 64), 128, smem_tc, st2>>>(*p, delta);
+    const size_t smem_q = sizeof(sdpa2::SmemQ) + 128, smem_k = sizeof(sdpa2::SmemK) + 128;
+    const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
+    if ((rc = allow_smem(extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>, smem_q))) return rc;
+    if ((rc = allow_smem(extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>, smem_k))) return rc;
+    (extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta);
+    (extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>)<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
