@@ -166,9 +166,13 @@ def run_ours(args):
     torch.manual_seed(0)
     model = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **MODEL).to(dev)
     model.train()
+    # N > 1: every p.grad is a view into one flat buffer and the step does ONE all-reduce (mean) after backward, so that
+    # the whole step, collective included, is captured in a CUDA graph (mop_b200/ddp.py).  --no-graph: torch DDP, eager.
+    use_graph = not args.no_graph
+    from mop_b200.ddp import FlatGradAllReduce
+    flat = FlatGradAllReduce(model) if (ddp and use_graph) else None
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
-                                                    gradient_as_bucket_view=True) if ddp else model
-    use_graph = (not ddp) and not args.no_graph
+                                                    gradient_as_bucket_view=True) if (ddp and not use_graph) else model
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True, capturable=use_graph)
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
     x_host = torch.randn(BATCH, 3, IMG, IMG, generator=gen).pin_memory()
@@ -176,16 +180,26 @@ def run_ours(args):
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(x, y):
-        opt.zero_grad(set_to_none=True)
+    def fwd_bwd(x, y):
+        if flat is not None:
+            flat.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = F.cross_entropy(net(x), y)
         loss.backward()
+        return loss
+
+    def step(x, y):
+        loss = fwd_bwd(x, y)
+        if flat is not None:
+            flat.reduce()
         opt.step()
         return loss
 
-    # ---- optional: the whole step (fwd + loss + bwd + AdamW) captured once in a CUDA graph and replayed -------
-    graph = None
+    # ---- the step captured in CUDA graphs and replayed.  N = 1: one graph (fwd + loss + bwd + AdamW).  N > 1: graph A
+    #      (fwd + loss + bwd into the flat gradient buffer), ONE eager NCCL all-reduce, graph B (scale + AdamW).
+    graph = graph_b = None
     if use_graph:
         static_x, static_y = x_dev.clone(), y_dev.clone()
         side = torch.cuda.Stream()
@@ -196,9 +210,17 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
-            static_loss = step(static_x, static_y)
+        if flat is None:
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = step(static_x, static_y)
+        else:
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd(static_x, static_y)
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b):
+                flat.scale()
+                opt.step()
         eager_step = step
 
         def step(x, y):  # noqa: F811  (same signature; inputs are copied into the graph's static buffers)
@@ -206,6 +228,9 @@ def run_ours(args):
                 static_x.copy_(x, non_blocking=True)
                 static_y.copy_(y, non_blocking=True)
             graph.replay()
+            if graph_b is not None:
+                flat.all_reduce_sum()
+                graph_b.replay()
             return static_loss
         x_dev, y_dev = static_x, static_y
 

@@ -47,3 +47,41 @@ def test_sharded_gradients_match_full_batch(tmp_path):
     for a, p in zip(got["grads"], model.parameters()):
         assert torch.allclose(a, p.grad, atol=1e-6)
     assert got["slow"] == 2.0
+
+
+def _worker_flat(rank, world, port, out):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from mop_b200 import ddp
+    ddp.init("gloo")
+    torch.manual_seed(rank)   # different initial weights per rank: the constructor broadcasts rank 0's
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    flat = ddp.FlatGradAllReduce(model)
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    lo, hi = ddp.shard_bounds(10, rank, world)
+    for _ in range(2):   # the second pass checks zero(): gradients must not accumulate across steps
+        flat.zero()
+        loss = torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi], reduction="sum") / 10 * world
+        loss.backward()
+        flat.reduce()
+    assert all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in model.parameters())   # still views of the flat buffer
+    if rank == 0:
+        torch.save({"grads": [p.grad.clone() for p in model.parameters()], "w": [p.detach().clone() for p in model.parameters()]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_matches_full_batch(tmp_path):
+    """FlatGradAllReduce (one flat buffer, one all-reduce; the multi-GPU bench path) == full-batch gradients."""
+    out = str(tmp_path / "f.pt")
+    mp.spawn(_worker_flat, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    for a, p in zip(got["w"], model.parameters()):
+        assert torch.equal(a, p.detach())
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()
+    for a, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(a, p.grad, atol=1e-6)
