@@ -40,7 +40,7 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 struct Ws {  // byte offsets into the workspace
-  size_t kc, sig, gram, gvec, mmat, dkc, spart, delta, total;
+  size_t kc, gram, gvec, mmat, dkc, spart, delta, total;
   int nm, nqb;
 };
 __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
@@ -51,7 +51,6 @@ __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
   w.kc = take(w.nm * BH * T * 64 * 2);       // bf16 [nm][BH][T][64] (columns >= dk are zero)
-  w.sig = take(w.nm * BH * T * 4);           // fp32 [nm][BH][T]
   w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
   w.gvec = w.mmat = w.dkc = w.spart = w.delta = 0;
   if (backward) {
