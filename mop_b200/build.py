@@ -29,7 +29,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, os.path.join(CSRC, "mop_abi.cu"), "-lcuda"]
+    extra = os.environ.get("MOP_NVCC_EXTRA", "").split()   # e.g. -DMOP_PHASE_TIMING (development only)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", OUT, os.path.join(CSRC, "mop_abi.cu"), "-lcuda"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -4,7 +4,8 @@
 // (batch, head) problem at a time, M=128 row blocks, one thread per row of every fp32 accumulator.  The backward
 // touches ~25 N x N maps per problem, far more than fits on chip, so every map that is needed again later is kept
 // as a bf16 tile image in a per-CTA scratch region of the caller's workspace (27 slots x 86.5 KB; written by the
-// owning threads or by cp.async.bulk, read back by cp.async.bulk straight into the operand buffer).  Nothing in
+// owning threads, read back by the whole CTA with cp.async straight into the operand buffer, overlapped with the
+// epilogues wherever the target buffer is free early).  Nothing in
 // the scratch is shared between CTAs and nothing survives the launch.
 //
 // Phases per problem (executable specification: oracle/edgewise_manual.py):
@@ -23,6 +24,12 @@
 //      contributions never have to be summed as maps).
 #pragma once
 #include "edgewise_tc_large.cuh"
+
+#ifdef MOP_PHASE_TIMING
+#define MOP_TS(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0) printf("ts %s %lld\n", #name, clock64()); } while (0)
+#else
+#define MOP_TS(name) do { } while (0)
+#endif
 
 namespace mop {
 namespace ewl {
@@ -54,7 +61,6 @@ struct __align__(128) SmemBwd {
   float vsum[2][64];              // sum_j dV_1[j,d] V[j,d], sum_j (F^T dY)[j,d] V[j,d]
   float amean[kMaxQ];             // mean over tokens of the row gate factors a[q][.]
   uint64_t bar[2];
-  uint64_t ldbar;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemBwd) <= 232448, "backward shared memory over the 227 KB limit");
@@ -104,14 +110,14 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
   auto slot = [&](int s) -> unsigned char* { return scratch + (size_t)s * kBufA; };
 
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.ldbar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = sm.tmem_slot;
   const uint32_t tD = tbase + 256u * (uint32_t)wg;
   const uint32_t tl = tD + ((uint32_t)(32 * warp4) << 16);
-  uint32_t phase = 0, ldphase = 0;
+  uint32_t phase = 0;
   const float w = 1.f / (1.f + __expf(-p.chain_value_logit[0]));
   const float bn = p.beta_not / (float)max(1, V - 1);
   const float sscale = rsqrtf((float)dk);
@@ -119,15 +125,15 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
 
   auto mma_wait = [&]() { mbar_wait(&sm.bar[wg], phase); phase ^= 1; tc_fence_after(); };
   auto commit = [&]() { mma_commit(&sm.bar[wg]); };
-  // generic-proxy writes (shared and global) -> visible to the async proxy (MMA operand reads, bulk copies); CTA barrier
-  auto publish_cta = [&]() { fence_async_all(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
+  // generic-proxy shared-memory writes -> visible to the async proxy (MMA operand reads); CTA barrier.  Scratch maps in
+  // global memory are written and read back (cp.async, ld.global.cg) through the generic proxy: the barrier orders them.
+  auto publish_cta = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
   auto publish_wg = [&]() { fence_async_smem(); tc_fence_before(); wg_sync(wg); tc_fence_after(); };
   auto sync_cta = [&]() { tc_fence_before(); __syncthreads(); tc_fence_after(); };
-  // bulk load of a scratch map into the A buffer (or an X image into the X buffer); every thread waits
-  auto load_start = [&](void* dst, const void* src, uint32_t bytes) {
-    if (tid == kSpillThread) { mbar_expect_tx(&sm.ldbar, bytes); bulk_g2s(dst, src, bytes, &sm.ldbar); }
-  };
-  auto load_wait = [&]() { mbar_wait(&sm.ldbar, ldphase); ldphase ^= 1; };
+  // load of a scratch map into the A buffer (or of an X image into the X buffer) by the whole CTA; every thread waits
+  // (measured: one cp.async.bulk of 86 KB took ~25k cycles - 4 B/cycle; 256 threads x cp.async 16 B move it ~10x faster)
+  auto load_start = [&](void* dst, const void* src, uint32_t bytes) { cp_async_block(dst, src, bytes); cp_async_commit(); };
+  auto load_wait = [&]() { cp_async_wait<0>(); fence_async_smem(); __syncthreads(); };
   // D[rows of this block, NN] = Xtile[rows] * (A buffer, K index = its rows)          (forward chain step)
   auto mma_x_a = [&]() {
     const uint32_t id = idesc_bf16(128, NN, 0, 1);
@@ -236,6 +242,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       }
       if (logs) rowmean = ls * invN;
     };
+    MOP_TS(T0);
     // =================================================================================================
     // phase 1a: pass R (views V-1 .. 0)
     // =================================================================================================
@@ -247,7 +254,6 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         for (int ch = 0; ch < 8; ++ch)
           *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = scale_chunk(kraw[ch], &sm.cvec[k][ch * 8]);
       }
-      if (tid == kSpillThread && !first) bulk_wait_read();
       publish_cta();
       if (blk_on) {
         if (t == 0) {
@@ -309,6 +315,8 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
           if (row < kRA) {
             *reinterpret_cast<uint4*>(sm.A + (2 * c) * (kRA * 16) + row * 16) = lo;
             *reinterpret_cast<uint4*>(sm.A + (2 * c + 1) * (kRA * 16) + row * 16) = hi;
+            *reinterpret_cast<uint4*>(map_chunk(kSlotA + k, 2 * c)) = lo;       // A_k is needed again by pass F and the sweeps
+            *reinterpret_cast<uint4*>(map_chunk(kSlotA + k, 2 * c + 1)) = hi;
           }
           if (first && row < kRX) {
             *reinterpret_cast<uint4*>(sm.X + (2 * c) * (kRX * 16) + row * 16) = lo;
@@ -319,7 +327,6 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
       }
       publish_cta();
-      if (tid == kSpillThread) bulk_s2g(slot(kSlotA + k), sm.A, map_bytes);
       if (first) continue;
       if (blk_on) {
         if (t == 0) { mma_x_a(); commit(); }
@@ -332,11 +339,11 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
               row < kRA ? *reinterpret_cast<const uint4*>(sm.A + c * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0);
       }
     }
+    MOP_TS(T1);
     // =================================================================================================
     // phase 1b: pass F (views 1 .. V-1)
     // =================================================================================================
     publish_cta();
-    if (tid == kSpillThread) { bulk_wait_all(); fence_async_all(); }
     load_start(sm.A, slot(kSlotA + 1), map_bytes);
     for (int k = 1; k < V; ++k) {
       const bool last = k == V - 1;
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       if (!last) publish_cta();
     }
     publish_cta();   // F in X and in its slot; colsum final; A and K buffers free
+    MOP_TS(T2);
     // =================================================================================================
     // gate factors; delta = dY . (y - F w V_V)
     // =================================================================================================
@@ -407,6 +415,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         if (lane == 0 && asum != 0.f) atomicAdd(&sm.amean[qq], asum);
       }
     }
+    MOP_TS(T2a);
     // exact (fp32) column sums of the four gate pre-activation gradients, accumulated in phase 2: [4][208] in the K region
     float* cs_s = reinterpret_cast<float*>(sm.K);
     for (int idx = tid; idx < 4 * kNmax; idx += 256) cs_s[idx] = 0.f;
@@ -427,6 +436,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       lse2 = st2.x;          // integer reference exponent (base 2) of this row of the mixed map
       inv_lmix = 1.f / st2.y;   // 1 / sum of the bf16-rounded exp2(mix - reference)
     }
+    MOP_TS(T2b);
     sync_cta();   // X (F) and the value tile are free
     // dY tile (A operand of dA = dY V_1^T, B operand of the value-gradient MMAs), V_1 tile
     unsigned char* dYt = sm.X + kOffDy;
@@ -440,6 +450,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
     }
     load_values(Vt, sm.vs1);
     publish_cta();
+    MOP_TS(T3);
     // =================================================================================================
     // phase 2: mixed-map backward over 32-column panels
     // =================================================================================================
@@ -577,6 +588,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       }
     }
     sync_cta();   // phase-2 MMAs complete: A buffer (value tile, key panels, b factors) and the dY tile region are reusable
+    MOP_TS(T4);
     // =================================================================================================
     // phase 3: db = sum_t dG_t^T a (MMA), head-parameter partials, feature-mean gradients
     // =================================================================================================
@@ -614,6 +626,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       }
       sync_cta();   // both warpgroups' MMAs have read the map
     }
+    MOP_TS(T4a);
     float db[kMaxQ];
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) db[q] = 0.f;
@@ -654,6 +667,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
     float* cprime_s = &sm.colsum[0][0];
     float* dkapF_s = &sm.colsum[kMaxV][0];
     float* dkapR_s = &sm.colsum[kMaxV + 1][0];
+    MOP_TS(T4b);
     // dS_k[i,j] += rterm_k[i] + cprime_k[j]:  channel k is S_k, channel V+k is S_k^T (row/column roles swapped)
     float rterm[kMaxV];
 #pragma unroll
@@ -685,6 +699,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
       }
     }
     sync_cta();
+    MOP_TS(T5);
     // =================================================================================================
     // phase 4: dV = (A^T dY) vs_1 + (F^T dY) w vs_V ; v_scale partials ; chain_value_logit partial
     // =================================================================================================
@@ -744,6 +759,7 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         ds[idx] = val;
       }
     }
+    MOP_TS(T6);
     // =================================================================================================
     // phase 5 / 6: chain seeds, sweeps and contributions
     // =================================================================================================
@@ -808,7 +824,9 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
     float* dq_acc = reinterpret_cast<float*>(slot(kSlotAcc)) + (size_t)row * 64;
     float* dk_acc = reinterpret_cast<float*>(slot(kSlotAcc + 1)) + (size_t)row * 64;
     // C (bf16, all rows, in the A buffer) is one additive part of dS_k:  T = C K -> dQ, scale sums ; U = C^T Q -> dK
-    auto contribute = [&](int k) {
+    // next_slot >= 0: once both warpgroups' MMAs have read C, that scratch map starts to load into the A buffer, so that its
+    // latency hides behind the epilogue (the caller waits for it with load_wait before the next use of the A buffer).
+    auto contribute = [&](int k, int next_slot) {
       publish_cta();   // C rows written by their owners
       if (blk_on) {
         if (t == 0) {
@@ -817,6 +835,12 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
           commit();
         }
         mma_wait();
+      }
+      if (next_slot >= 0) {
+        sync_cta();
+        load_start(sm.A, slot(next_slot), map_bytes);
+      }
+      if (blk_on) {
         if (warp_on) {
           // T part: dQ rows (fp32 partial sums live in the scratch; all loads are issued before the first use)
 #pragma unroll
@@ -899,59 +923,66 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
     };
     // one sweep: X holds the seed.  order[s] = view visited at step s (V-1 steps), pslot(s) = scratch slot of the
     // partial product multiplying X from the left (transposed); last_view = view of the final link (dA += X).
-    auto sweep = [&](bool fchain) {
+    // One sweep.  On entry X holds the seed (written by its row owners) and the load of the first view's A_k into the A
+    // buffer is in flight; on exit the load of `next_slot` is in flight.  Loads are issued as early as their target buffer
+    // is free so that they overlap the epilogues: P during the X' stash, X' during the softmax backward + contribution,
+    // the next A_k during the contribution's epilogue.
+    auto sweep = [&](bool fchain, int next_slot) {
       for (int s = 0; s < V - 1; ++s) {
         const int k = fchain ? V - 1 - s : s;
+        const int knext = fchain ? k - 1 : k + 1;   // view of the next step (or of the final link)
         int pslot;
         if (fchain) pslot = (k - 1 == 0) ? kSlotA + 0 : kSlotPfx + (k - 1) - 1;                 // P_{k-1}
         else pslot = (k + 1 == V - 1) ? kSlotA + V - 1 : kSlotSfx + (k + 1) - 1;               // A_{V-1}..A_{k+1}
-        publish_cta();   // X rows (seed or reloaded image) visible; A buffer free
-        load_start(sm.A, slot(kSlotA + k), map_bytes);
-        load_wait();
+        cp_async_wait<0>();
+        publish_cta();   // A_k and X (seed or reloaded image) landed / visible
         if (blk_on) {
           if (t == 0) { mma_x_at(); commit(); }     // X' = X A_k^T
           mma_wait();
-          if (warp_on) {
-            for (int c = 0; c < KS; ++c) {
-              float v[16];
-              tmem_ld_32x32b_x16(tl + 16 * c, v);
-              tmem_ld_wait();
-              if (row < kRX) {
-                uint4 lo, hi;
-                pack16(v, 1.f, lo, hi);
-                if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c) * (kRX * 16) + row * 16) = lo;
-                *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c + 1) * (kRX * 16) + row * 16) = hi;
-              }
-            }
-          }
         }
         sync_cta();      // both warpgroups' MMAs have read A_k
         load_start(sm.A, slot(pslot), map_bytes);
-        load_wait();
+        if (warp_on) {
+          for (int c = 0; c < KS; ++c) {
+            float v[16];
+            tmem_ld_32x32b_x16(tl + 16 * c, v);
+            tmem_ld_wait();
+            if (row < kRX) {
+              uint4 lo, hi;
+              pack16(v, 1.f, lo, hi);
+              if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c) * (kRX * 16) + row * 16) = lo;
+              *reinterpret_cast<uint4*>(slot(kSlotXN) + (size_t)(2 * c + 1) * (kRX * 16) + row * 16) = hi;
+            }
+          }
+        }
+        cp_async_wait<0>();
+        publish_cta();   // P landed; the X' image is complete in the scratch
         if (blk_on) {
           if (t == 0) { mma_at_x(); commit(); }     // dA_k part = P^T X
           mma_wait();
         }
-        sync_cta();      // A buffer (P) free: A_k comes back and is turned into C in place
+        sync_cta();      // A buffer (P) and X are free: A_k comes back (turned into C in place), X' replaces X
         load_start(sm.A, slot(kSlotA + k), map_bytes);
-        load_wait();
-        softmax_bwd_row(true);
-        contribute(k);   // (publishes; leaves the A buffer free)
-        // X <- X'
-        publish_cta();   // X' rows in the scratch visible to the bulk copy; nobody reads X any more
         load_start(sm.X, slot(kSlotXN), xmap_bytes);
-        load_wait();
+        cp_async_wait<1>();   // A_k only
+        fence_async_smem();
+        __syncthreads();
+        softmax_bwd_row(true);
+        contribute(k, kSlotA + knext);
       }
-      // final link
+      // final link: dA += X
       const int kl = fchain ? 0 : V - 1;
-      sync_cta();
-      load_start(sm.A, slot(kSlotA + kl), map_bytes);
-      load_wait();
+      cp_async_wait<0>();
+      fence_async_smem();
+      __syncthreads();   // A_kl and the last X' landed
       softmax_bwd_row(false);
-      contribute(kl);
+      contribute(kl, next_slot);
     };
-    sweep(true);
+    MOP_TS(T7);
+    sync_cta();
+    load_start(sm.A, slot(kSlotA + V - 1), map_bytes);   // first view of the F sweep
+    sweep(true, kSlotA + 0);                              // ... and of the R sweep
     // seed of the R sweep: X = (drho_R[i] + dkap_R[j]) / (R + eps)
     if (row < kRX) {
       uint4 rnext[2];
@@ -969,11 +1000,12 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
         *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) = pack8(r8);
       }
     }
-    sweep(false);
+    MOP_TS(T8pre);
+    sweep(false, kSlotDS + 0);
+    MOP_TS(T9);
     // direct parts + rank-1 feature terms
     for (int k = 0; k < V; ++k) {
-      load_start(sm.A, slot(kSlotDS + k), map_bytes);
-      load_wait();
+      load_wait();   // the direct part of dS_k (its load was started by the previous contribution)
       if (row_ok) {
         float rt = 0.f;
 #pragma unroll
@@ -991,8 +1023,9 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams 
           *reinterpret_cast<uint4*>(ptr) = pack8(v8);
         }
       }
-      contribute(k);
+      contribute(k, k + 1 < V ? kSlotDS + k + 1 : -1);
     }
+    MOP_TS(T10);
     // =================================================================================================
     // outputs: dQ, dK rows; q/k scale partials
     // =================================================================================================

@@ -225,13 +225,6 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
 // mixed score of one element from the raw MMA dot products (natural units); masks applied by the caller
 __device__ __forceinline__ float mix_n(const Mix& x, float n1, float n2) { return x.quart ? n1 * ((1.f - x.m) + x.m * x.gam * n2) : n1; }
 
-// 16-byte global -> shared copy without registers (zero fill when !valid); completion tracked by cp.async groups
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t n = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int R>
 __device__ __forceinline__ void load_act_tile_async(unsigned char* tile, const __nv_bfloat16* base, size_t stride, int row0, int T, int dk) {
   for (int idx = threadIdx.x; idx < R * 8; idx += blockDim.x) {
@@ -684,9 +677,6 @@ struct __align__(128) SmemK {
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
 
 // grid: B*H*nqb (128 keys per CTA), 256 threads (thread per key row; two warpgroups split the 64 query columns of every
 // tile), one CTA per SM.  TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)

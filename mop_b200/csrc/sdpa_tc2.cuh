@@ -19,9 +19,6 @@ namespace mop {
 namespace sdpa2 {
 
 using namespace tc;
-using qtc::cp_async4;
-using qtc::cp_async_commit;
-using qtc::cp_async_wait;
 using qtc::ex2;
 using qtc::kLn2;
 using qtc::kLog2e;

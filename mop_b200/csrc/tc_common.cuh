@@ -60,6 +60,23 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes performed
 
+// ---- cp.async (LDGSTS): per-thread 16 / 4 byte global -> shared copies tracked by commit / wait groups ------------
+// 16-byte global -> shared copy without registers (zero fill when !valid); completion tracked by cp.async groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// contiguous block global -> shared by the whole CTA (16-byte pieces, L2-only); caller commits / waits
+__device__ __forceinline__ void cp_async_block(void* smem_dst, const void* gsrc, uint32_t bytes) {
+  for (uint32_t off = threadIdx.x * 16u; off < bytes; off += blockDim.x * 16u)
+    cp_async16(reinterpret_cast<unsigned char*>(smem_dst) + off, reinterpret_cast<const unsigned char*>(gsrc) + off, true);
+}
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
