@@ -75,6 +75,7 @@ struct SmemVec {
   float vs1[64], vsL[64];
   float red[kMaxV + 2][4][64];      // cross-warp column sums
   float scal[8];
+  float hw[2][kMaxQ * kMaxC + kMaxQ];   // gate-head weights + biases of the row / column projection (staged once per CTA)
   uint64_t bar;
   uint32_t tmem_slot;
 };
@@ -242,6 +243,15 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
   const size_t hd = (size_t)H * dk;
   const int G = p.B * H;
+  {   // head weights: read through L2 once per CTA instead of once per use
+    const int nW = 4 * r * C;
+    for (int idx = tid; idx < 2 * (nW + 4 * r); idx += 128) {
+      const int half = idx / (nW + 4 * r), rem = idx % (nW + 4 * r);
+      sv_.hw[half][rem] = rem < nW ? (half ? p.col_w : p.row_w)[rem] : (half ? p.col_b : p.row_b)[rem - nW];
+    }
+    __syncthreads();
+  }
+  const int hw_bias = 4 * r * C;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
     // =================================================================================================
@@ -361,21 +371,21 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
     // =================================================================================================
     {
       const int which = tid >> 6, tok = tid & 63;  // 0: a (row factors), 1: b (column factors)
-      const float* W = which ? p.col_w : p.row_w;
-      const float* bias = which ? p.col_b : p.row_b;
+      const float* W = sv_.hw[which];
+      const float* bias = W + hw_bias;
       float (*own)[64] = which ? sv_.kap : sv_.rho;
       float (*swp)[64] = which ? sv_.rho : sv_.kap;
       for (int qq = 0; qq < kMaxQ; ++qq) {  // slot qq = 4t + k  <->  reference row q = t*r + k
         const int t = qq >> 2, k = qq & 3, q = t * r + k;
         float acc = 0.f;
         if (k < r) {
-          acc = __ldg(bias + q);
+          acc = bias[q];
           for (int c = 0; c < V; ++c) {
-            acc = fmaf(__ldg(W + q * C + c), own[c][tok], acc);
-            acc = fmaf(__ldg(W + q * C + V + c), swp[c][tok], acc);
+            acc = fmaf(W[q * C + c], own[c][tok], acc);
+            acc = fmaf(W[q * C + V + c], swp[c][tok], acc);
           }
-          acc = fmaf(__ldg(W + q * C + 2 * V), own[2 * V][tok], acc);
-          acc = fmaf(__ldg(W + q * C + 2 * V + 1), own[2 * V + 1][tok], acc);
+          acc = fmaf(W[q * C + 2 * V], own[2 * V][tok], acc);
+          acc = fmaf(W[q * C + 2 * V + 1], own[2 * V + 1][tok], acc);
         }
         (which ? sv_.b : sv_.a)[qq][tok] = acc;
         if constexpr (BWD)
@@ -613,8 +623,8 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
           const int t = qq >> 2, k = qq & 3;
           if (k < r) {
             const int q = t * r + k;
-            sr = fmaf(__ldg(p.row_w + q * C + c), bv_.da[qq][tok], sr);
-            sc = fmaf(__ldg(p.col_w + q * C + c), sv_.b[qq][tok], sc);
+            sr = fmaf(sv_.hw[0][q * C + c], bv_.da[qq][tok], sr);
+            sc = fmaf(sv_.hw[1][q * C + c], sv_.b[qq][tok], sc);
           }
         }
         bv_.drho[c][tok] = sr * (1.f / 64.f);

@@ -74,6 +74,17 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
   __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(p.dqkv);
   const size_t hd = (size_t)H * dk;
   const int G = p.B * H;
+  {   // head weights: read through L2 once per CTA instead of once per use
+    const int nW = 4 * r * C;
+    for (int idx = tid; idx < 2 * (nW + 4 * r); idx += 256) {
+      const int half = idx / (nW + 4 * r), rem = idx % (nW + 4 * r);
+      sv_.hw[half][rem] = rem < nW ? (half ? p.col_w : p.row_w)[rem] : (half ? p.col_b : p.row_b)[rem - nW];
+    }
+    __syncthreads();
+  }
+  const float* hw_row = sv_.hw[0];
+  const float* hw_col = sv_.hw[1];
+  const int hw_bias = 4 * r * C;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
     const size_t in_lo = (((size_t)pb * 64 + f.row_lo) * 3) * hd + (size_t)ph * dk;   // q row; +hd: k; +2hd: v
@@ -184,21 +195,21 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
     // ---- gate factors: thread = (a|b, token, half of the 16 slots) ------------------------------------------------
     {
       const int which = tid >> 7, tok = (tid & 127) >> 1, half = tid & 1;
-      const float* W = which ? p.col_w : p.row_w;
-      const float* bias = which ? p.col_b : p.row_b;
+      const float* W = which ? hw_col : hw_row;
+      const float* bias = W + hw_bias;
       float (*own)[64] = which ? sv_.kap : sv_.rho;
       float (*swp)[64] = which ? sv_.rho : sv_.kap;
       for (int qq = 8 * half; qq < 8 * half + 8; ++qq) {
         const int t = qq >> 2, k = qq & 3, q = t * r + k;
         float acc = 0.f;
         if (k < r) {
-          acc = __ldg(bias + q);
+          acc = bias[q];
           for (int c = 0; c < V; ++c) {
-            acc = fmaf(__ldg(W + q * C + c), own[c][tok], acc);
-            acc = fmaf(__ldg(W + q * C + V + c), swp[c][tok], acc);
+            acc = fmaf(W[q * C + c], own[c][tok], acc);
+            acc = fmaf(W[q * C + V + c], swp[c][tok], acc);
           }
-          acc = fmaf(__ldg(W + q * C + 2 * V), own[2 * V][tok], acc);
-          acc = fmaf(__ldg(W + q * C + 2 * V + 1), own[2 * V + 1][tok], acc);
+          acc = fmaf(W[q * C + 2 * V], own[2 * V][tok], acc);
+          acc = fmaf(W[q * C + 2 * V + 1], own[2 * V + 1][tok], acc);
         }
         (which ? sv_.b : sv_.a)[qq][tok] = acc;
         if (which == 0) *reinterpret_cast<__nv_bfloat16*>(bv_.a_bf + tile_off(64, tok, qq)) = __float2bfloat16_rn(acc);
@@ -437,8 +448,8 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
         const int t = qq >> 2, k = qq & 3;
         if (k < r) {
           const int q = t * r + k;
-          sr = fmaf(__ldg(p.row_w + q * C + c), bv_.da[qq][tok], sr);
-          sc = fmaf(__ldg(p.col_w + q * C + c), sv_.b[qq][tok], sc);
+          sr = fmaf(hw_row[q * C + c], bv_.da[qq][tok], sr);
+          sc = fmaf(hw_col[q * C + c], sv_.b[qq][tok], sc);
         }
       }
       bv_.drho[c][tok] = sr * (1.f / 64.f);
@@ -457,10 +468,23 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
           if (c < V) ft = half ? sv_.kap[c] : sv_.rho[c];
           else if (c < 2 * V) ft = half ? sv_.rho[c - V] : sv_.kap[c - V];
           else ft = half ? sv_.kap[c] : sv_.rho[c];
-          for (int i = 0; i < 64; ++i) s = fmaf(dv[qq][i], ft[i], s);
+          // four independent partial sums over float4 loads: the serial 64-step fma chain was shared-memory latency bound
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* dp = reinterpret_cast<const float4*>(dv[qq]);
+          const float4* fp = reinterpret_cast<const float4*>(ft);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 d4 = dp[i], f4 = fp[i];
+            a4.x = fmaf(d4.x, f4.x, a4.x); a4.y = fmaf(d4.y, f4.y, a4.y); a4.z = fmaf(d4.z, f4.z, a4.z); a4.w = fmaf(d4.w, f4.w, a4.w);
+          }
+          s = (a4.x + a4.y) + (a4.z + a4.w);
         } else {
           const int q = rem - nW, qq = 4 * (q / r) + (q % r);
-          for (int i = 0; i < 64; ++i) s += dv[qq][i];
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* dp = reinterpret_cast<const float4*>(dv[qq]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float4 d4 = dp[i]; a4.x += d4.x; a4.y += d4.y; a4.z += d4.z; a4.w += d4.w; }
+          s = (a4.x + a4.y) + (a4.z + a4.w);
         }
         dh[idx] = s;
       }
