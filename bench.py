@@ -37,6 +37,11 @@ import torch.nn.functional as F  # noqa: E402
 MODEL = dict(dim=224, depth=8, heads=4, n_classes=100, mlp_ratio=3.0, n_views=5, share_qkv=True, use_k3=True,
              gate_mode="lowrank", gate_rank=4, gate_init="mix5", drop_path=0.1)
 BATCH, IMG, PATCH, NTOK = 256, 32, 4, 64
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ewtc::edgewise_bwd2_kernel, B*H = 1024
+# problems) from the committed `ncu --set full` capture; algorithmic read bytes (Q, K, V, dy) are 29.4 MB, i.e. no re-reads
+# (the 22 MB of dqkv written stay in L2 until after the launch).
+DOMINANT_KERNEL_DRAM_BYTES = 29551360 + 159488
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01d_ncu_full_ew64_bwd_raw.csv (ncu --set full, one launch)"
 WORKLOAD = "ViTEdgewise E+ (dim224 depth8 heads4 V5 share_qkv use_k3 lowrank:mix5 r4), CIFAR-shaped 32x32, batch 256/GPU, fwd+bwd+AdamW"
 
 
@@ -320,7 +325,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["source"],
+                         "frac": achieved / pk["bf16"], "traffic": DOMINANT_KERNEL_DRAM_BYTES, "traffic_source": DOMINANT_KERNEL_DRAM_SOURCE,
+                         "peak_source": pk["source"],
                          "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
                          "fwd_ms": kern_ms.get("edgewise_fwd"), "bwd_ms": kern_ms.get("edgewise_bwd"),
                          "attention_tflops_fwd_bwd": 3 * f_fwd * MODEL["depth"] / (attn_ms * 1e-3) / 1e12 if attn_ms else None,

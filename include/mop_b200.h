@@ -185,6 +185,11 @@ int mop_selftest_umma(const float* A, const float* B, float* D, float* D2, int a
 int mop_selftest_umma128(const float* A, const float* B, float* D, int Ma, int Nn, int K, int b_mn, int Ra, int Rb, int Kb,
                          int b_k0, void* cuda_stream);
 
+/* Bring-up check of the TMA tile load: rows [row0, row0 + R) of (batch, head) of a bf16 [B][N][H][dk] tensor with element
+ * strides (sb, sn, sh) -> the R x 64 chunk-major shared-memory tile image, copied to `out` (R * 128 bytes). */
+int mop_selftest_tma(const void* x, void* out, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int R, int row0,
+                     int head, int batch, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

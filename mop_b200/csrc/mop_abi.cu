@@ -46,6 +46,36 @@ int sm_count() {
 }
 
 // ---------------------------------------------------------------------------
+// TMA tensor maps (tc_common.cuh: tma_load_tile).  The driver entry point is looked up at run time: no link-time libcuda.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(f);
+  }();
+  return fn;
+}
+// bf16 tensor [B][N][H][dk] with element strides (sb, sn, sh), last dimension contiguous; box = box_rows tokens x 64 columns
+int make_tile_map(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  MOP_REQUIRE(enc != nullptr, MOP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  auto stride = [](int64_t elems, int dim) -> cuuint64_t { return (dim > 1 && elems > 0) ? (cuuint64_t)elems * 2 : 16; };
+  const cuuint64_t dims[5] = {8, (cuuint64_t)N, (cuuint64_t)(dk / 8), (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {stride(sn, N), 16, stride(sh, H), stride(sb, B)};
+  const cuuint32_t box[5] = {8, (cuuint32_t)box_rows, 8, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MOP_REQUIRE(rc == CUDA_SUCCESS, MOP_ECUDA, "cuTensorMapEncodeTiled failed with code %d (N=%d H=%d dk=%d strides %lld %lld %lld)", (int)rc, N, H, dk,
+              (long long)sb, (long long)sn, (long long)sh);
+  return MOP_OK;
+}
+
+// ---------------------------------------------------------------------------
 static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
   MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
   MOP_REQUIRE(p->struct_bytes == (int32_t)sizeof(MopEdgewiseParams), MOP_EABI,
@@ -240,7 +270,11 @@ int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
     const size_t smem_tc = sizeof(sdpa2::SmemF) + 128;
     const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
     if ((rc = allow_smem(extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>, smem_tc))) return rc;
-    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 128, smem_tc, st>>>(*p);
+    CUtensorMap tmQ, tmK, tmV;
+    if ((rc = make_tile_map(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
+    if ((rc = make_tile_map(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
+    if ((rc = make_tile_map(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
+    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 128, smem_tc, st>>>(*p, tmQ, tmK, tmV);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
@@ -405,6 +439,19 @@ int mop_quartet_bwd(MopQuartetParams* p, void* stream) { return quartet_launch(p
 // ---------------------------------------------------------------------------
 // tcgen05 primitive self-test (tests/test_gpu_tc_primitives.py)
 // ---------------------------------------------------------------------------
+extern "C" int mop_selftest_tma(const void* x, void* out, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int R, int row0,
+                                int head, int batch, void* stream) {
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");
+  MOP_REQUIRE(R > 0 && R <= 256 && dk % 8 == 0 && dk <= 64, MOP_EINVAL, "bad selftest shape");
+  CUtensorMap tm;
+  int rc = make_tile_map(&tm, x, B, N, H, dk, sb, sn, sh, R);
+  if (rc != MOP_OK) return rc;
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(tc::selftest_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 128 + 1024));
+  tc::selftest_tma_kernel<<<1, 128, R * 128 + 1024, (cudaStream_t)stream>>>(tm, reinterpret_cast<unsigned char*>(out), R, row0, head, batch);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 extern "C" int mop_selftest_umma128(const float* A, const float* B, float* D, int Ma, int Nn, int K, int b_mn, int Ra, int Rb,
                                     int Kb, int b_k0, void* stream) {
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");

@@ -45,13 +45,17 @@ __device__ __forceinline__ float apply_extra(const MopSdpaParams& p, int b, int 
 struct __align__(128) SmemF {
   unsigned char Q[kT128], P[kT128];
   unsigned char K[2][kT64], V[2][kT64];
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
+  uint64_t ldq;      // TMA completion of the query tile
   uint32_t tmem_slot;
 };
 
 // grid: B*H*ceil(Nq/128), 128 threads; TMEM 128 columns (S | O): up to three CTAs per SM
+// Q / K / V tiles arrive by TMA (tc_common.cuh: tma_load_tile): one instruction per tile, issued by the MMA thread one tile ahead.
 template <bool EXTRA>
-__global__ void __launch_bounds__(128, 3) fwd_kernel(MopSdpaParams p) {
+__global__ void __launch_bounds__(128, 3) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                     const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
@@ -61,31 +65,32 @@ __global__ void __launch_bounds__(128, 3) fwd_kernel(MopSdpaParams p) {
   const bool row_ok = gi < Nq;
   const int dks = (dk + 15) >> 4;
   if (warp == 0) tmem_alloc<128>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_sb + (int64_t)h * p.q_sh;
-  const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_sb + (int64_t)h * p.k_sh;
-  const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_sb + (int64_t)h * p.v_sh;
-  auto fetch = [&](int buf, int k0) {
-    load_act_tile_async<64>(sm.K[buf], kp, (size_t)p.k_sn, k0, Nk, dk);
-    load_act_tile_async<64>(sm.V[buf], vp, (size_t)p.v_sn, k0, Nk, dk);
-    cp_async_commit();
-  };
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
   const int k_end = p.causal ? min(Nk, q0 + 128) : Nk;
   const int ntiles = (k_end + 63) >> 6;
-  if (ntiles > 0) fetch(0, 0);
-  load_act_tile<128>(sm.Q, qp, (size_t)p.q_sn, q0, Nq, dk);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  auto fetch = [&](int buf, int k0) {   // thread 0 only
+    mbar_expect_tx(&sm.ld[buf], 2 * kT64);
+    tma_load_tile(sm.K[buf], &tmK, k0, h, b, &sm.ld[buf]);
+    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldq, kT128);
+    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    if (ntiles > 0) fetch(0, 0);
+  }
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
   uint32_t phase = 0;
   float m_run = -INFINITY, l_run = 0.f;
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // P V of tile it-1: its buffers and P are free
-    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    publish();
     if (tid == 0) {
+      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
+      if (it == 0) mbar_wait(&sm.ldq, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
       mma_commit(&sm.bar);

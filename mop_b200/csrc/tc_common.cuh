@@ -9,6 +9,8 @@
 //   * an MN-major operand (tile rows = K index,  tile cols = M/N index): SBO = R*16,   LBO = 128
 // which means no kernel in this library ever transposes a tile: X, X^T, A_k and A_k^T are the same bytes.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace mop {
@@ -75,6 +77,18 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_block(void* smem_dst, const void* gsrc, uint32_t bytes) {
   for (uint32_t off = threadIdx.x * 16u; off < bytes; off += blockDim.x * 16u)
     cp_async16(reinterpret_cast<unsigned char*>(smem_dst) + off, reinterpret_cast<const unsigned char*>(gsrc) + off, true);
+}
+
+// ---- TMA tensor-map tile loads --------------------------------------------------------------------------------
+// A [.., tokens, .., dk] bf16 tensor is described to the TMA unit as the 5-D tensor
+//   (8 elements, token, 8-element chunk, head, batch)  with byte strides  (token stride, 16, head stride, batch stride)
+// so that a box {8, R, 8, 1, 1} lands in shared memory as [chunk][row][8 elements] = the chunk-major operand tile of this
+// library, in one instruction; rows / chunks outside the tensor are zero filled.  (Host side: mop::make_tile_map.)
+__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tm, int row0, int head, int batch, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row0), "r"(0), "r"(head), "r"(batch), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // ---- proxies / fences ---------------------------------------------------------------------------

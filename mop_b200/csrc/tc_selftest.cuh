@@ -136,5 +136,25 @@ __global__ void __launch_bounds__(256, 1) selftest128_kernel(const float* A, con
   if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
+
+// Bring-up of the TMA tile load: rows [row0, row0 + R) of head `head`, batch `batch` of a [B][N][H][dk] bf16 tensor -> chunk-major
+// tile in shared memory -> copied out verbatim (R * 128 bytes) for comparison on the host.
+__global__ void __launch_bounds__(128, 1) selftest_tma_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int R, int row0,
+                                                              int head, int batch) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < R * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)R * 128u);
+    tma_load_tile(smem, &tm, row0, head, batch, &bar);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = tid; i < R * 128 / 16; i += 128) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+
 }  // namespace tc
 }  // namespace mop

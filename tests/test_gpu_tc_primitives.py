@@ -56,3 +56,32 @@ def test_umma_m128_thread_per_row(Ma, Nn, K, b_mn, Ra, Rb, Kb, b_k0):
     torch.cuda.synchronize()
     err = (D[:Ma].double().cpu() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("B,N,H,dk,R,row0,head,batch,layout", [
+    (2, 300, 3, 64, 64, 128, 1, 1, "bnhd"),     # contiguous [B,N,H,dk]
+    (2, 196, 4, 56, 128, 128, 2, 0, "qkv"),     # a q/k/v slice of a [B,N,3,H,dk] projection, dk = 56, rows past the end
+    (1, 70, 1, 16, 64, 64, 0, 0, "bnhd"),       # single head / batch (degenerate strides), mostly out of bounds
+])
+def test_tma_tile_load_chunk_major(B, N, H, dk, R, row0, head, batch, layout):
+    """cp.async.bulk.tensor tile load through the 5-D tensor map lands as the chunk-major operand tile, zero filled."""
+    from mop_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N + dk)
+    if layout == "qkv":
+        full = torch.randn(B, N, 3, H, dk, generator=g).bfloat16().cuda()
+        x = full[:, :, 1]
+    else:
+        x = torch.randn(B, N, H, dk, generator=g).bfloat16().cuda()
+    sb, sn, sh, _ = x.stride()
+    out = torch.full((R * 128,), 0xEE, dtype=torch.uint8, device="cuda")
+    rc = lib.mop_selftest_tma(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, N, H, dk, C.c_int64(sb), C.c_int64(sn), C.c_int64(sh),
+                              R, row0, head, batch, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    got = out.view(torch.bfloat16).view(8, R, 8).float().cpu()          # [chunk][row][8]
+    want = torch.zeros(R, 64)
+    rows = x[batch, row0:row0 + R, head].float().cpu()
+    want[:rows.shape[0], :dk] = rows
+    want = want.view(R, 8, 8).permute(1, 0, 2)                           # [chunk][row][8]
+    assert torch.equal(got, want)
