@@ -392,9 +392,16 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   int rc;
   qtc::prep_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
   const bool hm = p->add_mask != nullptr;
+  // TMA tensor maps: activations [B,T,H,dk] (contiguous) and the centred keys in the workspace ([nm*B*H, T, 1, 64])
+  const int64_t sT = (int64_t)p->H * p->dk, sB = (int64_t)p->T * sT;
+  CUtensorMap tmQ, tmQ2, tmKc, tmV;
+  if ((rc = make_tile_map(&tmQ, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+  if ((rc = make_tile_map(&tmQ2, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+  if ((rc = make_tile_map(&tmKc, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
+  if ((rc = make_tile_map(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
   if (!bwd) {
     if ((rc = allow_smem(hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>, smem_f))) return rc;
-    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws);
+    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
   } else {
     if ((rc = allow_smem(hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>, smem_q))) return rc;
     if ((rc = allow_smem(hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>, smem_k))) return rc;

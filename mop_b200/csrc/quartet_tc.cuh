@@ -237,13 +237,18 @@ __device__ __forceinline__ void load_act_tile_async(unsigned char* tile, const _
 struct __align__(128) SmemF {
   unsigned char Q[kT128], Q2[kT128], P[kT128];
   unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
+  uint64_t ldq;      // TMA completion of the query tiles
   uint32_t tmem_slot;
 };
 
 // grid: B*H*nqb, 128 threads; two CTAs per SM (256 TMEM columns each: S1 | S2 | O)
+// tmQ / tmQ2 / tmV: the activations [B,T,H,dk]; tmKc: the centred keys in the workspace ([nm*B*H, T, 1, 64])
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+__global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+                                                     const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmKc,
+                                                     const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nqb = w.nqb;
@@ -255,12 +260,7 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (warp == 0) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
-  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
-  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
-  load_act_tile<128>(sm.Q, reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h), stride, q0, T, dk);
-  if (mx.quart) load_act_tile<128>(sm.Q2, reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h), stride, q0, T, dk);
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
   // the Gram tiles (hi, lo per map) borrow the second key / value buffers for the sigma prologue
   copy_tile64(sm.K1[1], ws + w.gram + (size_t)bh * 2 * kT64);
   copy_tile64(sm.K2[1], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
@@ -268,14 +268,20 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
     copy_tile64(sm.V[1], ws + w.gram + (BH + bh) * 2 * kT64);
     copy_tile64(sm.P, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
   }
-  auto fetch = [&](int buf, int k0) {
-    load_act_tile_async<64>(sm.K1[buf], kc1, 64, k0, T, 64);
-    if (mx.quart) load_act_tile_async<64>(sm.K2[buf], kc2, 64, k0, T, 64);
-    load_act_tile_async<64>(sm.V[buf], vbase, stride, k0, T, dk);
-    cp_async_commit();
-  };
-  fetch(0, 0);
   publish();
+  auto fetch = [&](int buf, int k0) {   // thread 0 only
+    mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
+    tma_load_tile(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
+    if (mx.quart) tma_load_tile(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
+    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldq, (mx.quart ? 2 : 1) * kT128);
+    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    if (mx.quart) tma_load_tile(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
+    fetch(0, 0);
+  }
+  mbar_wait(&sm.ldq, 0);   // every thread reads its query row below
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
   uint32_t phase = 0;
   // ---- sigma_i = s sqrt(q_i . (G q_i) / (T-1)),  G q by MMA (G = hi + lo)
@@ -314,9 +320,9 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // P V of tile it-1: its buffers and P are free
-    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    publish();
     if (tid == 0) {
+      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
       if (mx.quart)
