@@ -426,7 +426,9 @@ struct __align__(128) SmemQ {
   unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
   float gx[2][2][128];   // [warpgroup][map][row]: row-coefficient partial sums
   float red[16];
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
+  uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
 };
 
@@ -453,7 +455,9 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
 // grid: B*H*nqb, 256 threads (two warpgroups split the 64 columns of every tile), one CTA per SM
 // TMEM: S1 | S2 | dP | dQ1 | dQ2 (64 columns each)
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+__global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+                                                        const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
+                                                        const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31, dk = p.dk, T = p.T, nqb = w.nqb;
@@ -465,20 +469,23 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
-  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
-  const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h);
-  auto fetch = [&](int buf, int k0) {
-    load_act_tile_async<64>(sm.K1[buf], kc1, 64, k0, T, 64);
-    if (mx.quart) load_act_tile_async<64>(sm.K2[buf], kc2, 64, k0, T, 64);
-    load_act_tile_async<64>(sm.V[buf], vbase, stride, k0, T, dk);
-    cp_async_commit();
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  auto fetch = [&](int buf, int k0) {   // thread 0 only
+    mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
+    tma_load_tile(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
+    if (mx.quart) tma_load_tile(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
+    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
   };
-  fetch(0, 0);
-  load_act_tile<128>(sm.Q, reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h), stride, q0, T, dk);
-  if (mx.quart) load_act_tile<128>(sm.Q2, reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h), stride, q0, T, dk);
-  load_act_tile<128>(sm.dO, reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h), stride, q0, T, dk);
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldq, (mx.quart ? 3 : 2) * kT128);
+    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    if (mx.quart) tma_load_tile(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
+    tma_load_tile(sm.dO, &tmdO, q0, h, b, &sm.ldq);
+    fetch(0, 0);
+  }
   // per-row statistics (both warpgroups need them)
   const float* st = p.stats + (((size_t)b * p.H + h) * T + (row_ok ? gi : T - 1)) * 3;
   const float s1v = st[0], s2v = st[1], lse = st[2];
@@ -496,9 +503,6 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
     }
     if (wg == 0) (reinterpret_cast<float*>(ws + w.delta) + (size_t)bh * T)[gi] = dlt;   // for bwd_dkdv
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
@@ -507,9 +511,10 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // dQ MMAs of tile it-1: its buffers and W are free
-    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    publish();
     if (tid == 0) {
+      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
+      if (it == 0) mbar_wait(&sm.ldq, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {
         mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
@@ -560,6 +565,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
     }
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  if (tid != 0) mbar_wait(&sm.ldq, 0);   // (already complete: orders the TMA-written query tiles before the generic reads below)
   // row coefficients: combine the two column halves
   sm.gx[wg][0][t] = g1;
   sm.gx[wg][1][t] = g2;
@@ -679,7 +685,9 @@ struct __align__(128) SmemK {
   unsigned char K1[kT128], K2[kT128], V[kT128], PT[kT128], W1T[kT128], W2T[kT128];
   unsigned char Q[2][kT64], Q2[2][kT64], dO[2][kT64];   // double buffered query-side tiles
   float vec[2][4][64];                                   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
+  uint64_t ldk;      // TMA completion of the key / value tiles
   uint32_t tmem_slot;
 };
 
@@ -687,7 +695,9 @@ struct __align__(128) SmemK {
 // grid: B*H*nqb (128 keys per CTA), 256 threads (thread per key row; two warpgroups split the 64 query columns of every
 // tile), one CTA per SM.  TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+__global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
+                                                          const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, T = p.T, nkb = w.nqb;
@@ -699,18 +709,20 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* kc1 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (size_t)bh * T * 64;
-  const __nv_bfloat16* kc2 = reinterpret_cast<const __nv_bfloat16*>(ws + w.kc) + (BH + bh) * T * 64;
-  const __nv_bfloat16* qbase = reinterpret_cast<const __nv_bfloat16*>(p.q) + at(p, b, 0, h);
-  const __nv_bfloat16* q2base = mx.quart ? reinterpret_cast<const __nv_bfloat16*>(p.q2) + at(p, b, 0, h) : nullptr;
-  const __nv_bfloat16* dybase = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, 0, h);
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   const float* stats = p.stats + ((size_t)b * p.H + h) * T * 3;
   const float* delta = reinterpret_cast<const float*>(ws + w.delta) + (size_t)bh * T;
+  // query-side tiles by TMA (thread 0); the per-query statistics by 4-byte cp.async (threads 0..63)
   auto fetch = [&](int buf, int q0) {
-    load_act_tile_async<64>(sm.Q[buf], qbase, stride, q0, T, dk);
-    if (mx.quart) load_act_tile_async<64>(sm.Q2[buf], q2base, stride, q0, T, dk);
-    load_act_tile_async<64>(sm.dO[buf], dybase, stride, q0, T, dk);
+    if (tid == 0) {
+      mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
+      tma_load_tile(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
+      if (mx.quart) tma_load_tile(sm.Q2[buf], &tmQ2, q0, h, b, &sm.ld[buf]);
+      tma_load_tile(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
+    }
     if (tid < 64) {
       const int i = min(q0 + tid, T - 1);
       cp_async4(&sm.vec[buf][0][tid], stats + (size_t)i * 3);
@@ -720,13 +732,13 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
     }
     cp_async_commit();
   };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldk, (mx.quart ? 3 : 2) * kT128);
+    tma_load_tile(sm.K1, &tmKc, k0, 0, bh, &sm.ldk);
+    if (mx.quart) tma_load_tile(sm.K2, &tmKc, k0, 0, (int)BH + bh, &sm.ldk);
+    tma_load_tile(sm.V, &tmV, k0, h, b, &sm.ldk);
+  }
   fetch(0, k0);
-  load_act_tile<128>(sm.K1, kc1, 64, k0, T, 64);
-  if (mx.quart) load_act_tile<128>(sm.K2, kc2, 64, k0, T, 64);
-  load_act_tile<128>(sm.V, reinterpret_cast<const __nv_bfloat16*>(p.v) + at(p, b, 0, h), stride, k0, T, dk);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float dum0 = 0.f, dum1 = 0.f;
@@ -735,13 +747,14 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
     const int q0 = k0 + it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // output MMAs of tile it-1 have read their tiles
     if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    __syncthreads();
-    if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place
+    if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place (each thread converts the values it fetched itself)
       sm.vec[buf][0][tid] = 1.f / (sm.vec[buf][0][tid] + mx.eps);
       sm.vec[buf][1][tid] = mx.quart ? 1.f / (sm.vec[buf][1][tid] + mx.eps) : 0.f;
     }
-    publish();
+    __syncthreads();   // the per-query vectors of this tile are visible to every thread
     if (tid == 0) {
+      if (it == 0) mbar_wait(&sm.ldk, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
         mma_ss(tb, desc_kmajor(smem_u32(sm.K1), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
