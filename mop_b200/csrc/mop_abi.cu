@@ -308,8 +308,19 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
     const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
     if ((rc = allow_smem(extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>, smem_q))) return rc;
     if ((rc = allow_smem(extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>, smem_k))) return rc;
-    (extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta);
-    (extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>)<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta);
+    // TMA tensor maps: 128-row boxes for the stationary tiles, 64-row boxes for the streamed ones
+    const int64_t sY = (int64_t)p->H * p->dk, sYb = (int64_t)p->Nq * sY;
+    CUtensorMap tmQ, tmdO, tmK, tmV, tmQs, tmdOs, tmKL, tmVL;
+    if ((rc = make_tile_map(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
+    if ((rc = make_tile_map(&tmdO, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 128))) return rc;
+    if ((rc = make_tile_map(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
+    if ((rc = make_tile_map(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
+    if ((rc = make_tile_map(&tmQs, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 64))) return rc;
+    if ((rc = make_tile_map(&tmdOs, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 64))) return rc;
+    if ((rc = make_tile_map(&tmKL, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 128))) return rc;
+    if ((rc = make_tile_map(&tmVL, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 128))) return rc;
+    (extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta, tmQ, tmdO, tmK, tmV);
+    (extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>)<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta, tmQs, tmdOs, tmKL, tmVL);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

@@ -210,13 +210,17 @@ __device__ __forceinline__ void elem_x(const MopSdpaParams& p, int b, int h, int
 struct __align__(128) SmemQ {
   unsigned char Q[kT128], dO[kT128], W[kT128];
   unsigned char K[2][kT64], V[2][kT64];
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
+  uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
 };
 
 // grid: B*H*ceil(Nq/128), 256 threads; TMEM 256 columns (S | dP | dQ): two CTAs per SM
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* delta) {
+__global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* delta, const __grid_constant__ CUtensorMap tmQ,
+                                                        const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
+                                                        const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
@@ -226,23 +230,26 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
   const bool row_ok = gi < Nq;
   const int dks = (dk + 15) >> 4, c0 = 32 * wg;
   if (tid < 32) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_sb + (int64_t)h * p.q_sh;
-  const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_sb + (int64_t)h * p.k_sh;
-  const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_sb + (int64_t)h * p.v_sh;
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
   const size_t ystride = (size_t)p.H * dk;
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy) + ((int64_t)b * Nq * p.H + h) * dk;
   const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.y) + ((int64_t)b * Nq * p.H + h) * dk;
-  auto fetch = [&](int buf, int k0) {
-    load_act_tile_async<64>(sm.K[buf], kp, (size_t)p.k_sn, k0, Nk, dk);
-    load_act_tile_async<64>(sm.V[buf], vp, (size_t)p.v_sn, k0, Nk, dk);
-    cp_async_commit();
-  };
   const int k_end = p.causal ? min(Nk, q0 + 128) : Nk;
   const int ntiles = (k_end + 63) >> 6;
-  if (ntiles > 0) fetch(0, 0);
-  load_act_tile<128>(sm.Q, qp, (size_t)p.q_sn, q0, Nq, dk);
-  load_act_tile<128>(sm.dO, dyp, ystride, q0, Nq, dk);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  auto fetch = [&](int buf, int k0) {   // thread 0 only
+    mbar_expect_tx(&sm.ld[buf], 2 * kT64);
+    tma_load_tile(sm.K[buf], &tmK, k0, h, b, &sm.ld[buf]);
+    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldq, 2 * kT128);
+    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    tma_load_tile(sm.dO, &tmdO, q0, h, b, &sm.ldq);
+    if (ntiles > 0) fetch(0, 0);
+  }
   const float lse = p.lse[((int64_t)b * p.H + h) * Nq + (row_ok ? gi : Nq - 1)];
   float dlt = 0.f;
   if (row_ok) {
@@ -255,17 +262,15 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
     }
     if (wg == 0) delta[((int64_t)b * p.H + h) * Nq + gi] = dlt;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
-    if (it + 1 < ntiles) { fetch(buf ^ 1, k0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    publish();
     if (tid == 0) {
+      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
+      if (it == 0) mbar_wait(&sm.ldq, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {
         mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
@@ -327,14 +332,18 @@ struct __align__(128) SmemK {
   unsigned char K[kT128], V[kT128], PT[kT128], WT[kT128];
   unsigned char Q[2][kT64], dO[2][kT64];
   float vec[2][2][64];   // per query of the tile: lse, delta
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
+  uint64_t ldk;      // TMA completion of the key / value tiles
   uint32_t tmem_slot;
 };
 
 // grid: B*H*ceil(Nk/128), 256 threads (thread per key row; two warpgroups split the 64 query columns); TMEM 256 columns
 // (S^T | dP^T | dV | dK): two CTAs per SM
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const float* delta) {
+__global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const float* delta, const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
@@ -344,19 +353,21 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
   const bool key_ok = gj < Nk;
   const int dks = (dk + 15) >> 4, c0 = 32 * wg;
   if (tid < 32) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_sb + (int64_t)h * p.q_sh;
-  const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_sb + (int64_t)h * p.k_sh;
-  const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_sb + (int64_t)h * p.v_sh;
-  const size_t ystride = (size_t)p.H * dk;
-  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy) + ((int64_t)b * Nq * p.H + h) * dk;
+  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
   const float* lsep = p.lse + ((int64_t)b * p.H + h) * Nq;
   const float* dltp = delta + ((int64_t)b * p.H + h) * Nq;
   const int qstart = p.causal ? min(k0, Nq) & ~63 : 0;   // queries i >= j only when causal
   const int ntiles = (Nq - qstart + 63) >> 6;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // query-side tiles by TMA (thread 0); the per-query statistics by 4-byte cp.async (threads 0..63)
   auto fetch = [&](int buf, int q0) {
-    load_act_tile_async<64>(sm.Q[buf], qp, (size_t)p.q_sn, q0, Nq, dk);
-    load_act_tile_async<64>(sm.dO[buf], dyp, ystride, q0, Nq, dk);
+    if (tid == 0) {
+      mbar_expect_tx(&sm.ld[buf], 2 * kT64);
+      tma_load_tile(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
+      tma_load_tile(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
+    }
     if (tid < 64) {
       const int i = min(q0 + tid, Nq - 1);
       cp_async4(&sm.vec[buf][0][tid], lsep + i);
@@ -364,20 +375,22 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
     }
     cp_async_commit();
   };
+  if (tid == 0) {
+    mbar_expect_tx(&sm.ldk, 2 * kT128);
+    tma_load_tile(sm.K, &tmK, k0, h, b, &sm.ldk);
+    tma_load_tile(sm.V, &tmV, k0, h, b, &sm.ldk);
+  }
   if (ntiles > 0) fetch(0, qstart);
-  load_act_tile<128>(sm.K, kp, (size_t)p.k_sn, k0, Nk, dk);
-  load_act_tile<128>(sm.V, vp, (size_t)p.v_sn, k0, Nk, dk);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   for (int it = 0; it < ntiles; ++it) {
     const int q0 = qstart + it * 64, buf = it & 1;
     if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
     if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
-    publish();
+    __syncthreads();   // the per-query vectors of this tile are visible to every thread
     if (tid == 0) {
+      if (it == 0) mbar_wait(&sm.ldk, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
         mma_ss(tb, desc_kmajor(smem_u32(sm.K), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
