@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmop_b200.so")
+LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
 MOP_ABI_VERSION = 2
 MOP_F32, MOP_BF16 = 0, 1

@@ -274,7 +274,7 @@ int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
     if ((rc = make_tile_map(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
     if ((rc = make_tile_map(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
     if ((rc = make_tile_map(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
-    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 128, smem_tc, st>>>(*p, tmQ, tmK, tmV);
+    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 192, smem_tc, st>>>(*p, tmQ, tmK, tmV);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

@@ -15,6 +15,18 @@
 #pragma once
 #include "quartet_tc.cuh"
 
+#ifndef MOP_DBG
+#define MOP_DBG 0
+#endif
+#if MOP_DBG == 9
+#define TS_DECL long long ts_[24][6]; const bool ts_on = blockIdx.x == 700;
+#define TS(t, k) do { if (ts_on && (t) < 24) ts_[t][k] = clock64(); } while (0)
+#define TS_DUMP(name, n, K) do { if (ts_on) for (int t_ = 0; t_ < (n) && t_ < 24; ++t_) printf("%s t= %d %lld %lld %lld %lld %lld %lld\n", name, t_, ts_[t_][0], ts_[t_][1], ts_[t_][2], ts_[t_][3], K > 4 ? ts_[t_][4] : 0LL, K > 5 ? ts_[t_][5] : 0LL); } while (0)
+#else
+#define TS_DECL
+#define TS(t, k)
+#define TS_DUMP(name, n, K)
+#endif
 namespace mop {
 namespace sdpa2 {
 
@@ -42,151 +54,250 @@ __device__ __forceinline__ float apply_extra(const MopSdpaParams& p, int b, int 
   return s;
 }
 
+constexpr int kStages = 4;   // key / value tile ring of the forward kernel
 struct __align__(128) SmemF {
-  unsigned char Q[kT128], P[kT128];
-  unsigned char K[2][kT64], V[2][kT64];
-  uint64_t bar;      // MMA completion
-  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
-  uint64_t ldq;      // TMA completion of the query tile
+  unsigned char Q[kT128], P[2][kT128];
+  unsigned char K[kStages][kT64], V[kStages][kT64];
+  uint64_t bar_s[2];      // completion of the S MMA into score buffer 0 / 1            (tensor pipe -> softmax warps)
+  uint64_t bar_pv[2];     // completion of P V of even / odd tiles                      (tensor pipe -> softmax warps, MMA warp)
+  uint64_t p_ready[2];    // P(t) written into P[t & 1]: 128 arrivals                   (softmax warps -> P V warp)
+  uint64_t s_free[2];     // score buffer t & 1 has been read: 128 arrivals             (softmax warps -> S warp)
+  // every barrier is waited on phase by phase by each of its waiters, and its next completion depends on that waiter's
+  // progress - a waiter can never fall two phases behind (a parity wait cannot tell phase k from phase k + 2)
+  uint64_t ld[kStages];   // TMA completion of ring stage s
+  uint64_t fr[kStages];   // ring stage s free again: P V of its tile complete               (tensor pipe -> TMA warp)
+  uint64_t ldq;           // TMA completion of the query tile
   uint32_t tmem_slot;
 };
 
-// grid: B*H*ceil(Nq/128), 128 threads; TMEM 128 columns (S | O): up to three CTAs per SM
-// Q / K / V tiles arrive by TMA (tc_common.cuh: tma_load_tile): one instruction per tile, issued by the MMA thread one tile ahead.
+// grid: B*H*ceil(Nq/128), 192 threads, two CTAs per SM; TMEM 256 columns (S buffer 0 | S buffer 1 | O).
+// Warp-specialised, no CTA-wide barrier inside the loop:
+//   warps 0-3  softmax, one query row per thread: S(t) from TMEM -> exponentials -> P(t) (bf16, two buffers) -> arrive p_ready
+//   warp 4     one lane issues the TMA loads (Q once; K / V tiles into a four-stage ring, refilled when P V of the old tile is
+//              done) and S(t) = Q K_t^T as soon as K_t has landed and score buffer t&1 has been read (two tiles ahead)
+//   warp 5     one lane issues O += P(t) V_t when p_ready(t) completes
+// The single-lane roles are split over two warps because a lone issuing lane needs ~10 cycles per instruction: one lane doing
+// everything (~220 instructions per tile) was the bottleneck of the first pipelined version.  The running maximum is only
+// raised when a tile exceeds it by more than 2^8 (exponentials stay <= 256; fp32 sums and bf16 products keep their relative
+// precision), which removes nearly all rescales of O.
 template <bool EXTRA>
-__global__ void __launch_bounds__(128, 3) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
   const int nqb = (Nq + 127) >> 7, BH = p.B * p.H;
   const int qb = nqb - 1 - (int)(blockIdx.x / (unsigned)BH), bh = blockIdx.x % BH, b = bh / p.H, h = bh % p.H;
-  const int q0 = qb * 128, gi = q0 + tid;
-  const bool row_ok = gi < Nq;
-  const int dks = (dk + 15) >> 4;
-  if (warp == 0) tmem_alloc<128>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
+  const int q0 = qb * 128;
+  if (warp == 0) tmem_alloc<256>(&sm.tmem_slot);
+  if (tid == 0) {
+    mbar_init(&sm.bar_s[0], 1); mbar_init(&sm.bar_s[1], 1); mbar_init(&sm.bar_pv[0], 1); mbar_init(&sm.bar_pv[1], 1); mbar_init(&sm.ldq, 1);
+    mbar_init(&sm.p_ready[0], 128); mbar_init(&sm.p_ready[1], 128); mbar_init(&sm.s_free[0], 128); mbar_init(&sm.s_free[1], 128);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.ld[s], 1); mbar_init(&sm.fr[s], 1); }
+    fence_mbar_init();
+  }
   const int k_end = p.causal ? min(Nk, q0 + 128) : Nk;
   const int ntiles = (k_end + 63) >> 6;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  auto fetch = [&](int buf, int k0) {   // thread 0 only
-    mbar_expect_tx(&sm.ld[buf], 2 * kT64);
-    tma_load_tile(sm.K[buf], &tmK, k0, h, b, &sm.ld[buf]);
-    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(&sm.ldq, kT128);
-    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
-    if (ntiles > 0) fetch(0, 0);
-  }
-  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
-  uint32_t phase = 0;
-  float m_run = -INFINITY, l_run = 0.f;
-  for (int it = 0; it < ntiles; ++it) {
-    const int k0 = it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // P V of tile it-1: its buffers and P are free
-    if (tid == 0) {
-      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
-      if (it == 0) mbar_wait(&sm.ldq, 0);
-      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-      mma_commit(&sm.bar);
+  const uint32_t tb = sm.tmem_slot;
+  if (warp >= 4) {
+    if (tid == 128) {
+      // ---- TMA loads + S(t) = Q K_t^T ----------------------------------------------------------------------------
+      auto fetch = [&](int t) {
+        const int s = t & (kStages - 1);
+        mbar_expect_tx(&sm.ld[s], 2 * kT64);
+        tma_load_tile(sm.K[s], &tmK, 64 * t, h, b, &sm.ld[s]);
+        tma_load_tile(sm.V[s], &tmV, 64 * t, h, b, &sm.ld[s]);
+      };
+      const uint32_t id_s = idesc_bf16(128, 64, 0, 0);
+      const uint64_t dq = desc_kmajor(smem_u32(sm.Q), 128, 0), dk0 = desc_kmajor(smem_u32(sm.K[0]), 64, 0);
+      if (ntiles > 0) {
+        mbar_expect_tx(&sm.ldq, kT128);
+        tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+        for (int t = 0; t < min(ntiles, kStages); ++t) fetch(t);
+        mbar_wait(&sm.ldq, 0);
+      }
+      TS_DECL
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & (kStages - 1);
+        TS(t, 0);
+        if (t >= 2) { mbar_wait(&sm.s_free[t & 1], (uint32_t)((t - 2) >> 1) & 1u); tc_fence_after(); }   // S(t-2) has been read
+        TS(t, 1);
+#if MOP_DBG == 5
+        if (t < kStages)
+#endif
+        mbar_wait(&sm.ld[s], (uint32_t)(t >> 2) & 1u);
+        TS(t, 2);
+        const uint64_t dkk = dk0 + (uint64_t)(s * (kT64 >> 4));
+        const uint32_t dst = tb + 64 * (t & 1);
+        // one K step = two 8-column chunks: +2*R*16 bytes (>> 4 in the descriptor's address field); the tiles are zero
+        // filled past dk, so the full 64-wide contraction is always right
+#pragma unroll
+        for (int ks = 0; ks < (MOP_DBG == 7 ? 1 : 4); ++ks) mma_ss(dst, dq + (uint64_t)(ks * 256), dkk + (uint64_t)(ks * 128), id_s, ks > 0 ? 1u : 0u);
+        mma_commit(&sm.bar_s[t & 1]);
+        TS(t, 3);
+        if (t >= 2 && t + 2 < ntiles) {   // refill the ring stage of tile t-2 once P V(t-2) (issued right after p_ready(t-2)) is done
+          mbar_wait(&sm.fr[(t - 2) & (kStages - 1)], (uint32_t)((t - 2) >> 2) & 1u);
+#if MOP_DBG != 5
+          fetch(t + 2);
+#endif
+        }
+        TS(t, 4);
+      }
+      TS_DUMP("S-lane", ntiles, 5);
+    } else if (tid == 160) {
+      // ---- O += P(t) V_t ---------------------------------------------------------------------------------------
+      const uint32_t id_pv = idesc_bf16(128, 64, 0, 1);
+      const uint64_t dp0 = desc_kmajor(smem_u32(sm.P[0]), 128, 0), dv0 = desc_mnmajor(smem_u32(sm.V[0]), 64, 0);
+      TS_DECL
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & (kStages - 1);
+        TS(t, 0);
+#if MOP_DBG == 5
+        if (t < kStages)
+#endif
+        mbar_wait(&sm.ld[s], (uint32_t)(t >> 2) & 1u);   // V_t (long since landed: S(t) already used K_t of the same stage)
+        TS(t, 1);
+        mbar_wait(&sm.p_ready[t & 1], (uint32_t)(t >> 1) & 1u);   // P(t) written into P[t & 1]
+        tc_fence_after();
+        TS(t, 2);
+        const uint64_t dp = dp0 + (uint64_t)((t & 1) * (kT128 >> 4)), dv = dv0 + (uint64_t)(s * (kT64 >> 4));
+#pragma unroll
+        for (int ks = 0; ks < (MOP_DBG == 6 ? 1 : 4); ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 16), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        mma_commit(&sm.bar_pv[t & 1]);
+        mma_commit(&sm.fr[s]);
+        TS(t, 3);
+      }
+      TS_DUMP("PV-lane", ntiles, 4);
     }
-    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-    float sc[64];
+  } else {
+    // ---- softmax warps: one query row per thread ------------------------------------------------------------
+    const int gi = q0 + tid;
+    const bool row_ok = gi < Nq;
+    const uint32_t tl = tb + ((uint32_t)(32 * warp) << 16);
+    const float coef = EXTRA ? kLog2e : p.scale * kLog2e;   // exponent = score * coef - m_ref (base 2)
+    float m_ref = -INFINITY, l_run = 0.f;
+    TS_DECL
+    for (int it = 0; it < ntiles; ++it) {
+      const int k0 = it * 64;
+      TS(it, 0);
+      mbar_wait(&sm.bar_s[it & 1], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      TS(it, 1);
+      float sc[64];
+#if MOP_DBG == 4
+#pragma unroll
+      for (int e = 0; e < 64; ++e) sc[e] = (float)(e + it) * 0.01f;
+#else
+      tmem_ld_32x32b_x32(tl + 64 * (it & 1), sc);
+      tmem_ld_32x32b_x32(tl + 64 * (it & 1) + 32, sc + 32);
+      tmem_ld_wait();
+#endif
+      tc_fence_before();
+      mbar_arrive(&sm.s_free[it & 1]);
+      TS(it, 2);
+      if (k0 + 64 > Nk) {   // padded keys (uniform branch)
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (k0 + e >= Nk) sc[e] = -INFINITY;
+      }
+      if constexpr (EXTRA) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) sc[e] *= p.scale;
+        if (row_ok) {
+#pragma unroll 8
+          for (int e = 0; e < 64; ++e)
+            if (k0 + e < Nk) sc[e] = apply_extra(p, b, h, gi, k0 + e, sc[e]);
+        }
+      } else {
+        if (p.causal && k0 + 63 > q0) {   // diagonal tiles only
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (k0 + e > gi) sc[e] = -INFINITY;
+        }
+      }
+      float t0 = sc[0], t1 = sc[1], t2 = sc[2], t3 = sc[3];
+#pragma unroll
+      for (int e = 4; e < 64; e += 4) { t0 = fmaxf(t0, sc[e]); t1 = fmaxf(t1, sc[e + 1]); t2 = fmaxf(t2, sc[e + 2]); t3 = fmaxf(t3, sc[e + 3]); }
+      const float tm2 = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * coef;
+      const bool need = tm2 > m_ref + 8.f;                       // -inf + 8 = -inf: the first finite tile always raises it
+      const float m_new = need ? tm2 : m_ref;
+      const float corr = need ? ((m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new)) : 1.f;
+      const float mb = (m_new == -INFINITY) ? 0.f : m_new;
+      TS(it, 3);
+      if (it > 1) mbar_wait(&sm.bar_pv[it & 1], (uint32_t)((it - 2) >> 1) & 1u);
+      TS(it, 4);   // P V(it-2) (issued a tile ago): P[it & 1] is free
+      if (it > 0 && __any_sync(0xffffffffu, need)) {   // rare: O must be final up to tile it-1 before it is rescaled
+        mbar_wait(&sm.bar_pv[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
+        tc_fence_after();
+        {
+          float o[64];
+          tmem_ld_32x32b_x32(tl + 128, o);
+          tmem_ld_32x32b_x32(tl + 160, o + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 64; ++e) o[e] *= corr;
+          tmem_st_32x32b_x32(tl + 128, o);
+          tmem_st_32x32b_x32(tl + 160, o + 32);
+          tmem_st_wait();
+        }
+      }
+      l_run *= corr;
+      m_ref = m_new;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float pv[8];
+#pragma unroll
+#if MOP_DBG == 1
+        for (int e = 0; e < 8; ++e) pv[e] = fmaf(sc[8 * c + e], coef, -mb);
+#else
+        for (int e = 0; e < 8; ++e) pv[e] = ex2(fmaf(sc[8 * c + e], coef, -mb));
+#endif
+        ps0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        ps1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+#if MOP_DBG == 3
+        if (ps0 == 123.456f)
+#endif
+        *reinterpret_cast<uint4*>(sm.P[it & 1] + c * (128 * 16) + tid * 16) = pack8(pv);
+      }
+      l_run += ps0 + ps1;
+#if MOP_DBG != 2
+      fence_async_smem();   // P (generic proxy) -> tensor pipe (async proxy)
+#endif
+      tc_fence_before();    // this thread's TMEM reads / writes precede the MMAs issued after the arrive is observed
+      mbar_arrive(&sm.p_ready[it & 1]);
+      TS(it, 5);
+    }
+    if (tid == 0) TS_DUMP("softmax", ntiles, 6);
+    if (ntiles > 1) mbar_wait(&sm.bar_pv[ntiles & 1], (uint32_t)((ntiles - 2) >> 1) & 1u);
+    if (ntiles > 0) { mbar_wait(&sm.bar_pv[(ntiles - 1) & 1], (uint32_t)((ntiles - 1) >> 1) & 1u); tc_fence_after(); }
+    const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((int64_t)b * Nq + (row_ok ? gi : 0)) * p.H + h) * dk;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float v1[16];
-      tmem_ld_32x32b_x16(tl + 16 * c, v1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) sc[16 * c + e] = v1[e] * p.scale;
-    }
-    if (k0 + 64 > Nk) {   // padded keys (uniform branch)
-#pragma unroll
-      for (int e = 0; e < 64; ++e)
-        if (k0 + e >= Nk) sc[e] = -INFINITY;
-    }
-    if constexpr (EXTRA) {
-      if (row_ok) {
-#pragma unroll 8
-        for (int e = 0; e < 64; ++e)
-          if (k0 + e < Nk) sc[e] = apply_extra(p, b, h, gi, k0 + e, sc[e]);
-      }
-    } else {
-      if (p.causal && k0 + 63 > q0) {   // diagonal tiles only
-#pragma unroll
-        for (int e = 0; e < 64; ++e)
-          if (k0 + e > gi) sc[e] = -INFINITY;
-      }
-    }
-    float tmax = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < 64; ++e) tmax = fmaxf(tmax, sc[e]);
-    const float m_new = fmaxf(m_run, tmax);
-    const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
-    const float corr = (m_run == -INFINITY) ? 0.f : ex2(fmaf(m_run, kLog2e, -mb));
-    const bool need = it > 0 && m_new > m_run;
-    if (__any_sync(0xffffffffu, need)) {
-      const float scl = need ? corr : 1.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float o[16];
-        tmem_ld_32x32b_x16(tl + 64 + 16 * c, o);
+      float o[16];
+      if (ntiles > 0) {
+        tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
         tmem_ld_wait();
+      } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] *= scl;
-        tmem_st_32x32b_x16(tl + 64 + 16 * c, o);
+        for (int e = 0; e < 16; ++e) o[e] = 0.f;
       }
-      tmem_st_wait();
-    }
-    l_run *= corr;
-    m_run = m_new;
-    float ps = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float pv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { pv[e] = ex2(fmaf(sc[8 * c + e], kLog2e, -mb)); ps += pv[e]; }
-      *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
+      for (int e = 0; e < 16; ++e) o[e] *= il;
+      if (row_ok) {
+        if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
+        if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
+      }
     }
-    l_run += ps;
-    publish();
-    if (tid == 0) {
-      const uint32_t id = idesc_bf16(128, 64, 0, 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        mma_ss(tb + 64, desc_kmajor(smem_u32(sm.P), 128, 16 * ks), desc_mnmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
-      mma_commit(&sm.bar);
-    }
+    if (p.lse && row_ok) p.lse[((int64_t)b * p.H + h) * Nq + gi] = kLn2 * (m_ref + lg2(l_run));
   }
-  if (ntiles > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
-  const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((int64_t)b * Nq + (row_ok ? gi : 0)) * p.H + h) * dk;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float o[16];
-    if (ntiles > 0) {
-      tmem_ld_32x32b_x16(tl + 64 + 16 * c, o);
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) o[e] *= il;
-    if (row_ok) {
-      if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
-      if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
-    }
-  }
-  if (p.lse && row_ok) p.lse[((int64_t)b * p.H + h) * Nq + gi] = m_run + kLn2 * lg2(l_run);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tb);
+  if (warp == 0) tmem_dealloc<256>(tb);
 }
 
 // probability and dS of one element given the raw dot product and dP
