@@ -75,6 +75,22 @@ int make_tile_map(CUtensorMap* tm, const void* base, int B, int N, int H, int dk
   return MOP_OK;
 }
 
+// same tensor as (column, token, head, batch); box = 64 columns x box_rows tokens, 128-byte swizzle (tc_common.cuh: tma_load_tile_sw)
+int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  MOP_REQUIRE(enc != nullptr, MOP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  auto stride = [](int64_t elems, int dim) -> cuuint64_t { return (dim > 1 && elems > 0) ? (cuuint64_t)elems * 2 : 16; };
+  const cuuint64_t dims[4] = {(cuuint64_t)dk, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {stride(sn, N), stride(sh, H), stride(sb, B)};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MOP_REQUIRE(rc == CUDA_SUCCESS, MOP_ECUDA, "cuTensorMapEncodeTiled (128B swizzle) failed with code %d (N=%d H=%d dk=%d strides %lld %lld %lld)", (int)rc, N,
+              H, dk, (long long)sb, (long long)sn, (long long)sh);
+  return MOP_OK;
+}
+
 // ---------------------------------------------------------------------------
 static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
   MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
@@ -271,9 +287,9 @@ int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
     const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
     if ((rc = allow_smem(extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>, smem_tc))) return rc;
     CUtensorMap tmQ, tmK, tmV;
-    if ((rc = make_tile_map(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
-    if ((rc = make_tile_map(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
-    if ((rc = make_tile_map(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
     (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 192, smem_tc, st>>>(*p, tmQ, tmK, tmV);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
@@ -311,14 +327,14 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
     // TMA tensor maps: 128-row boxes for the stationary tiles, 64-row boxes for the streamed ones
     const int64_t sY = (int64_t)p->H * p->dk, sYb = (int64_t)p->Nq * sY;
     CUtensorMap tmQ, tmdO, tmK, tmV, tmQs, tmdOs, tmKL, tmVL;
-    if ((rc = make_tile_map(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
-    if ((rc = make_tile_map(&tmdO, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 128))) return rc;
-    if ((rc = make_tile_map(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
-    if ((rc = make_tile_map(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
-    if ((rc = make_tile_map(&tmQs, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 64))) return rc;
-    if ((rc = make_tile_map(&tmdOs, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 64))) return rc;
-    if ((rc = make_tile_map(&tmKL, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 128))) return rc;
-    if ((rc = make_tile_map(&tmVL, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmdO, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmQs, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmdOs, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmKL, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 128))) return rc;
     (extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta, tmQ, tmdO, tmK, tmV);
     (extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>)<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta, tmQs, tmdOs, tmKL, tmVL);
     MOP_CHECK_CUDA(cudaGetLastError());
@@ -406,10 +422,10 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   // TMA tensor maps: activations [B,T,H,dk] (contiguous) and the centred keys in the workspace ([nm*B*H, T, 1, 64])
   const int64_t sT = (int64_t)p->H * p->dk, sB = (int64_t)p->T * sT;
   CUtensorMap tmQ, tmQ2, tmKc, tmV;
-  if ((rc = make_tile_map(&tmQ, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-  if ((rc = make_tile_map(&tmQ2, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-  if ((rc = make_tile_map(&tmKc, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
-  if ((rc = make_tile_map(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
+  if ((rc = make_tile_map_sw(&tmQ, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+  if ((rc = make_tile_map_sw(&tmQ2, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+  if ((rc = make_tile_map_sw(&tmKc, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
+  if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
   if (!bwd) {
     if ((rc = allow_smem(hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>, smem_f))) return rc;
     (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
@@ -417,12 +433,12 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     if ((rc = allow_smem(hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>, smem_q))) return rc;
     if ((rc = allow_smem(hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>, smem_k))) return rc;
     CUtensorMap tmdO, tmQs, tmQ2s, tmdOs, tmKcL, tmVL;   // dO (128-row box); 64-row boxes of q, q2, dO; 128-row boxes of kc, v
-    if ((rc = make_tile_map(&tmdO, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-    if ((rc = make_tile_map(&tmQs, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
-    if ((rc = make_tile_map(&tmQ2s, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
-    if ((rc = make_tile_map(&tmdOs, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
-    if ((rc = make_tile_map(&tmKcL, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
-    if ((rc = make_tile_map(&tmVL, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmdO, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmQs, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmQ2s, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmdOs, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
+    if ((rc = make_tile_map_sw(&tmKcL, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
     (hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>)<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
     qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
     (hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>)<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws, tmQs, tmQ2s, tmdOs, tmKcL, tmVL);

@@ -104,9 +104,9 @@ __device__ __forceinline__ void copy_tile64(unsigned char* dst, const unsigned c
 __device__ __forceinline__ void mma_x_sym(uint32_t d_tmem, uint32_t xtile, uint32_t mhi, uint32_t mlo) {
   const uint32_t id = idesc_bf16(128, 64, 0, 0);
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_kmajor(xtile, 128, 16 * ks), desc_kmajor(mhi, 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_k_sw(xtile, 16 * ks), desc_kmajor(mhi, 64, 16 * ks), id, ks > 0 ? 1u : 0u);
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_kmajor(xtile, 128, 16 * ks), desc_kmajor(mlo, 64, 16 * ks), id, 1u);
+  for (int ks = 0; ks < 4; ++ks) mma_ss(d_tmem, desc_k_sw(xtile, 16 * ks), desc_kmajor(mlo, 64, 16 * ks), id, 1u);
 }
 
 // rows [row0, row0 + R) of a [.., T, H, dk] bf16 activation (token stride `stride` elements) -> chunk-major tile, zero fill
@@ -271,14 +271,14 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
   publish();
   auto fetch = [&](int buf, int k0) {   // thread 0 only
     mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
-    tma_load_tile(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
-    if (mx.quart) tma_load_tile(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
-    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+    tma_load_tile_sw(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
+    if (mx.quart) tma_load_tile_sw(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
+    tma_load_tile_sw(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldq, (mx.quart ? 2 : 1) * kT128);
-    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
-    if (mx.quart) tma_load_tile(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
+    tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    if (mx.quart) tma_load_tile_sw(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
     fetch(0, 0);
   }
   mbar_wait(&sm.ldq, 0);   // every thread reads its query row below
@@ -300,11 +300,11 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
     tmem_ld_wait();
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      unpack8(*reinterpret_cast<const uint4*>(sm.Q + (2 * c + hh) * (128 * 16) + tid * 16), x);
+      unpack8(*reinterpret_cast<const uint4*>(sm.Q + sw128_off(tid, 8 * (2 * c + hh))), x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) quad1 = fmaf(z1[8 * hh + e], x[e], quad1);
       if (mx.quart) {
-        unpack8(*reinterpret_cast<const uint4*>(sm.Q2 + (2 * c + hh) * (128 * 16) + tid * 16), x);
+        unpack8(*reinterpret_cast<const uint4*>(sm.Q2 + sw128_off(tid, 8 * (2 * c + hh))), x);
 #pragma unroll
         for (int e = 0; e < 8; ++e) quad2 = fmaf(z2[8 * hh + e], x[e], quad2);
       }
@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
       if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       if (mx.quart)
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       mma_commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.P), 128, 16 * ks), desc_mnmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.P), 128, 16 * ks), desc_mn_sw(smem_u32(sm.V[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       mma_commit(&sm.bar);
     }
   }
@@ -475,15 +475,15 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   tc_fence_after();
   auto fetch = [&](int buf, int k0) {   // thread 0 only
     mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
-    tma_load_tile(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
-    if (mx.quart) tma_load_tile(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
-    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+    tma_load_tile_sw(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
+    if (mx.quart) tma_load_tile_sw(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
+    tma_load_tile_sw(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldq, (mx.quart ? 3 : 2) * kT128);
-    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
-    if (mx.quart) tma_load_tile(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
-    tma_load_tile(sm.dO, &tmdO, q0, h, b, &sm.ldq);
+    tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    if (mx.quart) tma_load_tile_sw(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
+    tma_load_tile_sw(sm.dO, &tmdO, q0, h, b, &sm.ldq);
     fetch(0, 0);
   }
   // per-row statistics (both warpgroups need them)
@@ -517,9 +517,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {
-        mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.Q2), 128, 16 * ks), desc_kmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.dO), 128, 16 * ks), desc_kmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K1[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K2[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K1[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K2[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
@@ -719,9 +719,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   auto fetch = [&](int buf, int q0) {
     if (tid == 0) {
       mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
-      tma_load_tile(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
-      if (mx.quart) tma_load_tile(sm.Q2[buf], &tmQ2, q0, h, b, &sm.ld[buf]);
-      tma_load_tile(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
+      tma_load_tile_sw(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
+      if (mx.quart) tma_load_tile_sw(sm.Q2[buf], &tmQ2, q0, h, b, &sm.ld[buf]);
+      tma_load_tile_sw(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
     }
     if (tid < 64) {
       const int i = min(q0 + tid, T - 1);
@@ -734,9 +734,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldk, (mx.quart ? 3 : 2) * kT128);
-    tma_load_tile(sm.K1, &tmKc, k0, 0, bh, &sm.ldk);
-    if (mx.quart) tma_load_tile(sm.K2, &tmKc, k0, 0, (int)BH + bh, &sm.ldk);
-    tma_load_tile(sm.V, &tmV, k0, h, b, &sm.ldk);
+    tma_load_tile_sw(sm.K1, &tmKc, k0, 0, bh, &sm.ldk);
+    if (mx.quart) tma_load_tile_sw(sm.K2, &tmKc, k0, 0, (int)BH + bh, &sm.ldk);
+    tma_load_tile_sw(sm.V, &tmV, k0, h, b, &sm.ldk);
   }
   fetch(0, k0);
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
@@ -757,9 +757,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
-        mma_ss(tb, desc_kmajor(smem_u32(sm.K1), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_kmajor(smem_u32(sm.K2), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q2[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.V), 128, 16 * ks), desc_kmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_k_sw(smem_u32(sm.K1), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.K2), 16 * ks), desc_k_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 128, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
@@ -801,9 +801,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q2[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }

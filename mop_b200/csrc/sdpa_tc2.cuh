@@ -108,14 +108,14 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
       auto fetch = [&](int t) {
         const int s = t & (kStages - 1);
         mbar_expect_tx(&sm.ld[s], 2 * kT64);
-        tma_load_tile(sm.K[s], &tmK, 64 * t, h, b, &sm.ld[s]);
-        tma_load_tile(sm.V[s], &tmV, 64 * t, h, b, &sm.ld[s]);
+        tma_load_tile_sw(sm.K[s], &tmK, 64 * t, h, b, &sm.ld[s]);
+        tma_load_tile_sw(sm.V[s], &tmV, 64 * t, h, b, &sm.ld[s]);
       };
       const uint32_t id_s = idesc_bf16(128, 64, 0, 0);
-      const uint64_t dq = desc_kmajor(smem_u32(sm.Q), 128, 0), dk0 = desc_kmajor(smem_u32(sm.K[0]), 64, 0);
+      const uint64_t dq = desc_k_sw(smem_u32(sm.Q), 0), dk0 = desc_k_sw(smem_u32(sm.K[0]), 0);
       if (ntiles > 0) {
         mbar_expect_tx(&sm.ldq, kT128);
-        tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+        tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
         for (int t = 0; t < min(ntiles, kStages); ++t) fetch(t);
         mbar_wait(&sm.ldq, 0);
       }
@@ -132,10 +132,10 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
         TS(t, 2);
         const uint64_t dkk = dk0 + (uint64_t)(s * (kT64 >> 4));
         const uint32_t dst = tb + 64 * (t & 1);
-        // one K step = two 8-column chunks: +2*R*16 bytes (>> 4 in the descriptor's address field); the tiles are zero
-        // filled past dk, so the full 64-wide contraction is always right
+        // one K step = 16 columns = +32 bytes inside the 128-byte swizzle row (>> 4 in the descriptor's address field);
+        // the tiles are zero filled past dk, so the full 64-wide contraction is always right
 #pragma unroll
-        for (int ks = 0; ks < (MOP_DBG == 7 ? 1 : 4); ++ks) mma_ss(dst, dq + (uint64_t)(ks * 256), dkk + (uint64_t)(ks * 128), id_s, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < (MOP_DBG == 7 ? 1 : 4); ++ks) mma_ss(dst, dq + (uint64_t)(ks * 2), dkk + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
         mma_commit(&sm.bar_s[t & 1]);
         TS(t, 3);
         if (t >= 2 && t + 2 < ntiles) {   // refill the ring stage of tile t-2 once P V(t-2) (issued right after p_ready(t-2)) is done
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
     } else if (tid == 160) {
       // ---- O += P(t) V_t ---------------------------------------------------------------------------------------
       const uint32_t id_pv = idesc_bf16(128, 64, 0, 1);
-      const uint64_t dp0 = desc_kmajor(smem_u32(sm.P[0]), 128, 0), dv0 = desc_mnmajor(smem_u32(sm.V[0]), 64, 0);
+      const uint64_t dp0 = desc_kmajor(smem_u32(sm.P[0]), 128, 0), dv0 = desc_mn_sw(smem_u32(sm.V[0]), 0);
       TS_DECL
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & (kStages - 1);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
         TS(t, 2);
         const uint64_t dp = dp0 + (uint64_t)((t & 1) * (kT128 >> 4)), dv = dv0 + (uint64_t)(s * (kT64 >> 4));
 #pragma unroll
-        for (int ks = 0; ks < (MOP_DBG == 6 ? 1 : 4); ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 16), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < (MOP_DBG == 6 ? 1 : 4); ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 128), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
         mma_commit(&sm.bar_pv[t & 1]);
         mma_commit(&sm.fr[s]);
         TS(t, 3);
@@ -352,13 +352,13 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
   tc_fence_after();
   auto fetch = [&](int buf, int k0) {   // thread 0 only
     mbar_expect_tx(&sm.ld[buf], 2 * kT64);
-    tma_load_tile(sm.K[buf], &tmK, k0, h, b, &sm.ld[buf]);
-    tma_load_tile(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+    tma_load_tile_sw(sm.K[buf], &tmK, k0, h, b, &sm.ld[buf]);
+    tma_load_tile_sw(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldq, 2 * kT128);
-    tma_load_tile(sm.Q, &tmQ, q0, h, b, &sm.ldq);
-    tma_load_tile(sm.dO, &tmdO, q0, h, b, &sm.ldq);
+    tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    tma_load_tile_sw(sm.dO, &tmdO, q0, h, b, &sm.ldq);
     if (ntiles > 0) fetch(0, 0);
   }
   const float lse = p.lse[((int64_t)b * p.H + h) * Nq + (row_ok ? gi : Nq - 1)];
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {
-        mma_ss(tb, desc_kmajor(smem_u32(sm.Q), 128, 16 * ks), desc_kmajor(smem_u32(sm.K[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 64, desc_kmajor(smem_u32(sm.dO), 128, 16 * ks), desc_kmajor(smem_u32(sm.V[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 64, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.W), 128, 16 * ks), desc_mnmajor(smem_u32(sm.K[buf]), 64, 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.W), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       mma_commit(&sm.bar);
     }
   }
@@ -476,8 +476,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
   auto fetch = [&](int buf, int q0) {
     if (tid == 0) {
       mbar_expect_tx(&sm.ld[buf], 2 * kT64);
-      tma_load_tile(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
-      tma_load_tile(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
+      tma_load_tile_sw(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
+      tma_load_tile_sw(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
     }
     if (tid < 64) {
       const int i = min(q0 + tid, Nq - 1);
@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldk, 2 * kT128);
-    tma_load_tile(sm.K, &tmK, k0, h, b, &sm.ldk);
-    tma_load_tile(sm.V, &tmV, k0, h, b, &sm.ldk);
+    tma_load_tile_sw(sm.K, &tmK, k0, h, b, &sm.ldk);
+    tma_load_tile_sw(sm.V, &tmV, k0, h, b, &sm.ldk);
   }
   if (ntiles > 0) fetch(0, qstart);
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
-        mma_ss(tb, desc_kmajor(smem_u32(sm.K), 128, 16 * ks), desc_kmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 64, desc_kmajor(smem_u32(sm.V), 128, 16 * ks), desc_kmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb, desc_k_sw(smem_u32(sm.K), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+        mma_ss(tb + 64, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }
@@ -534,8 +534,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
       const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.dO[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.WT), 128, 16 * ks), desc_mnmajor(smem_u32(sm.Q[buf]), 64, 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.WT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar);
     }

@@ -28,23 +28,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // release.cta: t
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap after ~2 s of SM clock instead.
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try(a, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mop_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) break;
-  }
-  printf("mop_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
+  if (mbar_try(a, parity)) return;   // already complete: no clock read, no call
+  mbar_wait_slow(a, parity);
 }
 
 // ---- bulk (TMA, non-tensor) copies: one thread moves a contiguous block ---------------------------------
@@ -94,6 +101,19 @@ __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap*
       : "memory");
 }
 
+// 128-byte-swizzled variant: the activation is described as (column, token, head, batch) and a box {64, R, 1, 1} lands as R rows
+// of 128 bytes with the 16-byte chunks of row r XOR-swizzled by (r & 7) - the canonical SWIZZLE_128B operand layout of
+// tcgen05.mma (descriptors: desc_k_sw / desc_mn_sw).  One 128-byte request per row instead of eight 16-byte ones: 8x fewer
+// L2 requests and no half-used 32-byte sectors.  The tile base must be 1024-byte aligned.  (Host side: mop::make_tile_map_sw.)
+__device__ __forceinline__ void tma_load_tile_sw(void* smem_dst, const CUtensorMap* tm, int row0, int head, int batch, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row0), "r"(head), "r"(batch), "r"(smem_u32(bar))
+      : "memory");
+}
+// byte offset of element (r, c) inside a SWIZZLE_128B tile of 64 bf16 columns
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((((c >> 3) ^ r) & 7) << 4) + ((c & 7) << 1)); }
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -130,6 +150,14 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t R,
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t R, uint32_t k0) {
   return smem_desc(tile_saddr + k0 * 16, 128, R * 16);
 }
+// SWIZZLE_128B tiles (rows of 64 bf16 = 128 bytes, 8-row groups of 1024 bytes; layout_type 2)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
+// rows = M / N index, the 64 columns = K: K-major operand starting at K offset k0 (multiple of 16)
+__device__ __forceinline__ uint64_t desc_k_sw(uint32_t tile_saddr, uint32_t k0) { return smem_desc_sw128(tile_saddr + k0 * 2, 16, 1024); }
+// the 64 columns = M / N index, rows = K: MN-major operand starting at K offset (row) k0 (multiple of 16)
+__device__ __forceinline__ uint64_t desc_mn_sw(uint32_t tile_saddr, uint32_t k0) { return smem_desc_sw128(tile_saddr + k0 * 128, 1024, 1024); }
 // instruction descriptor: kind::f16, bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
