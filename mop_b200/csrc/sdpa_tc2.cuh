@@ -300,10 +300,17 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
   if (warp == 0) tmem_dealloc<256>(tb);
 }
 
-// probability and dS of one element given the raw dot product and dP
+// probability and dS / scale of one element given the raw dot product and dP (the factor `scale` of dS is applied once, to the
+// dQ / dK accumulators, instead of per element)
 __device__ __forceinline__ void elem(const MopSdpaParams& p, float raw, float dp, float lse, float dlt, bool masked, float& pr, float& ds) {
   pr = masked ? 0.f : ex2(fmaf(raw, p.scale * kLog2e, -lse * kLog2e));
-  ds = pr * (dp - dlt) * p.scale;
+  ds = pr * (dp - dlt);
+}
+// the same for an unmasked pair of elements on packed fp32 math: 3 FMA-pipe instructions + 2 MUFU for two elements
+__device__ __forceinline__ void elem2(float2 raw, float2 dp, float2 coef, float2 nlse, float2 ndlt, float2& pr, float2& ds) {
+  const float2 a = fma2(raw, coef, nlse);
+  pr = make_float2(ex2(a.x), ex2(a.y));
+  ds = mul2(pr, add2(dp, ndlt));
 }
 template <bool EXTRA>
 __device__ __forceinline__ void elem_x(const MopSdpaParams& p, int b, int h, int gi, int gj, float raw, float dp, float lse, float dlt,
@@ -312,7 +319,7 @@ __device__ __forceinline__ void elem_x(const MopSdpaParams& p, int b, int h, int
     float s = masked ? -INFINITY : raw * p.scale;
     if (!masked) s = apply_extra(p, b, h, gi, gj, s);
     pr = (s == -INFINITY) ? 0.f : ex2((s - lse) * kLog2e);
-    ds = pr * (dp - dlt) * p.scale;
+    ds = pr * (dp - dlt);
   } else {
     elem(p, raw, dp, lse, dlt, masked || (p.causal && gj > gi), pr, ds);
   }
@@ -321,7 +328,8 @@ __device__ __forceinline__ void elem_x(const MopSdpaParams& p, int b, int h, int
 struct __align__(128) SmemQ {
   unsigned char Q[kT128], dO[kT128], W[kT128];
   unsigned char K[2][kT64], V[2][kT64];
-  uint64_t bar;      // MMA completion
+  uint64_t bar;      // completion of S and dP (two issuing threads)
+  uint64_t bar2;     // completion of dQ += dS K
   uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
   uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
   const bool row_ok = gi < Nq;
   const int dks = (dk + 15) >> 4, c0 = 32 * wg;
   if (tid < 32) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&sm.bar, 2); mbar_init(&sm.bar2, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
   const size_t ystride = (size_t)p.H * dk;
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy) + ((int64_t)b * Nq * p.H + h) * dk;
   const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.y) + ((int64_t)b * Nq * p.H + h) * dk;
@@ -374,19 +382,27 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
     if (wg == 0) delta[((int64_t)b * p.H + h) * Nq + gi] = dlt;
   }
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
-  uint32_t phase = 0;
+  const float2 coef2 = make_float2(p.scale * kLog2e, p.scale * kLog2e), nlse2 = make_float2(-lse * kLog2e, -lse * kLog2e), ndlt2 = make_float2(-dlt, -dlt);
+  uint32_t phase = 0, phase2 = 0;
+  // The MMAs of one tile are issued by three threads of three different warps (S, dP, dQ): a lone issuing lane needs ~10 cycles
+  // per instruction, so one thread issuing all twelve MMAs and the TMA loads kept the other seven warps waiting.
+  const uint32_t id_in = idesc_bf16(128, 64, 0, 0), id_out = idesc_bf16(128, 64, 0, 1);
+  const uint64_t d_q = desc_k_sw(smem_u32(sm.Q), 0), d_do = desc_k_sw(smem_u32(sm.dO), 0), d_w = desc_kmajor(smem_u32(sm.W), 128, 0);
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+    if (it > 0) { mbar_wait(&sm.bar2, phase2); phase2 ^= 1; tc_fence_after(); }   // dQ(it-1): W and the other K / V buffer are free
     if (tid == 0) {
       if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
       if (it == 0) mbar_wait(&sm.ldq, 0);
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) {
-        mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 64, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      }
+      const uint64_t d_k = desc_k_sw(smem_u32(sm.K[buf]), 0);
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, d_q + (uint64_t)(2 * ks), d_k + (uint64_t)(2 * ks), id_in, ks > 0 ? 1u : 0u);
+      mma_commit(&sm.bar);
+    } else if (tid == 32) {
+      if (it == 0) mbar_wait(&sm.ldq, 0);
+      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
+      const uint64_t d_v = desc_k_sw(smem_u32(sm.V[buf]), 0);
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, d_do + (uint64_t)(2 * ks), d_v + (uint64_t)(2 * ks), id_in, ks > 0 ? 1u : 0u);
       mma_commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
@@ -397,26 +413,35 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
       tmem_ld_32x32b_x16(tl + col, v1);
       tmem_ld_32x32b_x16(tl + 64 + col, dp);
       tmem_ld_wait();
+      if (!EXTRA && !(p.causal && k0 + 63 > q0)) {
+        // no mask needed: zero-filled key rows (>= Nk) contribute nothing to dS K, rows >= Nq are never written
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int gj = k0 + col + e;
-        float pr;
-        elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], lse, dlt, gj >= Nk || !row_ok, pr, ws_[e]);
+        for (int e = 0; e < 16; e += 2) {
+          float2 pr, ds;
+          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, nlse2, ndlt2, pr, ds);
+          ws_[e] = ds.x; ws_[e + 1] = ds.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int gj = k0 + col + e;
+          float pr;
+          elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], lse, dlt, gj >= Nk || !row_ok, pr, ws_[e]);
+        }
       }
       const int ch = col >> 3;
       *reinterpret_cast<uint4*>(sm.W + ch * (128 * 16) + t * 16) = pack8(ws_);
       *reinterpret_cast<uint4*>(sm.W + (ch + 1) * (128 * 16) + t * 16) = pack8(ws_ + 8);
     }
     publish();
-    if (tid == 0) {
-      const uint32_t id = idesc_bf16(128, 64, 0, 1);
+    if (tid == 64) {
+      const uint64_t d_kt = desc_mn_sw(smem_u32(sm.K[buf]), 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.W), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
-      mma_commit(&sm.bar);
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb + 128, d_w + (uint64_t)(256 * ks), d_kt + (uint64_t)(128 * ks), id_out, (it > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&sm.bar2);
     }
   }
-  if (ntiles > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+  if (ntiles > 0) { mbar_wait(&sm.bar2, phase2); phase2 ^= 1; tc_fence_after(); }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.dq) + (((int64_t)b * Nq + (row_ok ? gi : 0)) * p.H + h) * dk;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -429,6 +454,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] *= p.scale;
     if (row_ok) {
       if (col < dk) *reinterpret_cast<uint4*>(out + col) = pack8(acc);
       if (col + 8 < dk) *reinterpret_cast<uint4*>(out + col + 8) = pack8(acc + 8);
@@ -443,7 +470,8 @@ struct __align__(128) SmemK {
   unsigned char K[kT128], V[kT128], PT[kT128], WT[kT128];
   unsigned char Q[2][kT64], dO[2][kT64];
   float vec[2][2][64];   // per query of the tile: lse, delta
-  uint64_t bar;      // MMA completion
+  uint64_t bar;      // completion of S^T and dP^T (two issuing threads)
+  uint64_t bar2;     // completion of dV += P^T dO and dK += dS^T Q (two issuing threads)
   uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
   uint64_t ldk;      // TMA completion of the key / value tiles
   uint32_t tmem_slot;
@@ -464,7 +492,7 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
   const bool key_ok = gj < Nk;
   const int dks = (dk + 15) >> 4, c0 = 32 * wg;
   if (tid < 32) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&sm.bar, 2); mbar_init(&sm.bar2, 2); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
   const float* lsep = p.lse + ((int64_t)b * p.H + h) * Nq;
   const float* dltp = delta + ((int64_t)b * p.H + h) * Nq;
   const int qstart = p.causal ? min(k0, Nq) & ~63 : 0;   // queries i >= j only when causal
@@ -493,20 +521,21 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
   }
   if (ntiles > 0) fetch(0, qstart);
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase2 = 0;
+  // four issuing threads in four warps (S^T, dP^T | dV, dK): see bwd_dq_kernel
+  const uint32_t id_in = idesc_bf16(128, 64, 0, 0), id_out = idesc_bf16(128, 64, 0, 1);
+  const uint64_t d_k = desc_k_sw(smem_u32(sm.K), 0), d_v = desc_k_sw(smem_u32(sm.V), 0);
+  const uint64_t d_pt = desc_kmajor(smem_u32(sm.PT), 128, 0), d_wt = desc_kmajor(smem_u32(sm.WT), 128, 0);
   for (int it = 0; it < ntiles; ++it) {
     const int q0 = qstart + it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+    if (it > 0) { mbar_wait(&sm.bar2, phase2); phase2 ^= 1; tc_fence_after(); }
     if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();   // the per-query vectors of this tile are visible to every thread
-    if (tid == 0) {
+    if (tid == 0 || tid == 32) {   // transposed tiles: rows = keys, columns = queries
       if (it == 0) mbar_wait(&sm.ldk, 0);
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
-        mma_ss(tb, desc_k_sw(smem_u32(sm.K), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 64, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      }
+      const uint64_t da = tid ? d_v : d_k, db = desc_k_sw(smem_u32(tid ? sm.dO[buf] : sm.Q[buf]), 0);
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb + (tid ? 64 : 0), da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), id_in, ks > 0 ? 1u : 0u);
       mma_commit(&sm.bar);
     }
     mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
@@ -517,10 +546,24 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
       tmem_ld_32x32b_x16(tl + colb, v1);
       tmem_ld_32x32b_x16(tl + 64 + colb, dp);
       tmem_ld_wait();
+      if (!EXTRA && !(p.causal && q0 < k0 + 127)) {
+        // no mask needed: zero-filled query rows (>= Nq) contribute nothing to P^T dO / dS^T Q, keys >= Nk are never written
+        const float2 coef2 = make_float2(p.scale * kLog2e, p.scale * kLog2e), nl2e = make_float2(-kLog2e, -kLog2e), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int col = colb + e, gi = q0 + col;
-        elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], sm.vec[buf][0][col], sm.vec[buf][1][col], gi >= Nq || !key_ok, pt[e], wt[e]);
+        for (int e = 0; e < 16; e += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(&sm.vec[buf][0][colb + e]), d4 = *reinterpret_cast<const float4*>(&sm.vec[buf][1][colb + e]);
+          float2 pr, ds;
+          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, mul2(make_float2(l4.x, l4.y), nl2e), mul2(make_float2(d4.x, d4.y), neg1), pr, ds);
+          pt[e] = pr.x; pt[e + 1] = pr.y; wt[e] = ds.x; wt[e + 1] = ds.y;
+          elem2(make_float2(v1[e + 2], v1[e + 3]), make_float2(dp[e + 2], dp[e + 3]), coef2, mul2(make_float2(l4.z, l4.w), nl2e), mul2(make_float2(d4.z, d4.w), neg1), pr, ds);
+          pt[e + 2] = pr.x; pt[e + 3] = pr.y; wt[e + 2] = ds.x; wt[e + 3] = ds.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = colb + e, gi = q0 + col;
+          elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], sm.vec[buf][0][col], sm.vec[buf][1][col], gi >= Nq || !key_ok, pt[e], wt[e]);
+        }
       }
       const int ch = colb >> 3;
       *reinterpret_cast<uint4*>(sm.PT + ch * (128 * 16) + t * 16) = pack8(pt);
@@ -529,18 +572,15 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
       *reinterpret_cast<uint4*>(sm.WT + (ch + 1) * (128 * 16) + t * 16) = pack8(wt + 8);
     }
     publish();
-    if (tid == 0) {
-      const uint32_t id = idesc_bf16(128, 64, 0, 1);
-      const uint32_t acc0 = it > 0 ? 1u : 0u;
+    if (tid == 64 || tid == 96) {   // K index = queries of this tile
+      const bool second = tid == 96;
+      const uint64_t da = second ? d_wt : d_pt, db = desc_mn_sw(smem_u32(second ? sm.Q[buf] : sm.dO[buf]), 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.WT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-      }
-      mma_commit(&sm.bar);
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb + (second ? 192 : 128), da + (uint64_t)(256 * ks), db + (uint64_t)(128 * ks), id_out, (it > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&sm.bar2);
     }
   }
-  if (ntiles > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }
+  if (ntiles > 0) { mbar_wait(&sm.bar2, phase2); phase2 ^= 1; tc_fence_after(); }
   __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + (((int64_t)b * Nk + (key_ok ? gj : 0)) * p.H + h) * dk;
   __nv_bfloat16* dkp = reinterpret_cast<__nv_bfloat16*>(p.dk_) + (((int64_t)b * Nk + (key_ok ? gj : 0)) * p.H + h) * dk;
 #pragma unroll
@@ -555,6 +595,8 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
 #pragma unroll
       for (int e = 0; e < 16; ++e) { av[e] = 0.f; ak[e] = 0.f; }
     }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) ak[e] *= p.scale;
     if (key_ok) {
       if (col < dk) { *reinterpret_cast<uint4*>(dv + col) = pack8(av); *reinterpret_cast<uint4*>(dkp + col) = pack8(ak); }
       if (col + 8 < dk) { *reinterpret_cast<uint4*>(dv + col + 8) = pack8(av + 8); *reinterpret_cast<uint4*>(dkp + col + 8) = pack8(ak + 8); }

@@ -114,6 +114,23 @@ __device__ __forceinline__ void tma_load_tile_sw(void* smem_dst, const CUtensorM
 // byte offset of element (r, c) inside a SWIZZLE_128B tile of 64 bf16 columns
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((((c >> 3) ^ r) & 7) << 4) + ((c & 7) << 1)); }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2): one issue slot for two elements --------------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
