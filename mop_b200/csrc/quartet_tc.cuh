@@ -315,6 +315,8 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
   tc_fence_before();
   __syncthreads();   // the Gram tiles are dead: their buffers may receive key / value tiles
   float m_run = -INFINITY, l_run = 0.f;
+  const float fa_ = mx.quart ? a1 * (1.f - mx.m) : a1, fb_ = mx.quart ? a1 * mx.m * mx.gam * a2 : 0.f;
+  const float2 fA2 = make_float2(fa_, fa_), fB2 = make_float2(fb_, fb_), l2e2 = make_float2(kLog2e, kLog2e);
   const int k_end = min(T, q0 + 128);
   const int ntiles = (k_end + 63) >> 6;
   for (int it = 0; it < ntiles; ++it) {
@@ -340,7 +342,11 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) sc[16 * c + e] = mix_n(mx, v1[e] * a1, mx.quart ? v2[e] * a2 : 0.f);
+      for (int e = 0; e < 16; e += 2) {   // mix = n1 ((1-m) + m gamma n2) = u (fA + fB v) on packed fp32 math
+        const float2 tt = mx.quart ? fma2(fB2, make_float2(v2[e], v2[e + 1]), fA2) : fA2;
+        const float2 r = mul2(make_float2(v1[e], v1[e + 1]), tt);
+        sc[16 * c + e] = r.x; sc[16 * c + e + 1] = r.y;
+      }
     }
     if (need_mask) {   // tiles on the diagonal / past the end only (uniform branch)
 #pragma unroll
@@ -376,15 +382,21 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
     }
     l_run *= corr;
     m_run = m_new;
-    float ps = 0.f;
+    float2 ps2 = make_float2(0.f, 0.f);
+    const float2 nmb2 = make_float2(-mb, -mb);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float pv[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { pv[e] = ex2(fmaf(sc[8 * c + e], kLog2e, -mb)); ps += pv[e]; }
+      for (int e = 0; e < 8; e += 2) {
+        const float2 a = fma2(make_float2(sc[8 * c + e], sc[8 * c + e + 1]), l2e2, nmb2);
+        const float2 pr = make_float2(ex2(a.x), ex2(a.y));
+        ps2 = add2(ps2, pr);
+        pv[e] = pr.x; pv[e + 1] = pr.y;
+      }
       *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
     }
-    l_run += ps;
+    l_run += ps2.x + ps2.y;
     publish();
     if (tid == 0) {
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
@@ -506,6 +518,13 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
+  // Unmasked tiles (entirely below the diagonal; zero-filled key rows >= T contribute nothing) run on packed fp32 math with the
+  // per-row constants folded in.  With u, v the raw dot products:  t = f / (sigma1+eps) = A1 + B1 v,  s = scale u t,
+  // D = P (dP - delta),  W1 = D t,  W2 = D u B1;  the row sums the epilogue needs all follow from Sa = sum D u, Sb = sum D u v.
+  const float fA = mx.quart ? 1.f - mx.m : 1.f, fB = mx.quart ? mx.m * mx.gam * p.scale * i2 : 0.f;   // f = fA + fB v
+  const float2 A1 = make_float2(fA * i1, fA * i1), B1 = make_float2(fB * i1, fB * i1), cs2 = make_float2(p.scale * kLog2e, p.scale * kLog2e);
+  const float2 L2 = make_float2(-lse * kLog2e, -lse * kLog2e), nd2 = make_float2(-dlt, -dlt);
+  float2 Sa2 = make_float2(0.f, 0.f), Sb2 = make_float2(0.f, 0.f);
   const int k_end = min(T, q0 + 128);
   const int ntiles = (k_end + 63) >> 6;
   for (int it = 0; it < ntiles; ++it) {
@@ -532,18 +551,32 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + col, v2);
       tmem_ld_32x32b_x16(tl + 128 + col, dp);
       tmem_ld_wait();
+      if (!HAS_MASK && k0 + 63 <= q0) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int gj = k0 + col + e;
-        const bool masked = gj > gi || gj >= T || !row_ok;
-        float addm = 0.f;
-        if constexpr (HAS_MASK)
-          if (!masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
-        const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, lse, dlt, masked, addm, &sc0, &sc1);
-        g1 = fmaf(o.dn1, o.c1, g1);
-        g2 = fmaf(o.dn2, o.c2, g2);
-        w1[e] = o.dn1 * i1;
-        w2[e] = o.dn2 * i2;
+        for (int e = 0; e < 16; e += 2) {
+          const float2 u = make_float2(v1[e], v1[e + 1]), v = mx.quart ? make_float2(v2[e], v2[e + 1]) : make_float2(0.f, 0.f);
+          const float2 tt = fma2(B1, v, A1);
+          const float2 a = fma2(mul2(u, tt), cs2, L2);
+          const float2 D = mul2(make_float2(ex2(a.x), ex2(a.y)), add2(make_float2(dp[e], dp[e + 1]), nd2));
+          const float2 Du = mul2(D, u), W1 = mul2(D, tt), W2 = mul2(Du, B1);
+          Sa2 = add2(Sa2, Du);
+          Sb2 = fma2(Du, v, Sb2);
+          w1[e] = W1.x; w1[e + 1] = W1.y; w2[e] = W2.x; w2[e + 1] = W2.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int gj = k0 + col + e;
+          const bool masked = gj > gi || gj >= T || !row_ok;
+          float addm = 0.f;
+          if constexpr (HAS_MASK)
+            if (!masked) addm = p.add_mask[(int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)gj * p.am_sk];
+          const ElemOut o = elem_bwd(mx, v1[e], mx.quart ? v2[e] : 0.f, dp[e], p.scale, i1, i2, lse, dlt, masked, addm, &sc0, &sc1);
+          g1 = fmaf(o.dn1, o.c1, g1);
+          g2 = fmaf(o.dn2, o.c2, g2);
+          w1[e] = o.dn1 * i1;
+          w2[e] = o.dn2 * i2;
+        }
       }
       const int ch = col >> 3;
       *reinterpret_cast<uint4*>(sm.W1 + ch * (128 * 16) + t * 16) = pack8(w1);
@@ -566,6 +599,15 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
   if (tid != 0) mbar_wait(&sm.ldq, 0);   // (already complete: orders the TMA-written query tiles before the generic reads below)
+  if (row_ok) {   // fold the packed-math tiles into the row sums
+    const float Sa = Sa2.x + Sa2.y, Sb = Sb2.x + Sb2.y, al1 = p.scale * i1, al2 = p.scale * i2;
+    g1 += p.scale * (fA * Sa + fB * Sb);
+    if (mx.quart) {
+      g2 += mx.m * mx.gam * al1 * p.scale * Sb;
+      sc0 += al1 * (mx.gam * al2 * Sb - Sa);
+      sc1 += mx.m * al1 * al2 * Sb;
+    }
+  }
   // row coefficients: combine the two column halves
   sm.gx[wg][0][t] = g1;
   sm.gx[wg][1][t] = g2;
@@ -684,7 +726,7 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
 struct __align__(128) SmemK {
   unsigned char K1[kT128], K2[kT128], V[kT128], PT[kT128], W1T[kT128], W2T[kT128];
   unsigned char Q[2][kT64], Q2[2][kT64], dO[2][kT64];   // double buffered query-side tiles
-  float vec[2][4][64];                                   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta
+  float vec[2][8][64];   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta | packed-math constants A1, B1, L, -delta
   uint64_t bar;      // MMA completion
   uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
   uint64_t ldk;      // TMA completion of the key / value tiles
@@ -750,6 +792,11 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
     if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place (each thread converts the values it fetched itself)
       sm.vec[buf][0][tid] = 1.f / (sm.vec[buf][0][tid] + mx.eps);
       sm.vec[buf][1][tid] = mx.quart ? 1.f / (sm.vec[buf][1][tid] + mx.eps) : 0.f;
+      const float i1 = sm.vec[buf][0][tid], i2 = sm.vec[buf][1][tid];
+      sm.vec[buf][4][tid] = (mx.quart ? 1.f - mx.m : 1.f) * i1;                       // t = f / (sigma1+eps) = A1 + B1 v  (see bwd_dq_kernel)
+      sm.vec[buf][5][tid] = mx.quart ? mx.m * mx.gam * p.scale * i2 * i1 : 0.f;
+      sm.vec[buf][6][tid] = -sm.vec[buf][2][tid] * kLog2e;
+      sm.vec[buf][7][tid] = -sm.vec[buf][3][tid];
     }
     __syncthreads();   // the per-query vectors of this tile are visible to every thread
     if (tid == 0) {
@@ -772,6 +819,27 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + colb, v2);
       tmem_ld_32x32b_x16(tl + 128 + colb, dp);
       tmem_ld_wait();
+      if (!HAS_MASK && q0 >= k0 + 127) {   // unmasked tile (zero-filled query rows >= T contribute nothing): packed fp32 math
+        const float2 cs2 = make_float2(p.scale * kLog2e, p.scale * kLog2e);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 A4 = *reinterpret_cast<const float4*>(&sm.vec[buf][4][colb + e]), B4 = *reinterpret_cast<const float4*>(&sm.vec[buf][5][colb + e]);
+          const float4 L4 = *reinterpret_cast<const float4*>(&sm.vec[buf][6][colb + e]), N4 = *reinterpret_cast<const float4*>(&sm.vec[buf][7][colb + e]);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int x = e + 2 * hh;
+            const float2 A1 = hh ? make_float2(A4.z, A4.w) : make_float2(A4.x, A4.y), B1 = hh ? make_float2(B4.z, B4.w) : make_float2(B4.x, B4.y);
+            const float2 L2 = hh ? make_float2(L4.z, L4.w) : make_float2(L4.x, L4.y), nd2 = hh ? make_float2(N4.z, N4.w) : make_float2(N4.x, N4.y);
+            const float2 u = make_float2(v1[x], v1[x + 1]), v = mx.quart ? make_float2(v2[x], v2[x + 1]) : make_float2(0.f, 0.f);
+            const float2 tt = fma2(B1, v, A1);
+            const float2 a = fma2(mul2(u, tt), cs2, L2);
+            const float2 pr = make_float2(ex2(a.x), ex2(a.y));
+            const float2 D = mul2(pr, add2(make_float2(dp[x], dp[x + 1]), nd2));
+            const float2 W1 = mul2(D, tt), W2 = mul2(mul2(D, u), B1);
+            pt[x] = pr.x; pt[x + 1] = pr.y; w1[x] = W1.x; w1[x + 1] = W1.y; w2[x] = W2.x; w2[x + 1] = W2.y;
+          }
+        }
+      } else
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int col = colb + e, gi = q0 + col;
