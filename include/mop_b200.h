@@ -186,7 +186,8 @@ int mop_selftest_umma128(const float* A, const float* B, float* D, int Ma, int N
                          int b_k0, void* cuda_stream);
 
 /* Bring-up check of the TMA tile load: rows [row0, row0 + R) of (batch, head) of a bf16 [B][N][H][dk] tensor with element
- * strides (sb, sn, sh) -> the R x 64 chunk-major shared-memory tile image, copied to `out` (R * 128 bytes). */
+ * strides (sb, sn, sh) -> the R x 64 shared-memory tile image in the 128-byte swizzled operand layout (16-byte chunk c of row r
+ * stored at chunk c ^ (r & 7)), copied to `out` (R * 128 bytes). */
 int mop_selftest_tma(const void* x, void* out, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int R, int row0,
                      int head, int batch, void* cuda_stream);
 

@@ -59,23 +59,8 @@ static TensorMapEncodeFn tensor_map_encoder() {
   }();
   return fn;
 }
-// bf16 tensor [B][N][H][dk] with element strides (sb, sn, sh), last dimension contiguous; box = box_rows tokens x 64 columns
-int make_tile_map(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows) {
-  TensorMapEncodeFn enc = tensor_map_encoder();
-  MOP_REQUIRE(enc != nullptr, MOP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  auto stride = [](int64_t elems, int dim) -> cuuint64_t { return (dim > 1 && elems > 0) ? (cuuint64_t)elems * 2 : 16; };
-  const cuuint64_t dims[5] = {8, (cuuint64_t)N, (cuuint64_t)(dk / 8), (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t strides[4] = {stride(sn, N), 16, stride(sh, H), stride(sb, B)};
-  const cuuint32_t box[5] = {8, (cuuint32_t)box_rows, 8, 1, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MOP_REQUIRE(rc == CUDA_SUCCESS, MOP_ECUDA, "cuTensorMapEncodeTiled failed with code %d (N=%d H=%d dk=%d strides %lld %lld %lld)", (int)rc, N, H, dk,
-              (long long)sb, (long long)sn, (long long)sh);
-  return MOP_OK;
-}
-
-// same tensor as (column, token, head, batch); box = 64 columns x box_rows tokens, 128-byte swizzle (tc_common.cuh: tma_load_tile_sw)
+// bf16 tensor [B][N][H][dk] with element strides (sb, sn, sh), last dimension contiguous, described to the TMA unit as
+// (column, token, head, batch); box = 64 columns x box_rows tokens, 128-byte swizzle (tc_common.cuh: tma_load_tile_sw)
 int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   MOP_REQUIRE(enc != nullptr, MOP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -485,7 +470,7 @@ extern "C" int mop_selftest_tma(const void* x, void* out, int B, int N, int H, i
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");
   MOP_REQUIRE(R > 0 && R <= 256 && dk % 8 == 0 && dk <= 64, MOP_EINVAL, "bad selftest shape");
   CUtensorMap tm;
-  int rc = make_tile_map(&tm, x, B, N, H, dk, sb, sn, sh, R);
+  int rc = make_tile_map_sw(&tm, x, B, N, H, dk, sb, sn, sh, R);
   if (rc != MOP_OK) return rc;
   MOP_CHECK_CUDA(cudaFuncSetAttribute(tc::selftest_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 128 + 1024));
   tc::selftest_tma_kernel<<<1, 128, R * 128 + 1024, (cudaStream_t)stream>>>(tm, reinterpret_cast<unsigned char*>(out), R, row0, head, batch);

@@ -15,10 +15,8 @@
 #pragma once
 #include "quartet_tc.cuh"
 
-#ifndef MOP_DBG
-#define MOP_DBG 0
-#endif
-#if MOP_DBG == 9
+// -DMOP_FWD_TIMELINE: one CTA of the forward kernel prints clock64 stamps of its roles per tile (tools/ts_timeline.py); development only
+#ifdef MOP_FWD_TIMELINE
 #define TS_DECL long long ts_[24][6]; const bool ts_on = blockIdx.x == 700;
 #define TS(t, k) do { if (ts_on && (t) < 24) ts_[t][k] = clock64(); } while (0)
 #define TS_DUMP(name, n, K) do { if (ts_on) for (int t_ = 0; t_ < (n) && t_ < 24; ++t_) printf("%s t= %d %lld %lld %lld %lld %lld %lld\n", name, t_, ts_[t_][0], ts_[t_][1], ts_[t_][2], ts_[t_][3], K > 4 ? ts_[t_][4] : 0LL, K > 5 ? ts_[t_][5] : 0LL); } while (0)
@@ -125,9 +123,6 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
         TS(t, 0);
         if (t >= 2) { mbar_wait(&sm.s_free[t & 1], (uint32_t)((t - 2) >> 1) & 1u); tc_fence_after(); }   // S(t-2) has been read
         TS(t, 1);
-#if MOP_DBG == 5
-        if (t < kStages)
-#endif
         mbar_wait(&sm.ld[s], (uint32_t)(t >> 2) & 1u);
         TS(t, 2);
         const uint64_t dkk = dk0 + (uint64_t)(s * (kT64 >> 4));
@@ -135,14 +130,12 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
         // one K step = 16 columns = +32 bytes inside the 128-byte swizzle row (>> 4 in the descriptor's address field);
         // the tiles are zero filled past dk, so the full 64-wide contraction is always right
 #pragma unroll
-        for (int ks = 0; ks < (MOP_DBG == 7 ? 1 : 4); ++ks) mma_ss(dst, dq + (uint64_t)(ks * 2), dkk + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) mma_ss(dst, dq + (uint64_t)(ks * 2), dkk + (uint64_t)(ks * 2), id_s, ks > 0 ? 1u : 0u);
         mma_commit(&sm.bar_s[t & 1]);
         TS(t, 3);
         if (t >= 2 && t + 2 < ntiles) {   // refill the ring stage of tile t-2 once P V(t-2) (issued right after p_ready(t-2)) is done
           mbar_wait(&sm.fr[(t - 2) & (kStages - 1)], (uint32_t)((t - 2) >> 2) & 1u);
-#if MOP_DBG != 5
           fetch(t + 2);
-#endif
         }
         TS(t, 4);
       }
@@ -155,9 +148,6 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & (kStages - 1);
         TS(t, 0);
-#if MOP_DBG == 5
-        if (t < kStages)
-#endif
         mbar_wait(&sm.ld[s], (uint32_t)(t >> 2) & 1u);   // V_t (long since landed: S(t) already used K_t of the same stage)
         TS(t, 1);
         mbar_wait(&sm.p_ready[t & 1], (uint32_t)(t >> 1) & 1u);   // P(t) written into P[t & 1]
@@ -165,7 +155,7 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
         TS(t, 2);
         const uint64_t dp = dp0 + (uint64_t)((t & 1) * (kT128 >> 4)), dv = dv0 + (uint64_t)(s * (kT64 >> 4));
 #pragma unroll
-        for (int ks = 0; ks < (MOP_DBG == 6 ? 1 : 4); ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 128), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 128), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
         mma_commit(&sm.bar_pv[t & 1]);
         mma_commit(&sm.fr[s]);
         TS(t, 3);
@@ -187,14 +177,9 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
       tc_fence_after();
       TS(it, 1);
       float sc[64];
-#if MOP_DBG == 4
-#pragma unroll
-      for (int e = 0; e < 64; ++e) sc[e] = (float)(e + it) * 0.01f;
-#else
       tmem_ld_32x32b_x32(tl + 64 * (it & 1), sc);
       tmem_ld_32x32b_x32(tl + 64 * (it & 1) + 32, sc + 32);
       tmem_ld_wait();
-#endif
       tc_fence_before();
       mbar_arrive(&sm.s_free[it & 1]);
       TS(it, 2);
@@ -246,27 +231,22 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
       }
       l_run *= corr;
       m_ref = m_new;
-      float ps0 = 0.f, ps1 = 0.f;
+      float2 ps0 = make_float2(0.f, 0.f), ps1 = ps0;   // packed fp32 pairs: one FFMA2 / FADD2 per two elements
+      const float2 coef2 = make_float2(coef, coef), nmb2 = make_float2(-mb, -mb);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float pv[8];
 #pragma unroll
-#if MOP_DBG == 1
-        for (int e = 0; e < 8; ++e) pv[e] = fmaf(sc[8 * c + e], coef, -mb);
-#else
-        for (int e = 0; e < 8; ++e) pv[e] = ex2(fmaf(sc[8 * c + e], coef, -mb));
-#endif
-        ps0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        ps1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-#if MOP_DBG == 3
-        if (ps0 == 123.456f)
-#endif
+        for (int e = 0; e < 8; e += 2) {
+          const float2 a = fma2(make_float2(sc[8 * c + e], sc[8 * c + e + 1]), coef2, nmb2);
+          pv[e] = ex2(a.x); pv[e + 1] = ex2(a.y);
+        }
+        ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
+        ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
         *reinterpret_cast<uint4*>(sm.P[it & 1] + c * (128 * 16) + tid * 16) = pack8(pv);
       }
-      l_run += ps0 + ps1;
-#if MOP_DBG != 2
+      l_run += (ps0.x + ps0.y) + (ps1.x + ps1.y);
       fence_async_smem();   // P (generic proxy) -> tensor pipe (async proxy)
-#endif
       tc_fence_before();    // this thread's TMEM reads / writes precede the MMAs issued after the arrive is observed
       mbar_arrive(&sm.p_ready[it & 1]);
       TS(it, 5);

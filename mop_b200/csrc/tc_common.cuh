@@ -90,21 +90,12 @@ __device__ __forceinline__ void cp_async_block(void* smem_dst, const void* gsrc,
 }
 
 // ---- TMA tensor-map tile loads --------------------------------------------------------------------------------
-// A [.., tokens, .., dk] bf16 tensor is described to the TMA unit as the 5-D tensor
-//   (8 elements, token, 8-element chunk, head, batch)  with byte strides  (token stride, 16, head stride, batch stride)
-// so that a box {8, R, 8, 1, 1} lands in shared memory as [chunk][row][8 elements] = the chunk-major operand tile of this
-// library, in one instruction; rows / chunks outside the tensor are zero filled.  (Host side: mop::make_tile_map.)
-__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tm, int row0, int head, int batch, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row0), "r"(0), "r"(head), "r"(batch), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// 128-byte-swizzled variant: the activation is described as (column, token, head, batch) and a box {64, R, 1, 1} lands as R rows
-// of 128 bytes with the 16-byte chunks of row r XOR-swizzled by (r & 7) - the canonical SWIZZLE_128B operand layout of
-// tcgen05.mma (descriptors: desc_k_sw / desc_mn_sw).  One 128-byte request per row instead of eight 16-byte ones: 8x fewer
-// L2 requests and no half-used 32-byte sectors.  The tile base must be 1024-byte aligned.  (Host side: mop::make_tile_map_sw.)
+// A [.., tokens, .., dk] bf16 tensor is described to the TMA unit as (column, token, head, batch); a box {64, R, 1, 1} lands in
+// shared memory as R rows of 128 bytes with the 16-byte chunks of row r XOR-swizzled by (r & 7) - the canonical SWIZZLE_128B
+// operand layout of tcgen05.mma (descriptors: desc_k_sw / desc_mn_sw), usable K-major (rows = M/N index) and MN-major
+// (rows = K index) from the same bytes.  Rows / columns outside the tensor are zero filled; the tile base must be 1024-byte
+// aligned.  (Host side: mop::make_tile_map_sw.)  A first version used 16-byte inner boxes (chunk-major tiles): eight times the
+// L2 requests and half of every 32-byte sector wasted - lts tag throughput 57 %, TMA latency ~4000 cycles under load.
 __device__ __forceinline__ void tma_load_tile_sw(void* smem_dst, const CUtensorMap* tm, int row0, int head, int batch, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256, 1) selftest128_kernel(const float* A, con
 }
 
 
-// Bring-up of the TMA tile load: rows [row0, row0 + R) of head `head`, batch `batch` of a [B][N][H][dk] bf16 tensor -> chunk-major
-// tile in shared memory -> copied out verbatim (R * 128 bytes) for comparison on the host.
+// Bring-up of the TMA tile load: rows [row0, row0 + R) of head `head`, batch `batch` of a [B][N][H][dk] bf16 tensor -> 128-byte
+// swizzled tile in shared memory -> copied out verbatim (R * 128 bytes) for comparison on the host.
 __global__ void __launch_bounds__(128, 1) selftest_tma_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int R, int row0,
                                                               int head, int batch) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128, 1) selftest_tma_kernel(const __grid_const
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar, (uint32_t)R * 128u);
-    tma_load_tile(smem, &tm, row0, head, batch, &bar);
+    tma_load_tile_sw(smem, &tm, row0, head, batch, &bar);
   }
   mbar_wait(&bar, 0);
   for (int i = tid; i < R * 128 / 16; i += 128) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];

@@ -63,8 +63,8 @@ def test_umma_m128_thread_per_row(Ma, Nn, K, b_mn, Ra, Rb, Kb, b_k0):
     (2, 196, 4, 56, 128, 128, 2, 0, "qkv"),     # a q/k/v slice of a [B,N,3,H,dk] projection, dk = 56, rows past the end
     (1, 70, 1, 16, 64, 64, 0, 0, "bnhd"),       # single head / batch (degenerate strides), mostly out of bounds
 ])
-def test_tma_tile_load_chunk_major(B, N, H, dk, R, row0, head, batch, layout):
-    """cp.async.bulk.tensor tile load through the 5-D tensor map lands as the chunk-major operand tile, zero filled."""
+def test_tma_tile_load_swizzle128(B, N, H, dk, R, row0, head, batch, layout):
+    """cp.async.bulk.tensor tile load through the 4-D tensor map lands as the 128-byte-swizzled operand tile, zero filled."""
     from mop_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(N + dk)
@@ -79,9 +79,13 @@ def test_tma_tile_load_chunk_major(B, N, H, dk, R, row0, head, batch, layout):
                               R, row0, head, batch, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
-    got = out.view(torch.bfloat16).view(8, R, 8).float().cpu()          # [chunk][row][8]
+    got = out.view(torch.bfloat16).view(R, 8, 8).float().cpu()          # [row][stored chunk][8]
     want = torch.zeros(R, 64)
     rows = x[batch, row0:row0 + R, head].float().cpu()
     want[:rows.shape[0], :dk] = rows
-    want = want.view(R, 8, 8).permute(1, 0, 2)                           # [chunk][row][8]
-    assert torch.equal(got, want)
+    want = want.view(R, 8, 8)                                            # [row][logical chunk][8]
+    r = torch.arange(R).view(R, 1)
+    stored = torch.arange(8).view(1, 8) ^ (r & 7)                        # logical chunk c of row r is stored at chunk c ^ (r & 7)
+    swz = torch.empty_like(want)
+    swz[r.expand(R, 8), stored] = want
+    assert torch.equal(got, swz)

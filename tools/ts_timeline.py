@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Print the per-tile clock64 timeline written by a -DMOP_DBG=9 build (development aid)."""
+"""Print the per-tile clock64 timeline written by a -DMOP_FWD_TIMELINE build (development aid)."""
 import re, sys
 L = [l.split() for l in open(sys.argv[1]) if re.match(r'(S-lane|PV-lane|softmax) t=', l)]
 base = min(int(x) for l in L for x in l[3:] if int(x) > 0)
