@@ -214,10 +214,16 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
   const Frag f;
 
   if (warp == 0) tmem_alloc<TmemCols<BWD>::value>(&sv_.tmem_slot);
-  if (tid == 0) { mbar_init(&sv_.bar, 1); fence_mbar_init(); }
+  // The MMAs of one step are issued by lane 0 of ALL four warps (independent destination tiles, dealt round-robin): a lone
+  // issuing lane needs ~10 cycles per instruction and ~12 instructions per tcgen05.mma, and everybody else waits for it.
+  // Every leader commits (a commit with nothing outstanding arrives at once), so the barrier always counts four arrivals.
+  constexpr int kIssuers = 4;
+  if (tid == 0) { mbar_init(&sv_.bar, kIssuers); fence_mbar_init(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const bool leader = (tid & 31) == 0;
+  auto mine = [&](int idx) { return (idx & (kIssuers - 1)) == warp; };
   const uint32_t tbase = sv_.tmem_slot;
   const uint32_t tlane = tbase + ((uint32_t)(32 * warp) << 16);  // this warp's TMEM subpartition
   uint32_t phase = 0;
@@ -295,9 +301,11 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
     // =================================================================================================
     // stage 1: S_i = Qc_i K^T   (bwd: also dA = dY V_1^T)
     // =================================================================================================
-    if (tid == 0) {
-      for (int i = 0; i < V; ++i) gemm(kTS + i, 0, taddr(SL::QC + i), false, taddr(SL::K), false, false, ksteps, 64);
-      if constexpr (BWD) gemm(kTY, 0, taddr(Slots<true>::DY), false, taddr(SL::V1), false, false, ksteps, 64);
+    if (leader) {
+      for (int i = 0; i < V; ++i)
+        if (mine(i)) gemm(kTS + i, 0, taddr(SL::QC + i), false, taddr(SL::K), false, false, ksteps, 64);
+      if constexpr (BWD)
+        if (mine(V)) gemm(kTY, 0, taddr(Slots<true>::DY), false, taddr(SL::V1), false, false, ksteps, 64);
       mma_commit(&sv_.bar);
     }
     wait_mma();
@@ -320,9 +328,9 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
       uint32_t xf = taddr(SL::A + 0), xr = taddr(SL::A + V - 1);
       for (int s = 1; s < V; ++s) {
         publish();
-        if (tid == 0) {
-          gemm(kTF, 0, xf, false, taddr(SL::A + s), true, false, 4, 64);
-          gemm(kTR, 0, xr, false, taddr(SL::A + V - 1 - s), true, false, 4, 64);
+        if (leader) {
+          if (mine(0)) gemm(kTF, 0, xf, false, taddr(SL::A + s), true, false, 4, 64);
+          if (mine(1)) gemm(kTR, 0, xr, false, taddr(SL::A + V - 1 - s), true, false, 4, 64);
           mma_commit(&sv_.bar);
         }
         wait_mma();
@@ -436,9 +444,11 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
       // y = A V_1 + w F V_V
       // ===============================================================================================
       publish();
-      if (tid == 0) {
-        gemm(kTY, 0, taddr(SL::AMIX), false, taddr(SL::V1), true, false, 4, 64);
-        gemm(kTY, 0, sF, false, taddr(SL::VL), true, true, 4, 64);
+      if (leader) {
+        if (mine(0)) {   // both accumulate into the same tile: one issuer, in order
+          gemm(kTY, 0, taddr(SL::AMIX), false, taddr(SL::V1), true, false, 4, 64);
+          gemm(kTY, 0, sF, false, taddr(SL::VL), true, true, 4, 64);
+        }
         mma_commit(&sv_.bar);
       }
       wait_mma();
@@ -543,11 +553,12 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
       // B2: dF += dY (w V_V)^T ; dV1 = A^T dY ; dVL = F^T dY ; db_t = dG_t^T a
       // ===============================================================================================
       publish();
-      if (tid == 0) {
-        gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::VL), false, true, ksteps, 64);
-        gemm(kTdV1, 0, taddr(SB::AMIX), true, taddr(SB::DY), true, false, 4, 64);
-        gemm(kTdVL, 0, sF, true, taddr(SB::DY), true, false, 4, 64);
-        for (int t = 0; t < 4; ++t) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(bv_.a_bf), true, false, 4, 16);
+      if (leader) {
+        if (mine(0)) gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::VL), false, true, ksteps, 64);
+        if (mine(1)) gemm(kTdV1, 0, taddr(SB::AMIX), true, taddr(SB::DY), true, false, 4, 64);
+        if (mine(2)) gemm(kTdVL, 0, sF, true, taddr(SB::DY), true, false, 4, 64);
+        for (int t = 0; t < 4; ++t)
+          if (mine(3 + t)) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(bv_.a_bf), true, false, 4, 16);
         mma_commit(&sv_.bar);
       }
       wait_mma();
@@ -700,13 +711,13 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
         for (int s = 0; s <= V - 2; ++s) {
           const int kF = V - 1 - s, kR = s;
           publish();
-          if (tid == 0) {
+          if (leader) {
             const uint32_t pPrev = (kF - 1 == 0) ? taddr(SB::A + 0) : taddr(SB::P(kF - 1));
             const uint32_t rNext = (kR + 1 == V - 1) ? taddr(SB::A + V - 1) : taddr(SB::R(V - 1 - (kR + 1)));
-            gemm(kTAF, 0, pPrev, true, taddr(xf), true, false, 4, 64);
-            gemm(kTXF, 0, taddr(xf), false, taddr(SB::A + kF), false, false, 4, 64);
-            gemm(kTAR, 0, rNext, true, taddr(xr), true, false, 4, 64);
-            gemm(kTXR, 0, taddr(xr), false, taddr(SB::A + kR), false, false, 4, 64);
+            if (mine(0)) gemm(kTAF, 0, pPrev, true, taddr(xf), true, false, 4, 64);
+            if (mine(1)) gemm(kTXF, 0, taddr(xf), false, taddr(SB::A + kF), false, false, 4, 64);
+            if (mine(2)) gemm(kTAR, 0, rNext, true, taddr(xr), true, false, 4, 64);
+            if (mine(3)) gemm(kTXR, 0, taddr(xr), false, taddr(SB::A + kR), false, false, 4, 64);
             mma_commit(&sv_.bar);
           }
           wait_mma();
@@ -768,10 +779,10 @@ __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseP
         *reinterpret_cast<uint4*>(tile(SB::X + 1) + ch * 1024 + rr * 16) = q;
       }
       publish();
-      if (tid == 0) {
+      if (leader) {
         for (int k = 0; k < V; ++k) {
-          gemm(kTT + k, 0, taddr(ds_slot(k)), false, taddr(SB::K), true, false, 4, 64);
-          gemm(tileU(k), 0, taddr(ds_slot(k)), true, taddr(SB::X + 1), true, false, 4, 64);
+          if (mine(2 * k)) gemm(kTT + k, 0, taddr(ds_slot(k)), false, taddr(SB::K), true, false, 4, 64);
+          if (mine(2 * k + 1)) gemm(tileU(k), 0, taddr(ds_slot(k)), true, taddr(SB::X + 1), true, false, 4, 64);
         }
         mma_commit(&sv_.bar);
       }

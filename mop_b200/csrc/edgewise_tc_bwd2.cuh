@@ -45,7 +45,12 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
   const Frag f;
 
   if (tid < 32) tmem_alloc<512>(&sv_.tmem_slot);
-  if (tid == 0) { mbar_init(&sv_.bar, 1); fence_mbar_init(); }
+  // MMAs are issued by lane 0 of all eight warps, dealt round-robin (see edgewise_tc.cuh); every leader commits
+  constexpr int kIssuers = 8;
+  const int wid = tid >> 5;
+  const bool leader = (tid & 31) == 0;
+  auto mine = [&](int idx) { return (idx & (kIssuers - 1)) == wid; };
+  if (tid == 0) { mbar_init(&sv_.bar, kIssuers); fence_mbar_init(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,9 +128,10 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
     }
     publish();
     // ---- stage 1: S_i, dA ---------------------------------------------------------------------------------
-    if (tid == 0) {
-      for (int i = 0; i < V; ++i) gemm(kTS + i, 0, taddr(SB::QC + i), false, taddr(SB::K), false, false, ksteps, 64);
-      gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::V1), false, false, ksteps, 64);
+    if (leader) {
+      for (int i = 0; i < V; ++i)
+        if (mine(i)) gemm(kTS + i, 0, taddr(SB::QC + i), false, taddr(SB::K), false, false, ksteps, 64);
+      if (mine(V)) gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::V1), false, false, ksteps, 64);
       mma_commit(&sv_.bar);
     }
     wait_mma();
@@ -147,9 +153,9 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
       uint32_t xf = taddr(SB::A + 0), xr = taddr(SB::A + V - 1);
       for (int s = 1; s < V; ++s) {
         publish();
-        if (tid == 0) {
-          gemm(kTF, 0, xf, false, taddr(SB::A + s), true, false, 4, 64);
-          gemm(kTR, 0, xr, false, taddr(SB::A + V - 1 - s), true, false, 4, 64);
+        if (leader) {
+          if (mine(0)) gemm(kTF, 0, xf, false, taddr(SB::A + s), true, false, 4, 64);
+          if (mine(4)) gemm(kTR, 0, xr, false, taddr(SB::A + V - 1 - s), true, false, 4, 64);   // a warp of the other warpgroup
           mma_commit(&sv_.bar);
         }
         wait_mma();
@@ -374,11 +380,12 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
     }
     // ---- early GEMMs ---------------------------------------------------------------------------------------------
     publish();
-    if (tid == 0) {
-      gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::VL), false, true, ksteps, 64);
-      gemm(kTdV1, 0, taddr(SB::AMIX), true, taddr(SB::DY), true, false, 4, 64);
-      gemm(kTdVL, 0, sF, true, taddr(SB::DY), true, false, 4, 64);
-      for (int t = 0; t < 4; ++t) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(bv_.a_bf), true, false, 4, 16);
+    if (leader) {
+      if (mine(0)) gemm(kTY, 0, taddr(SB::DY), false, taddr(SB::VL), false, true, ksteps, 64);
+      if (mine(1)) gemm(kTdV1, 0, taddr(SB::AMIX), true, taddr(SB::DY), true, false, 4, 64);
+      if (mine(2)) gemm(kTdVL, 0, sF, true, taddr(SB::DY), true, false, 4, 64);
+      for (int t = 0; t < 4; ++t)
+        if (mine(3 + t)) gemm(kTdb, 16 * t, taddr(SB::X + t), true, smem_u32(bv_.a_bf), true, false, 4, 16);
       mma_commit(&sv_.bar);
     }
     for (int idx = tid; idx < kMaxQ * 64; idx += 256) bv_.da[idx >> 6][idx & 63] = xv.da2[0][idx >> 6][idx & 63] + xv.da2[1][idx >> 6][idx & 63];
@@ -533,13 +540,13 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
       for (int s = 0; s <= V - 2; ++s) {
         const int kF = V - 1 - s, kR = s;
         publish();
-        if (tid == 0) {
+        if (leader) {
           const uint32_t pPrev = (kF - 1 == 0) ? taddr(SB::A + 0) : taddr(SB::P(kF - 1));
           const uint32_t rNext = (kR + 1 == V - 1) ? taddr(SB::A + V - 1) : taddr(SB::R(V - 1 - (kR + 1)));
-          gemm(kTAF, 0, pPrev, true, taddr(xf), true, false, 4, 64);
-          gemm(kTXF, 0, taddr(xf), false, taddr(SB::A + kF), false, false, 4, 64);
-          gemm(kTAR, 0, rNext, true, taddr(xr), true, false, 4, 64);
-          gemm(kTXR, 0, taddr(xr), false, taddr(SB::A + kR), false, false, 4, 64);
+          if (mine(0)) gemm(kTAF, 0, pPrev, true, taddr(xf), true, false, 4, 64);
+          if (mine(1)) gemm(kTXF, 0, taddr(xf), false, taddr(SB::A + kF), false, false, 4, 64);
+          if (mine(4)) gemm(kTAR, 0, rNext, true, taddr(xr), true, false, 4, 64);
+          if (mine(5)) gemm(kTXR, 0, taddr(xr), false, taddr(SB::A + kR), false, false, 4, 64);
           mma_commit(&sv_.bar);
         }
         wait_mma();
@@ -601,10 +608,10 @@ __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams
       *reinterpret_cast<uint4*>(tile(SB::X + 1) + ch * 1024 + rr * 16) = q;
     }
     publish();
-    if (tid == 0) {
+    if (leader) {
       for (int k = 0; k < V; ++k) {
-        gemm(tileT2(k), 0, taddr(ds_slot(k)), false, taddr(SB::K), true, false, 4, 64);
-        gemm(tileU2(k), 0, taddr(ds_slot(k)), true, taddr(SB::X + 1), true, false, 4, 64);
+        if (mine(2 * k)) gemm(tileT2(k), 0, taddr(ds_slot(k)), false, taddr(SB::K), true, false, 4, 64);
+        if (mine(2 * k + 1)) gemm(tileU2(k), 0, taddr(ds_slot(k)), true, taddr(SB::X + 1), true, false, 4, 64);
       }
       mma_commit(&sv_.bar);
     }
