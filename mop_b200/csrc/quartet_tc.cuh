@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
-  // Unmasked tiles (entirely below the diagonal; zero-filled key rows >= T contribute nothing) run on packed fp32 math with the
-  // per-row constants folded in.  With u, v the raw dot products:  t = f / (sigma1+eps) = A1 + B1 v,  s = scale u t,
+  // Without an additive mask the tiles run on packed fp32 math with the per-row constants folded in (zero-filled key rows >= T
+  // contribute nothing; on diagonal tiles the probabilities above the diagonal are zeroed).  With u, v the raw dot products:  t = f / (sigma1+eps) = A1 + B1 v,  s = scale u t,
   // D = P (dP - delta),  W1 = D t,  W2 = D u B1;  the row sums the epilogue needs all follow from Sa = sum D u, Sb = sum D u v.
   const float fA = mx.quart ? 1.f - mx.m : 1.f, fB = mx.quart ? mx.m * mx.gam * p.scale * i2 : 0.f;   // f = fA + fB v
   const float2 A1 = make_float2(fA * i1, fA * i1), B1 = make_float2(fB * i1, fB * i1), cs2 = make_float2(p.scale * kLog2e, p.scale * kLog2e);
@@ -551,13 +551,17 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + col, v2);
       tmem_ld_32x32b_x16(tl + 128 + col, dp);
       tmem_ld_wait();
-      if (!HAS_MASK && k0 + 63 <= q0) {
+      if (!HAS_MASK) {
+        const int lim = gi - k0 - col;   // causal: element e of this chunk is masked when e > lim (diagonal tiles only)
+        const bool diag = k0 + 63 > q0;
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
           const float2 u = make_float2(v1[e], v1[e + 1]), v = mx.quart ? make_float2(v2[e], v2[e + 1]) : make_float2(0.f, 0.f);
           const float2 tt = fma2(B1, v, A1);
           const float2 a = fma2(mul2(u, tt), cs2, L2);
-          const float2 D = mul2(make_float2(ex2(a.x), ex2(a.y)), add2(make_float2(dp[e], dp[e + 1]), nd2));
+          float2 pr = make_float2(ex2(a.x), ex2(a.y));
+          if (diag) { pr.x = e > lim ? 0.f : pr.x; pr.y = e + 1 > lim ? 0.f : pr.y; }
+          const float2 D = mul2(pr, add2(make_float2(dp[e], dp[e + 1]), nd2));
           const float2 Du = mul2(D, u), W1 = mul2(D, tt), W2 = mul2(Du, B1);
           Sa2 = add2(Sa2, Du);
           Sb2 = fma2(Du, v, Sb2);
@@ -819,7 +823,9 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + colb, v2);
       tmem_ld_32x32b_x16(tl + 128 + colb, dp);
       tmem_ld_wait();
-      if (!HAS_MASK && q0 >= k0 + 127) {   // unmasked tile (zero-filled query rows >= T contribute nothing): packed fp32 math
+      if (!HAS_MASK) {   // packed fp32 math (zero-filled query rows >= T contribute nothing; causal zeroing on diagonal tiles)
+        const bool diag = q0 < k0 + 127;
+        const int lim = gj - q0 - colb;   // query column x of this chunk is masked when x < lim
         const float2 cs2 = make_float2(p.scale * kLog2e, p.scale * kLog2e);
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
@@ -833,7 +839,8 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
             const float2 u = make_float2(v1[x], v1[x + 1]), v = mx.quart ? make_float2(v2[x], v2[x + 1]) : make_float2(0.f, 0.f);
             const float2 tt = fma2(B1, v, A1);
             const float2 a = fma2(mul2(u, tt), cs2, L2);
-            const float2 pr = make_float2(ex2(a.x), ex2(a.y));
+            float2 pr = make_float2(ex2(a.x), ex2(a.y));
+            if (diag) { pr.x = x < lim ? 0.f : pr.x; pr.y = x + 1 < lim ? 0.f : pr.y; }
             const float2 D = mul2(pr, add2(make_float2(dp[x], dp[x + 1]), nd2));
             const float2 W1 = mul2(D, tt), W2 = mul2(mul2(D, u), B1);
             pt[x] = pr.x; pt[x + 1] = pr.y; w1[x] = W1.x; w1[x + 1] = W1.y; w2[x] = W2.x; w2[x + 1] = W2.y;

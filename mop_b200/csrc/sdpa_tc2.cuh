@@ -287,9 +287,9 @@ __device__ __forceinline__ void elem(const MopSdpaParams& p, float raw, float dp
   ds = pr * (dp - dlt);
 }
 // the same for an unmasked pair of elements on packed fp32 math: 3 FMA-pipe instructions + 2 MUFU for two elements
-__device__ __forceinline__ void elem2(float2 raw, float2 dp, float2 coef, float2 nlse, float2 ndlt, float2& pr, float2& ds) {
+__device__ __forceinline__ void elem2(float2 raw, float2 dp, float2 coef, float2 nlse, float2 ndlt, bool m0, bool m1, float2& pr, float2& ds) {
   const float2 a = fma2(raw, coef, nlse);
-  pr = make_float2(ex2(a.x), ex2(a.y));
+  pr = make_float2(m0 ? 0.f : ex2(a.x), m1 ? 0.f : ex2(a.y));   // m0 / m1: causal zeroing (diagonal tiles)
   ds = mul2(pr, add2(dp, ndlt));
 }
 template <bool EXTRA>
@@ -393,12 +393,14 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
       tmem_ld_32x32b_x16(tl + col, v1);
       tmem_ld_32x32b_x16(tl + 64 + col, dp);
       tmem_ld_wait();
-      if (!EXTRA && !(p.causal && k0 + 63 > q0)) {
-        // no mask needed: zero-filled key rows (>= Nk) contribute nothing to dS K, rows >= Nq are never written
+      if (!EXTRA) {
+        // zero-filled key rows (>= Nk) contribute nothing to dS K, rows >= Nq are never written: only the causal diagonal masks
+        const bool diag = p.causal && k0 + 63 > q0;
+        const int lim = gi - k0 - col;   // element e is above the diagonal when e > lim
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
           float2 pr, ds;
-          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, nlse2, ndlt2, pr, ds);
+          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, nlse2, ndlt2, diag && e > lim, diag && e + 1 > lim, pr, ds);
           ws_[e] = ds.x; ws_[e + 1] = ds.y;
         }
       } else {
@@ -526,16 +528,20 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
       tmem_ld_32x32b_x16(tl + colb, v1);
       tmem_ld_32x32b_x16(tl + 64 + colb, dp);
       tmem_ld_wait();
-      if (!EXTRA && !(p.causal && q0 < k0 + 127)) {
-        // no mask needed: zero-filled query rows (>= Nq) contribute nothing to P^T dO / dS^T Q, keys >= Nk are never written
+      if (!EXTRA) {
+        // zero-filled query rows (>= Nq) contribute nothing to P^T dO / dS^T Q, keys >= Nk are never written: only the diagonal masks
+        const bool diag = p.causal && q0 < k0 + 127;
+        const int lim = gj - q0 - colb;   // query column x is above the diagonal (masked) when x < lim
         const float2 coef2 = make_float2(p.scale * kLog2e, p.scale * kLog2e), nl2e = make_float2(-kLog2e, -kLog2e), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           const float4 l4 = *reinterpret_cast<const float4*>(&sm.vec[buf][0][colb + e]), d4 = *reinterpret_cast<const float4*>(&sm.vec[buf][1][colb + e]);
           float2 pr, ds;
-          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, mul2(make_float2(l4.x, l4.y), nl2e), mul2(make_float2(d4.x, d4.y), neg1), pr, ds);
+          elem2(make_float2(v1[e], v1[e + 1]), make_float2(dp[e], dp[e + 1]), coef2, mul2(make_float2(l4.x, l4.y), nl2e), mul2(make_float2(d4.x, d4.y), neg1),
+                diag && e < lim, diag && e + 1 < lim, pr, ds);
           pt[e] = pr.x; pt[e + 1] = pr.y; wt[e] = ds.x; wt[e + 1] = ds.y;
-          elem2(make_float2(v1[e + 2], v1[e + 3]), make_float2(dp[e + 2], dp[e + 3]), coef2, mul2(make_float2(l4.z, l4.w), nl2e), mul2(make_float2(d4.z, d4.w), neg1), pr, ds);
+          elem2(make_float2(v1[e + 2], v1[e + 3]), make_float2(dp[e + 2], dp[e + 3]), coef2, mul2(make_float2(l4.z, l4.w), nl2e), mul2(make_float2(d4.z, d4.w), neg1),
+                diag && e + 2 < lim, diag && e + 3 < lim, pr, ds);
           pt[e + 2] = pr.x; pt[e + 3] = pr.y; wt[e + 2] = ds.x; wt[e + 3] = ds.y;
         }
       } else {
