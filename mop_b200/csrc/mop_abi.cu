@@ -413,7 +413,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
   if (!bwd) {
     if ((rc = allow_smem(hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>, smem_f))) return rc;
-    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 128, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
+    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 192, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
   } else {
     if ((rc = allow_smem(hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>, smem_q))) return rc;
     if ((rc = allow_smem(hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>, smem_k))) return rc;

@@ -23,6 +23,16 @@
 #include "quartet_simt.cuh"
 #include "tc_common.cuh"
 
+// -DMOP_FWD_TIMELINE: one CTA of the forward kernel prints clock64 stamps of its roles per tile (tools/ts_timeline.py); development only
+#ifdef MOP_FWD_TIMELINE
+#define TS_DECL long long ts_[24][6]; const bool ts_on = blockIdx.x == MOP_FWD_TIMELINE;
+#define TS(t, k) do { if (ts_on && (t) < 24) ts_[t][k] = clock64(); } while (0)
+#define TS_DUMP(name, n, K) do { if (ts_on) for (int t_ = 0; t_ < (n) && t_ < 24; ++t_) printf("%s t= %d %lld %lld %lld %lld %lld %lld\n", name, t_, ts_[t_][0], ts_[t_][1], ts_[t_][2], ts_[t_][3], K > 4 ? ts_[t_][4] : 0LL, K > 5 ? ts_[t_][5] : 0LL); } while (0)
+#else
+#define TS_DECL
+#define TS(t, k)
+#define TS_DUMP(name, n, K)
+#endif
 namespace mop {
 namespace qtc {
 
@@ -234,19 +244,35 @@ __device__ __forceinline__ void load_act_tile_async(unsigned char* tile, const _
   }
 }
 
+constexpr int kKStages = 3;   // key ring of the forward kernel (the value ring has two stages)
 struct __align__(128) SmemF {
   unsigned char Q[kT128], Q2[kT128], P[kT128];
-  unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
-  uint64_t bar;      // MMA completion
-  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
-  uint64_t ldq;      // TMA completion of the query tiles
+  unsigned char K1[kKStages][kT64], K2[kKStages][kT64], V[2][kT64];
+  uint64_t bar_s;        // S1 and S2 of a tile complete (two issuing lanes -> two arrivals); phase 0 = the sigma prologue
+  uint64_t bar_pv;       // P V of a tile complete                                   (tensor pipe -> softmax warps, lane B)
+  uint64_t p_ready;      // P(t) written: 128 arrivals                                (softmax warps -> lane B)
+  uint64_t s_free;       // the score columns have been read: 128 arrivals            (softmax warps -> lanes A and B)
+  uint64_t ldk[kKStages], ldv[2];   // TMA completion of the key / value ring stages
+  uint64_t ldq;          // TMA completion of the query tiles
   uint32_t tmem_slot;
 };
 
-// grid: B*H*nqb, 128 threads; two CTAs per SM (256 TMEM columns each: S1 | S2 | O)
+// grid: B*H*nqb, 192 threads, two CTAs per SM (256 TMEM columns each: S1 | S2 | O).
 // tmQ / tmQ2 / tmV: the activations [B,T,H,dk]; tmKc: the centred keys in the workspace ([nm*B*H, T, 1, 64])
+// Warp-specialised like sdpa2::fwd_kernel (sdpa_tc2.cuh), no CTA-wide barrier inside the loop:
+//   warps 0-3       one query row per thread: scores -> registers (arrive s_free) -> mix -> lazy online softmax -> P (arrive p_ready)
+//   lane A (warp 4) key TMA loads (three-stage ring, refilled as soon as the scores of the old tile have been read) and
+//                   S1(t+1) = Q Kc1^T, issued the moment tile t's scores are in registers
+//   lane B (warp 5) S2(t+1) = Q2 Kc2^T at the same moment, then O += P(t) V_t when p_ready(t) completes, and the value TMA loads
+// One lane doing all of it needed ~2900 cycles per tile (~110 cycles per tcgen05.mma, TMA latency exposed by a two-stage ring)
+// against ~2000 for the softmax warps.  Every mbarrier is waited on phase by phase by each of its waiters and its next phase
+// cannot complete before that waiter has moved on (parity waits cannot tell phase k from k + 2).
+#ifndef MOP_QLAZY
+#define MOP_QLAZY 8.f
+#endif
+constexpr float kLazy = MOP_QLAZY;   // the running maximum is raised only when a tile exceeds it by 2^kLazy
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                      const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmKc,
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -254,176 +280,265 @@ __global__ void __launch_bounds__(128, 2) fwd_kernel(MopQuartetParams p, Ws w, u
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nqb = w.nqb;
   // heavy (late) query blocks first: the causal work per block grows with its index
   const int qb = nqb - 1 - (int)(blockIdx.x / ((unsigned)p.B * p.H)), bh = blockIdx.x % (p.B * p.H), b = bh / p.H, h = bh % p.H;
-  const int q0 = qb * 128, gi = q0 + tid;
-  const bool row_ok = gi < T;
-  const int dks = (dk + 15) >> 4;
+  const int q0 = qb * 128;
   const Mix mx = load_mix(p);
-  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  const size_t BH = (size_t)p.B * p.H;
   if (warp == 0) tmem_alloc<256>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
-  // the Gram tiles (hi, lo per map) borrow the second key / value buffers for the sigma prologue
-  copy_tile64(sm.K1[1], ws + w.gram + (size_t)bh * 2 * kT64);
-  copy_tile64(sm.K2[1], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
-  if (mx.quart) {
-    copy_tile64(sm.V[1], ws + w.gram + (BH + bh) * 2 * kT64);
-    copy_tile64(sm.P, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
-  }
-  publish();
-  auto fetch = [&](int buf, int k0) {   // thread 0 only
-    mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
-    tma_load_tile_sw(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
-    if (mx.quart) tma_load_tile_sw(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
-    tma_load_tile_sw(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
-  };
   if (tid == 0) {
-    mbar_expect_tx(&sm.ldq, (mx.quart ? 2 : 1) * kT128);
-    tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
-    if (mx.quart) tma_load_tile_sw(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
-    fetch(0, 0);
+    mbar_init(&sm.bar_s, 2); mbar_init(&sm.bar_pv, 1); mbar_init(&sm.p_ready, 128); mbar_init(&sm.s_free, 128);
+    for (int s = 0; s < kKStages; ++s) mbar_init(&sm.ldk[s], 1);
+    mbar_init(&sm.ldv[0], 1); mbar_init(&sm.ldv[1], 1); mbar_init(&sm.ldq, 1);
+    fence_mbar_init();
   }
-  mbar_wait(&sm.ldq, 0);   // every thread reads its query row below
-  const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp) << 16);
-  uint32_t phase = 0;
-  // ---- sigma_i = s sqrt(q_i . (G q_i) / (T-1)),  G q by MMA (G = hi + lo)
-  if (tid == 0) {
-    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1[1]), smem_u32(sm.K2[1]));
-    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V[1]), smem_u32(sm.P));
-    mma_commit(&sm.bar);
-  }
-  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-  float quad1 = 0.f, quad2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float z1[16], z2[16], x[8];
-    tmem_ld_32x32b_x16(tl + 16 * c, z1);
-    if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, z2);
-    tmem_ld_wait();
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      unpack8(*reinterpret_cast<const uint4*>(sm.Q + sw128_off(tid, 8 * (2 * c + hh))), x);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) quad1 = fmaf(z1[8 * hh + e], x[e], quad1);
-      if (mx.quart) {
-        unpack8(*reinterpret_cast<const uint4*>(sm.Q2 + sw128_off(tid, 8 * (2 * c + hh))), x);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) quad2 = fmaf(z2[8 * hh + e], x[e], quad2);
-      }
-    }
-  }
-  const float s1v = p.scale * sqrtf(fmaxf(quad1, 0.f) / (float)(T - 1)), s2v = mx.quart ? p.scale * sqrtf(fmaxf(quad2, 0.f) / (float)(T - 1)) : 0.f;
-  const float a1 = p.scale / (s1v + mx.eps), a2 = mx.quart ? p.scale / (s2v + mx.eps) : 0.f;
   tc_fence_before();
-  __syncthreads();   // the Gram tiles are dead: their buffers may receive key / value tiles
-  float m_run = -INFINITY, l_run = 0.f;
-  const float fa_ = mx.quart ? a1 * (1.f - mx.m) : a1, fb_ = mx.quart ? a1 * mx.m * mx.gam * a2 : 0.f;
-  const float2 fA2 = make_float2(fa_, fa_), fB2 = make_float2(fb_, fb_), l2e2 = make_float2(kLog2e, kLog2e);
+  __syncthreads();   // barriers initialised, TMEM allocated
+  tc_fence_after();
   const int k_end = min(T, q0 + 128);
-  const int ntiles = (k_end + 63) >> 6;
-  for (int it = 0; it < ntiles; ++it) {
-    const int k0 = it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // P V of tile it-1: its buffers and P are free
-    if (tid == 0) {
-      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
-      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      if (mx.quart)
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      mma_commit(&sm.bar);
+  const int ntiles = (k_end + 63) >> 6;   // >= 1
+  auto fetch_k = [&](int t, int s) {   // lane A
+    mbar_expect_tx(&sm.ldk[s], (mx.quart ? 2 : 1) * kT64);
+    tma_load_tile_sw(sm.K1[s], &tmKc, 64 * t, 0, bh, &sm.ldk[s]);
+    if (mx.quart) tma_load_tile_sw(sm.K2[s], &tmKc, 64 * t, 0, (int)BH + bh, &sm.ldk[s]);
+  };
+  auto fetch_v = [&](int t) {          // lane B
+    mbar_expect_tx(&sm.ldv[t & 1], kT64);
+    tma_load_tile_sw(sm.V[t & 1], &tmV, 64 * t, h, b, &sm.ldv[t & 1]);
+  };
+  const uint32_t tb = sm.tmem_slot;
+  if (tid == 128) {
+    // query tiles by TMA; the Gram tile images (hi, lo per map; 8 KB each, contiguous in the workspace) by bulk copies into key-ring
+    // stages 1 and 2, which the sigma prologue borrows - all on one transaction barrier, no thread copies anything
+    mbar_expect_tx(&sm.ldq, (mx.quart ? 2 : 1) * (kT128 + 2 * kT64));
+    tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
+    bulk_g2s(sm.K1[1], ws + w.gram + (size_t)bh * 2 * kT64, kT64, &sm.ldq);
+    bulk_g2s(sm.K2[1], ws + w.gram + (size_t)bh * 2 * kT64 + kT64, kT64, &sm.ldq);
+    if (mx.quart) {
+      tma_load_tile_sw(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
+      bulk_g2s(sm.K1[2], ws + w.gram + (BH + bh) * 2 * kT64, kT64, &sm.ldq);
+      bulk_g2s(sm.K2[2], ws + w.gram + (BH + bh) * 2 * kT64 + kT64, kT64, &sm.ldq);
     }
-    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-    float sc[64];
-    float tmax = -INFINITY;
-    const bool need_mask = (k0 + 63 > q0) || (k0 + 64 > T);
+    fetch_k(0, 0);
+    // ---- sigma prologue: G q by MMA (G = hi + lo) into the score columns
+    mbar_wait(&sm.ldq, 0);
+    mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1[1]), smem_u32(sm.K2[1]));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.K1[2]), smem_u32(sm.K2[2]));
+    mma_commit(&sm.bar_s);   // phase 0 of bar_s (two arrivals: this one and lane B's); tile t completes phase t + 1
+  } else if (tid == 160) {
+    fetch_v(0);
+    mma_commit(&sm.bar_s);   // nothing outstanding: arrives at once
+  }
+  float s1v = 0.f, s2v = 0.f, a1 = 0.f, a2 = 0.f;
+  if (warp < 4) {
+    mbar_wait(&sm.ldq, 0);   // every softmax thread reads its query row below
+    mbar_wait(&sm.bar_s, 0);
+    tc_fence_after();
+    const uint32_t tl = tb + ((uint32_t)(32 * warp) << 16);
+    float quad1 = 0.f, quad2 = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float v1[16], v2[16];
-      tmem_ld_32x32b_x16(tl + 16 * c, v1);
-      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
+      float z1[16], z2[16], x[8];
+      tmem_ld_32x32b_x16(tl + 16 * c, z1);
+      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, z2);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; e += 2) {   // mix = n1 ((1-m) + m gamma n2) = u (fA + fB v) on packed fp32 math
-        const float2 tt = mx.quart ? fma2(fB2, make_float2(v2[e], v2[e + 1]), fA2) : fA2;
-        const float2 r = mul2(make_float2(v1[e], v1[e + 1]), tt);
-        sc[16 * c + e] = r.x; sc[16 * c + e + 1] = r.y;
+      for (int hh = 0; hh < 2; ++hh) {
+        unpack8(*reinterpret_cast<const uint4*>(sm.Q + sw128_off(tid, 8 * (2 * c + hh))), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) quad1 = fmaf(z1[8 * hh + e], x[e], quad1);
+        if (mx.quart) {
+          unpack8(*reinterpret_cast<const uint4*>(sm.Q2 + sw128_off(tid, 8 * (2 * c + hh))), x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) quad2 = fmaf(z2[8 * hh + e], x[e], quad2);
+        }
       }
     }
-    if (need_mask) {   // tiles on the diagonal / past the end only (uniform branch)
+    s1v = p.scale * sqrtf(fmaxf(quad1, 0.f) / (float)(T - 1));
+    s2v = mx.quart ? p.scale * sqrtf(fmaxf(quad2, 0.f) / (float)(T - 1)) : 0.f;
+    a1 = p.scale / (s1v + mx.eps);
+    a2 = mx.quart ? p.scale / (s2v + mx.eps) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();   // the Gram tiles and the prologue's TMEM columns are dead: key stages 1, 2 and the score columns are free
+  tc_fence_after();
+  if (warp >= 4) {
+    const uint32_t id_s = idesc_bf16(128, 64, 0, 0);
+    if (tid == 128) {
+      // ---- lane A: key TMA loads + S1 ----------------------------------------------------------------------------
+      const uint64_t dq1 = desc_k_sw(smem_u32(sm.Q), 0), dk1 = desc_k_sw(smem_u32(sm.K1[0]), 0);
+      for (int t = 1; t < min(ntiles, kKStages); ++t) fetch_k(t, t);
+      TS_DECL
+      int st = 0, par = 0;   // ring stage / parity of the tile whose S1 is issued next
+      for (int t = 0; t < ntiles; ++t) {   // issues S1(t); for t >= 1 right after the scores of tile t-1 have been read
+        TS(t, 0);
+        if (t >= 1) {
+          mbar_wait(&sm.s_free, (uint32_t)(t - 1) & 1u);   // => S1 / S2(t-1) complete: their key stage is free
+          tc_fence_after();
+          if (t + 2 < ntiles) fetch_k(t + 2, st == 0 ? kKStages - 1 : st - 1);   // tile t+2 takes the stage of tile t-1
+        }
+        TS(t, 1);
+        mbar_wait(&sm.ldk[st], (uint32_t)par);
+        TS(t, 2);
+        const uint64_t off = (uint64_t)(st * (kT64 >> 4));
 #pragma unroll
-      for (int e = 0; e < 64; ++e)
-        if (k0 + e > gi || k0 + e >= T) sc[e] = -INFINITY;
-    }
-    if constexpr (HAS_MASK) {
-      if (row_ok) {
-        const float* am = p.add_mask + (int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)k0 * p.am_sk;
-#pragma unroll 8
-        for (int e = 0; e < 64; ++e)
-          if (k0 + e < T) sc[e] += am[(int64_t)e * p.am_sk];
+        for (int ks = 0; ks < 4; ++ks) mma_ss(tb, dq1 + (uint64_t)(2 * ks), dk1 + off + (uint64_t)(2 * ks), id_s, ks > 0 ? 1u : 0u);
+        mma_commit(&sm.bar_s);
+        TS(t, 3);
+        if (++st == kKStages) { st = 0; par ^= 1; }
       }
-    }
+      TS_DUMP("S-lane", ntiles, 4);
+    } else if (tid == 160) {
+      // ---- lane B: S2, O += P(t) V_t, value TMA loads ----------------------------------------------------------------
+      const uint32_t id_pv = idesc_bf16(128, 64, 0, 1);
+      const uint64_t dq2 = desc_k_sw(smem_u32(sm.Q2), 0), dk2 = desc_k_sw(smem_u32(sm.K2[0]), 0);
+      const uint64_t dp = desc_kmajor(smem_u32(sm.P), 128, 0), dv0 = desc_mn_sw(smem_u32(sm.V[0]), 0);
+      if (ntiles > 1) fetch_v(1);
+      TS_DECL
+      int st = 0, par = 0;
+      auto issue_s2 = [&](int t) {   // S2(t) (nothing to do without the second map) + this lane's arrival on bar_s
+        if (mx.quart) {
+          mbar_wait(&sm.ldk[st], (uint32_t)par);
+          const uint64_t off = (uint64_t)(st * (kT64 >> 4));
 #pragma unroll
-    for (int e = 0; e < 64; ++e) tmax = fmaxf(tmax, sc[e]);
-    const float m_new = fmaxf(m_run, tmax);
-    const float mb = (m_new == -INFINITY) ? 0.f : m_new * kLog2e;
-    const float corr = (m_run == -INFINITY) ? 0.f : ex2(fmaf(m_run, kLog2e, -mb));
-    const bool need = it > 0 && m_new > m_run;
-    if (__any_sync(0xffffffffu, need)) {
-      const float scl = need ? corr : 1.f;
+          for (int ks = 0; ks < 4; ++ks) mma_ss(tb + 64, dq2 + (uint64_t)(2 * ks), dk2 + off + (uint64_t)(2 * ks), id_s, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&sm.bar_s);
+        if (++st == kKStages) { st = 0; par ^= 1; }
+      };
+      issue_s2(0);
+      for (int t = 0; t < ntiles; ++t) {
+        TS(t, 0);
+        if (t + 1 < ntiles) {
+          mbar_wait(&sm.s_free, (uint32_t)t & 1u);   // the scores of tile t are in registers
+          tc_fence_after();
+          issue_s2(t + 1);
+        }
+        if (t >= 1 && t + 1 < ntiles) {   // refill the value stage of tile t-1.  Must precede this tile's commit on bar_pv: a
+          mbar_wait(&sm.bar_pv, (uint32_t)(t - 1) & 1u);   // parity wait cannot tell phase t-1 from phase t+1
+          fetch_v(t + 1);
+        }
+        TS(t, 1);
+        mbar_wait(&sm.ldv[t & 1], (uint32_t)(t >> 1) & 1u);
+        mbar_wait(&sm.p_ready, (uint32_t)t & 1u);
+        tc_fence_after();
+        TS(t, 2);
+        const uint64_t dv = dv0 + (uint64_t)((t & 1) * (kT64 >> 4));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_ss(tb + 128, dp + (uint64_t)(ks * 256), dv + (uint64_t)(ks * 128), id_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        mma_commit(&sm.bar_pv);
+        TS(t, 3);
+      }
+      TS_DUMP("PV-lane", ntiles, 4);
+    }
+  } else {
+    // ---- softmax warps: one query row per thread ------------------------------------------------------------
+    const int gi = q0 + tid;
+    const bool row_ok = gi < T;
+    const uint32_t tl = tb + ((uint32_t)(32 * warp) << 16);
+    const float fa_ = mx.quart ? a1 * (1.f - mx.m) : a1, fb_ = mx.quart ? a1 * mx.m * mx.gam * a2 : 0.f;
+    const float2 fA2 = make_float2(fa_, fa_), fB2 = make_float2(fb_, fb_), l2e2 = make_float2(kLog2e, kLog2e);
+    float m_ref = -INFINITY, l_run = 0.f;   // m_ref in base-2 units
+    TS_DECL
+    for (int it = 0; it < ntiles; ++it) {
+      const int k0 = it * 64;
+      TS(it, 0);
+      mbar_wait(&sm.bar_s, (uint32_t)(it + 1) & 1u);
+      tc_fence_after();
+      TS(it, 1);
+      float sc[64];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float o[16];
-        tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
+        float v1[16], v2[16];
+        tmem_ld_32x32b_x16(tl + 16 * c, v1);
+        if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + 16 * c, v2);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] *= scl;
-        tmem_st_32x32b_x16(tl + 128 + 16 * c, o);
+        for (int e = 0; e < 16; e += 2) {   // mix = n1 ((1-m) + m gamma n2) = u (fA + fB v) on packed fp32 math
+          const float2 tt = mx.quart ? fma2(fB2, make_float2(v2[e], v2[e + 1]), fA2) : fA2;
+          const float2 r = mul2(make_float2(v1[e], v1[e + 1]), tt);
+          sc[16 * c + e] = r.x; sc[16 * c + e + 1] = r.y;
+        }
       }
-      tmem_st_wait();
-    }
-    l_run *= corr;
-    m_run = m_new;
-    float2 ps2 = make_float2(0.f, 0.f);
-    const float2 nmb2 = make_float2(-mb, -mb);
+      tc_fence_before();
+      mbar_arrive(&sm.s_free);
+      TS(it, 2);
+      if ((k0 + 63 > q0) || (k0 + 64 > T)) {   // tiles on the diagonal / past the end only (uniform branch)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float pv[8];
-#pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        const float2 a = fma2(make_float2(sc[8 * c + e], sc[8 * c + e + 1]), l2e2, nmb2);
-        const float2 pr = make_float2(ex2(a.x), ex2(a.y));
-        ps2 = add2(ps2, pr);
-        pv[e] = pr.x; pv[e + 1] = pr.y;
+        for (int e = 0; e < 64; ++e)
+          if (k0 + e > gi || k0 + e >= T) sc[e] = -INFINITY;
       }
-      *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
-    }
-    l_run += ps2.x + ps2.y;
-    publish();
-    if (tid == 0) {
-      const uint32_t id = idesc_bf16(128, 64, 0, 1);
+      if constexpr (HAS_MASK) {
+        if (row_ok) {
+          const float* am = p.add_mask + (int64_t)b * p.am_sb + (int64_t)h * p.am_sh + (int64_t)gi * p.am_sq + (int64_t)k0 * p.am_sk;
+#pragma unroll 8
+          for (int e = 0; e < 64; ++e)
+            if (k0 + e < T) sc[e] += am[(int64_t)e * p.am_sk];
+        }
+      }
+      float t0 = sc[0], t1 = sc[1], t2 = sc[2], t3 = sc[3];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        mma_ss(tb + 128, desc_kmajor(smem_u32(sm.P), 128, 16 * ks), desc_mn_sw(smem_u32(sm.V[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
-      mma_commit(&sm.bar);
-    }
-  }
-  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-  const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
+      for (int e = 4; e < 64; e += 4) { t0 = fmaxf(t0, sc[e]); t1 = fmaxf(t1, sc[e + 1]); t2 = fmaxf(t2, sc[e + 2]); t3 = fmaxf(t3, sc[e + 3]); }
+      const float tm2 = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * kLog2e;
+      const bool need = tm2 > m_ref + kLazy;                        // -inf + 8 = -inf: the first finite tile always raises it
+      const float m_new = need ? tm2 : m_ref;
+      const float corr = need ? ((m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new)) : 1.f;
+      const float mb = (m_new == -INFINITY) ? 0.f : m_new;
+      TS(it, 3);
+      if (it > 0) { mbar_wait(&sm.bar_pv, (uint32_t)(it - 1) & 1u); tc_fence_after(); }   // P V(it-1) (issued most of a tile ago): P is free, O final
+      TS(it, 4);
+      if (it > 0 && __any_sync(0xffffffffu, need)) {   // rare
+        float o[64];
+        tmem_ld_32x32b_x32(tl + 128, o);
+        tmem_ld_32x32b_x32(tl + 160, o + 32);
+        tmem_ld_wait();
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float o[16];
-    tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
-    tmem_ld_wait();
+        for (int e = 0; e < 64; ++e) o[e] *= corr;
+        tmem_st_32x32b_x32(tl + 128, o);
+        tmem_st_32x32b_x32(tl + 160, o + 32);
+        tmem_st_wait();
+      }
+      l_run *= corr;
+      m_ref = m_new;
+      float2 ps0 = make_float2(0.f, 0.f), ps1 = ps0;
+      const float2 nmb2 = make_float2(-mb, -mb);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) o[e] *= il;
-    if (row_ok) {
-      if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
-      if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
+      for (int c = 0; c < 8; ++c) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float2 a = fma2(make_float2(sc[8 * c + e], sc[8 * c + e + 1]), l2e2, nmb2);
+          pv[e] = ex2(a.x); pv[e + 1] = ex2(a.y);
+        }
+        ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
+        ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
+        *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
+      }
+      l_run += (ps0.x + ps0.y) + (ps1.x + ps1.y);
+      fence_async_smem();   // P (generic proxy) -> tensor pipe (async proxy)
+      tc_fence_before();
+      mbar_arrive(&sm.p_ready);
+      TS(it, 5);
     }
-  }
-  if (p.stats && row_ok) {
-    float* st = p.stats + (((size_t)b * p.H + h) * T + gi) * 3;
-    st[0] = s1v; st[1] = s2v; st[2] = m_run + kLn2 * lg2(l_run);
+    if (tid == 0) TS_DUMP("softmax", ntiles, 6);
+    mbar_wait(&sm.bar_pv, (uint32_t)(ntiles - 1) & 1u);
+    tc_fence_after();
+    const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float o[16];
+      tmem_ld_32x32b_x16(tl + 128 + 16 * c, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] *= il;
+      if (row_ok) {
+        if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
+        if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
+      }
+    }
+    if (p.stats && row_ok) {
+      float* st = p.stats + (((size_t)b * p.H + h) * T + gi) * 3;
+      st[0] = s1v; st[1] = s2v; st[2] = kLn2 * (m_ref + lg2(l_run));
+    }
   }
   tc_fence_before();
   __syncthreads();

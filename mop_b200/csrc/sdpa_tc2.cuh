@@ -15,16 +15,6 @@
 #pragma once
 #include "quartet_tc.cuh"
 
-// -DMOP_FWD_TIMELINE: one CTA of the forward kernel prints clock64 stamps of its roles per tile (tools/ts_timeline.py); development only
-#ifdef MOP_FWD_TIMELINE
-#define TS_DECL long long ts_[24][6]; const bool ts_on = blockIdx.x == 700;
-#define TS(t, k) do { if (ts_on && (t) < 24) ts_[t][k] = clock64(); } while (0)
-#define TS_DUMP(name, n, K) do { if (ts_on) for (int t_ = 0; t_ < (n) && t_ < 24; ++t_) printf("%s t= %d %lld %lld %lld %lld %lld %lld\n", name, t_, ts_[t_][0], ts_[t_][1], ts_[t_][2], ts_[t_][3], K > 4 ? ts_[t_][4] : 0LL, K > 5 ? ts_[t_][5] : 0LL); } while (0)
-#else
-#define TS_DECL
-#define TS(t, k)
-#define TS_DUMP(name, n, K)
-#endif
 namespace mop {
 namespace sdpa2 {
 

@@ -43,7 +43,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(a, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("mop_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      printf("mop_b200: mbarrier wait timed out (block %d thread %d, barrier at shared offset %u, parity %u)\n", blockIdx.x, threadIdx.x, a, parity);
       __trap();
     }
   }

@@ -77,7 +77,9 @@ def test_causal_logic_bit_exact():
 
 
 @pytest.mark.parametrize("B,H,T,dk,quart,mask", [
-    (2, 2, 257, 64, True, False),     # ragged T, two query blocks + tail
+    (8, 4, 257, 64, True, False),     # ragged T, two query blocks + tail; 32 (batch, head) problems: the two scalar gradients are
+                                      # cancelling sums whose bf16-operand noise reaches 3e-2 with 4 problems on either kernel
+                                      # generation (measured over seeds) and averages down with the problem count
     (1, 3, 128, 32, True, True),      # additive mask, exactly one block
     (2, 2, 200, 64, False, False),    # use_quartet = False: single z-scored map
     (1, 2, 1024, 64, True, False),    # GPT-1024 shape (one batch entry)
