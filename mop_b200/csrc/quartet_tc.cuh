@@ -553,7 +553,9 @@ struct __align__(128) SmemQ {
   unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
   float gx[2][2][128];   // [warpgroup][map][row]: row-coefficient partial sums
   float red[16];
-  uint64_t bar;      // MMA completion
+  uint64_t bar;      // MMA completion (Gram epilogue)
+  uint64_t bar_in;   // S1, S2, dP of a tile complete (three issuing threads)
+  uint64_t bar_out;  // dQ1, dQ2 of a tile complete (two issuing threads)
   uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
   uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
@@ -596,7 +598,11 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in, 3); mbar_init(&sm.bar_out, 2);
+    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1);
+    fence_mbar_init();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
     if (wg == 0) (reinterpret_cast<float*>(ws + w.delta) + (size_t)bh * T)[gi] = dlt;   // for bwd_dkdv
   }
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, ph_in = 0, ph_out = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
   // Without an additive mask the tiles run on packed fp32 math with the per-row constants folded in (zero-filled key rows >= T
   // contribute nothing; on diagonal tiles the probabilities above the diagonal are zeroed).  With u, v the raw dot products:  t = f / (sigma1+eps) = A1 + B1 v,  s = scale u t,
@@ -644,20 +650,25 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const int ntiles = (k_end + 63) >> 6;
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // dQ MMAs of tile it-1: its buffers and W are free
-    if (tid == 0) {
-      if (it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
+    if (it > 0) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after(); }   // dQ MMAs of tile it-1: its buffers and W are free
+    // One CTA per SM: nothing hides a lone issuing lane (~110 cycles per tcgen05.mma).  S1 / S2 / dP are issued by lane 0 of three
+    // warps, dQ1 / dQ2 by two more; every one of them commits (an empty commit arrives at once).
+    if (tid == 0 || tid == 32 || tid == 64) {
+      if (tid == 0 && it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
       if (it == 0) mbar_wait(&sm.ldq, 0);
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) {
-        mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      if (tid == 0) {
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      } else if (tid == 32) {
+        if (mx.quart)
+          for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      } else {
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
-      mma_commit(&sm.bar);
+      mma_commit(&sm.bar_in);
     }
-    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+    mbar_wait(&sm.bar_in, ph_in); ph_in ^= 1; tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col = c0 + 16 * c;
@@ -706,18 +717,22 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
       }
     }
     publish();
-    if (tid == 0) {
+    if (tid == 128 || tid == 160) {
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
+      if (tid == 128) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K1[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K2[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K1[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+      } else if (mx.quart) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K2[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       }
-      mma_commit(&sm.bar);
+      mma_commit(&sm.bar_out);
     }
   }
-  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
-  if (tid != 0) mbar_wait(&sm.ldq, 0);   // (already complete: orders the TMA-written query tiles before the generic reads below)
+  mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after();
+  mbar_wait(&sm.ldq, 0);   // (already complete: orders the TMA-written query tiles before the generic reads below)
   if (row_ok) {   // fold the packed-math tiles into the row sums
     const float Sa = Sa2.x + Sa2.y, Sb = Sb2.x + Sb2.y, al1 = p.scale * i1, al2 = p.scale * i2;
     g1 += p.scale * (fA * Sa + fB * Sb);
@@ -846,7 +861,9 @@ struct __align__(128) SmemK {
   unsigned char K1[kT128], K2[kT128], V[kT128], PT[kT128], W1T[kT128], W2T[kT128];
   unsigned char Q[2][kT64], Q2[2][kT64], dO[2][kT64];   // double buffered query-side tiles
   float vec[2][8][64];   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta | packed-math constants A1, B1, L, -delta
-  uint64_t bar;      // MMA completion
+  uint64_t bar;      // MMA completion (M kc epilogue)
+  uint64_t bar_in;   // S1^T, S2^T, dP^T of a tile complete (three issuing threads)
+  uint64_t bar_out;  // dV, dKc1, dKc2 of a tile complete (three issuing threads)
   uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
   uint64_t ldk;      // TMA completion of the key / value tiles
   uint32_t tmem_slot;
@@ -870,7 +887,11 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   const Mix mx = load_mix(p);
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
-  if (tid == 0) { mbar_init(&sm.bar, 1); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in, 3); mbar_init(&sm.bar_out, 3);
+    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1);
+    fence_mbar_init();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -901,12 +922,12 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   }
   fetch(0, k0);
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, ph_in = 0, ph_out = 0;
   float dum0 = 0.f, dum1 = 0.f;
   const int ntiles = (T - k0 + 63) >> 6;   // queries i >= j only (k0 is a multiple of 64)
   for (int it = 0; it < ntiles; ++it) {
     const int q0 = k0 + it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after(); }   // output MMAs of tile it-1 have read their tiles
+    if (it > 0) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after(); }   // output MMAs of tile it-1 have read their tiles
     if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
     if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place (each thread converts the values it fetched itself)
       sm.vec[buf][0][tid] = 1.f / (sm.vec[buf][0][tid] + mx.eps);
@@ -918,18 +939,21 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       sm.vec[buf][7][tid] = -sm.vec[buf][3][tid];
     }
     __syncthreads();   // the per-query vectors of this tile are visible to every thread
-    if (tid == 0) {
+    if (tid == 0 || tid == 32 || tid == 64) {   // transposed tiles: rows = keys, columns = queries; one issuing thread per product
       if (it == 0) mbar_wait(&sm.ldk, 0);
       mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
       const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      for (int ks = 0; ks < dks; ++ks) {   // transposed tiles: rows = keys, columns = queries
-        mma_ss(tb, desc_k_sw(smem_u32(sm.K1), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.K2), 16 * ks), desc_k_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-        mma_ss(tb + 128, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      if (tid == 0) {
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.K1), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      } else if (tid == 32) {
+        if (mx.quart)
+          for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.K2), 16 * ks), desc_k_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
+      } else {
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 128, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
       }
-      mma_commit(&sm.bar);
+      mma_commit(&sm.bar_in);
     }
-    mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+    mbar_wait(&sm.bar_in, ph_in); ph_in ^= 1; tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int colb = c0 + 16 * c;
@@ -986,19 +1010,26 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       }
     }
     publish();
-    if (tid == 0) {
+    if (tid == 128 || tid == 160 || tid == 192) {   // K index = queries of this tile; one issuing thread per product
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
       const uint32_t acc0 = it > 0 ? 1u : 0u;
+      if (tid == 128) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {   // K index = queries of this tile
-        mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
-        if (mx.quart) mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+      } else if (tid == 160) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+      } else if (mx.quart) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       }
-      mma_commit(&sm.bar);
+      mma_commit(&sm.bar_out);
     }
   }
-  mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
+  mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after();
   // dV: this warpgroup's 32 columns
   __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + at(p, b, key_ok ? gj : 0, h);
 #pragma unroll
