@@ -549,14 +549,14 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, u
 // backward
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(128) SmemQ {
-  unsigned char Q[kT128], Q2[kT128], dO[kT128], W1[kT128], W2[kT128];
-  unsigned char K1[2][kT64], K2[2][kT64], V[2][kT64];   // double buffered key / value tiles
+  unsigned char Q[kT128], Q2[kT128], dO[kT128], W1[2][kT128], W2[2][kT128];   // W: one buffer per tile parity
+  unsigned char K1[3][kT64], K2[3][kT64], V[3][kT64];   // three-stage key / value ring
   float gx[2][2][128];   // [warpgroup][map][row]: row-coefficient partial sums
   float red[16];
   uint64_t bar;      // MMA completion (Gram epilogue)
   uint64_t bar_in;   // S1, S2, dP of a tile complete (three issuing threads)
   uint64_t bar_out;  // dQ1, dQ2 of a tile complete (two issuing threads)
-  uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
+  uint64_t ld[3];    // TMA completion of the ring stages
   uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
 };
@@ -582,7 +582,10 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
 }
 
 // grid: B*H*nqb, 256 threads (two warpgroups split the 64 columns of every tile), one CTA per SM
-// TMEM: S1 | S2 | dP | dQ1 | dQ2 (64 columns each)
+// TMEM: two input buffers {S1 | S2 | dP} at columns 0 and 192, dQ1 at 384, dQ2 at 448 (64 columns each).
+// Software pipeline: S1 / S2 / dP of tile t+1 are issued (three lanes) as soon as tile t's have completed, into the other input
+// buffer, so they run during tile t's element math; dQ += W K of tile t (two lanes) runs during tile t+1's element math (W has one
+// buffer per tile parity); one lane refills the three-stage key / value ring once dQ(t-1) is done.
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
@@ -600,24 +603,28 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) {
     mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in, 3); mbar_init(&sm.bar_out, 2);
-    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldq, 1);
+    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ld[2], 1); mbar_init(&sm.ldq, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  auto fetch = [&](int buf, int k0) {   // thread 0 only
-    mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
-    tma_load_tile_sw(sm.K1[buf], &tmKc, k0, 0, bh, &sm.ld[buf]);
-    if (mx.quart) tma_load_tile_sw(sm.K2[buf], &tmKc, k0, 0, (int)BH + bh, &sm.ld[buf]);
-    tma_load_tile_sw(sm.V[buf], &tmV, k0, h, b, &sm.ld[buf]);
+  const int k_end = min(T, q0 + 128);
+  const int ntiles = (k_end + 63) >> 6;   // >= 1
+  auto fetch = [&](int tile) {   // one thread: key tile `tile` -> ring stage tile % 3
+    const int s = tile % 3, k0 = 64 * tile;
+    mbar_expect_tx(&sm.ld[s], (mx.quart ? 3 : 2) * kT64);
+    tma_load_tile_sw(sm.K1[s], &tmKc, k0, 0, bh, &sm.ld[s]);
+    if (mx.quart) tma_load_tile_sw(sm.K2[s], &tmKc, k0, 0, (int)BH + bh, &sm.ld[s]);
+    tma_load_tile_sw(sm.V[s], &tmV, k0, h, b, &sm.ld[s]);
   };
   if (tid == 0) {
     mbar_expect_tx(&sm.ldq, (mx.quart ? 3 : 2) * kT128);
     tma_load_tile_sw(sm.Q, &tmQ, q0, h, b, &sm.ldq);
     if (mx.quart) tma_load_tile_sw(sm.Q2, &tmQ2, q0, h, b, &sm.ldq);
     tma_load_tile_sw(sm.dO, &tmdO, q0, h, b, &sm.ldq);
-    fetch(0, 0);
+    fetch(0);
+    if (ntiles > 1) fetch(1);
   }
   // per-row statistics (both warpgroups need them)
   const float* st = p.stats + (((size_t)b * p.H + h) * T + (row_ok ? gi : T - 1)) * 3;
@@ -646,36 +653,37 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   const float2 A1 = make_float2(fA * i1, fA * i1), B1 = make_float2(fB * i1, fB * i1), cs2 = make_float2(p.scale * kLog2e, p.scale * kLog2e);
   const float2 L2 = make_float2(-lse * kLog2e, -lse * kLog2e), nd2 = make_float2(-dlt, -dlt);
   float2 Sa2 = make_float2(0.f, 0.f), Sb2 = make_float2(0.f, 0.f);
-  const int k_end = min(T, q0 + 128);
-  const int ntiles = (k_end + 63) >> 6;
-  for (int it = 0; it < ntiles; ++it) {
-    const int k0 = it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after(); }   // dQ MMAs of tile it-1: its buffers and W are free
-    // One CTA per SM: nothing hides a lone issuing lane (~110 cycles per tcgen05.mma).  S1 / S2 / dP are issued by lane 0 of three
-    // warps, dQ1 / dQ2 by two more; every one of them commits (an empty commit arrives at once).
-    if (tid == 0 || tid == 32 || tid == 64) {
-      if (tid == 0 && it + 1 < ntiles) fetch(buf ^ 1, k0 + 64);
-      if (it == 0) mbar_wait(&sm.ldq, 0);
-      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      if (tid == 0) {
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      } else if (tid == 32) {
-        if (mx.quart)
-          for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      } else {
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      }
-      mma_commit(&sm.bar_in);
+  // S1 / S2 / dP of tile `tile` into input buffer tile & 1: lane 0 of warps 0, 1, 2, one product each; all three commit (an empty
+  // commit arrives at once).  A lone issuing lane needs ~110 cycles per tcgen05.mma and one CTA per SM hides none of it.
+  auto issue_in = [&](int tile) {
+    const int s = tile % 3;
+    if (tile == 0) mbar_wait(&sm.ldq, 0);
+    mbar_wait(&sm.ld[s], (uint32_t)(tile / 3) & 1u);
+    const uint32_t id = idesc_bf16(128, 64, 0, 0), xc = tb + 192u * (uint32_t)(tile & 1);
+    if (tid == 0) {
+      for (int ks = 0; ks < dks; ++ks) mma_ss(xc, desc_k_sw(smem_u32(sm.Q), 16 * ks), desc_k_sw(smem_u32(sm.K1[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
+    } else if (tid == 32) {
+      if (mx.quart)
+        for (int ks = 0; ks < dks; ++ks) mma_ss(xc + 64, desc_k_sw(smem_u32(sm.Q2), 16 * ks), desc_k_sw(smem_u32(sm.K2[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
+    } else {
+      for (int ks = 0; ks < dks; ++ks) mma_ss(xc + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
     }
+    mma_commit(&sm.bar_in);
+  };
+  const bool in_lane = tid == 0 || tid == 32 || tid == 64;
+  if (in_lane) issue_in(0);
+  for (int it = 0; it < ntiles; ++it) {
+    const int k0 = it * 64, par = it & 1;
+    const uint32_t tx = tl + 192u * (uint32_t)par;   // this tile's input buffer
     mbar_wait(&sm.bar_in, ph_in); ph_in ^= 1; tc_fence_after();
+    if (in_lane && it + 1 < ntiles) issue_in(it + 1);   // the other input buffer was consumed before the barrier of tile it-1
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int col = c0 + 16 * c;
       float v1[16], v2[16], dp[16], w1[16], w2[16];
-      tmem_ld_32x32b_x16(tl + col, v1);
-      if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + col, v2);
-      tmem_ld_32x32b_x16(tl + 128 + col, dp);
+      tmem_ld_32x32b_x16(tx + col, v1);
+      if (mx.quart) tmem_ld_32x32b_x16(tx + 64 + col, v2);
+      tmem_ld_32x32b_x16(tx + 128 + col, dp);
       tmem_ld_wait();
       if (!HAS_MASK) {
         const int lim = gi - k0 - col;   // causal: element e of this chunk is masked when e > lim (diagonal tiles only)
@@ -709,29 +717,35 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
         }
       }
       const int ch = col >> 3;
-      *reinterpret_cast<uint4*>(sm.W1 + ch * (128 * 16) + t * 16) = pack8(w1);
-      *reinterpret_cast<uint4*>(sm.W1 + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
+      *reinterpret_cast<uint4*>(sm.W1[par] + ch * (128 * 16) + t * 16) = pack8(w1);   // W[par] is free: dQ(it-2) completed before the barrier of tile it-1
+      *reinterpret_cast<uint4*>(sm.W1[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
       if (mx.quart) {
-        *reinterpret_cast<uint4*>(sm.W2 + ch * (128 * 16) + t * 16) = pack8(w2);
-        *reinterpret_cast<uint4*>(sm.W2 + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
+        *reinterpret_cast<uint4*>(sm.W2[par] + ch * (128 * 16) + t * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
       }
     }
-    publish();
+    if (tid == 96) {   // ring refill (lane 0 of warp 3): dQ(it-1), issued a tile ago, has read the keys of stage (it-1) % 3
+      if (it >= 1) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; }
+      if (it + 2 < ntiles) fetch(it + 2);
+    }
+    publish();   // W visible to the tensor pipe; every thread now knows dQ(it-1) has completed
     if (tid == 128 || tid == 160) {
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
+      const int s = it % 3;
       if (tid == 128) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tb + 192, desc_kmajor(smem_u32(sm.W1), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K1[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_ss(tb + 384, desc_kmajor(smem_u32(sm.W1[par]), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K1[s]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       } else if (mx.quart) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W2), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K2[buf]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_ss(tb + 448, desc_kmajor(smem_u32(sm.W2[par]), 128, 16 * ks), desc_mn_sw(smem_u32(sm.K2[s]), 16 * ks), id, (it > 0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar_out);
     }
   }
-  mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after();
+  // dQ(ntiles-2) completed before the last barrier, so the parity of the last phase is unambiguous for every thread
+  mbar_wait(&sm.bar_out, (uint32_t)(ntiles - 1) & 1u); tc_fence_after();
   mbar_wait(&sm.ldq, 0);   // (already complete: orders the TMA-written query tiles before the generic reads below)
   if (row_ok) {   // fold the packed-math tiles into the row sums
     const float Sa = Sa2.x + Sa2.y, Sb = Sb2.x + Sb2.y, al1 = p.scale * i1, al2 = p.scale * i2;
@@ -750,12 +764,12 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
   copy_tile64(sm.K2[0], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
   if (mx.quart) {
     copy_tile64(sm.V[0], ws + w.gram + (BH + bh) * 2 * kT64);
-    copy_tile64(sm.W1, ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
+    copy_tile64(sm.W1[0], ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
   }
   publish();
   if (tid == 0) {
     mma_x_sym(tb, smem_u32(sm.Q), smem_u32(sm.K1[0]), smem_u32(sm.K2[0]));
-    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V[0]), smem_u32(sm.W1));
+    if (mx.quart) mma_x_sym(tb + 64, smem_u32(sm.Q2), smem_u32(sm.V[0]), smem_u32(sm.W1[0]));
     mma_commit(&sm.bar);
   }
   mbar_wait(&sm.bar, phase); phase ^= 1; tc_fence_after();
@@ -770,7 +784,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
     for (int c = 0; c < 2; ++c) {   // this warpgroup's 32 output columns
       const int col = c0 + 16 * c;
       float acc[16], wv[16];
-      tmem_ld_32x32b_x16(tl + (map ? 256 : 192) + col, acc);
+      tmem_ld_32x32b_x16(tl + (map ? 448 : 384) + col, acc);
       tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + col, wv);
       tmem_ld_wait();
 #pragma unroll
