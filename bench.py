@@ -40,8 +40,8 @@ BATCH, IMG, PATCH, NTOK = 256, 32, 4, 64
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ewtc::edgewise_bwd2_kernel, B*H = 1024
 # problems) from the committed `ncu --set full` capture; algorithmic read bytes (Q, K, V, dy) are 29.4 MB, i.e. no re-reads
 # (the 22 MB of dqkv written stay in L2 until after the launch).
-DOMINANT_KERNEL_DRAM_BYTES = 29551360 + 159488
-DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01d_ncu_full_ew64_bwd_raw.csv (ncu --set full, one launch)"
+DOMINANT_KERNEL_DRAM_BYTES = 29555712 + 138496
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01e_ew64_bwd_ncu_full_raw.csv (ncu --set full, one launch)"
 WORKLOAD = "ViTEdgewise E+ (dim224 depth8 heads4 V5 share_qkv use_k3 lowrank:mix5 r4), CIFAR-shaped 32x32, batch 256/GPU, fwd+bwd+AdamW"
 
 
