@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, u
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, T = p.T, nqb = w.nqb;
   // heavy (late) query blocks first: the causal work per block grows with its index
   const int qb = nqb - 1 - (int)(blockIdx.x / ((unsigned)p.B * p.H)), bh = blockIdx.x % (p.B * p.H), b = bh / p.H, h = bh % p.H;
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
                                                         const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31, dk = p.dk, T = p.T, nqb = w.nqb;
   const int qb = nqb - 1 - (int)(blockIdx.x / ((unsigned)p.B * p.H)), bh = blockIdx.x % (p.B * p.H), b = bh / p.H, h = bh % p.H;
   const int q0 = qb * 128, gi = q0 + t;
@@ -892,6 +894,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
                                                           const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, T = p.T, nkb = w.nqb;
   const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;   // early key blocks (most work) first
   const int k0 = kb * 128, gj = k0 + t;

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __gr
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, warp = tid >> 5, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
   const int nqb = (Nq + 127) >> 7, BH = p.B * p.H;
   const int qb = nqb - 1 - (int)(blockIdx.x / (unsigned)BH), bh = blockIdx.x % BH, b = bh / p.H, h = bh % p.H;
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* 
                                                         const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemQ& sm = *reinterpret_cast<SmemQ*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
   const int nqb = (Nq + 127) >> 7, BH = p.B * p.H;
   const int qb = nqb - 1 - (int)(blockIdx.x / (unsigned)BH), bh = blockIdx.x % BH, b = bh / p.H, h = bh % p.H;
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const
                                                           const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemK& sm = *reinterpret_cast<SmemK*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, Nq = p.Nq, Nk = p.Nk;
   const int nkb = (Nk + 127) >> 7;
   const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;
