@@ -874,20 +874,23 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
 }
 
 struct __align__(128) SmemK {
-  unsigned char K1[kT128], K2[kT128], V[kT128], PT[kT128], W1T[kT128], W2T[kT128];
-  unsigned char Q[2][kT64], Q2[2][kT64], dO[2][kT64];   // double buffered query-side tiles
-  float vec[2][8][64];   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta | packed-math constants A1, B1, L, -delta
+  unsigned char K1[kT128], K2[kT128], V[kT128], PT[2][kT128], W1T[2][kT128], W2T[2][kT128];   // P^T / W^T: one buffer per tile parity
+  unsigned char Q[3][kT64], Q2[3][kT64], dO[3][kT64];   // three-stage ring of query-side tiles
+  float vec[3][8][64];   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta | packed-math constants A1, B1, L, -delta
   uint64_t bar;      // MMA completion (M kc epilogue)
   uint64_t bar_in;   // S1^T, S2^T, dP^T of a tile complete (three issuing threads)
   uint64_t bar_out;  // dV, dKc1, dKc2 of a tile complete (three issuing threads)
-  uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
+  uint64_t ld[3];    // TMA completion of the query-side ring stages
   uint64_t ldk;      // TMA completion of the key / value tiles
   uint32_t tmem_slot;
 };
 
 
 // grid: B*H*nqb (128 keys per CTA), 256 threads (thread per key row; two warpgroups split the 64 query columns of every
-// tile), one CTA per SM.  TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each)
+// tile), one CTA per SM.  TMEM: S1^T | S2^T | dP^T | dV | dKc1 | dKc2  (64 columns each).
+// The three accumulators leave room for one input buffer only, so the input products of tile t+1 are issued at the barrier of tile
+// t (ahead of the output products in the tensor pipe's queue); the output products of tile t run during tile t+1 (P^T / W^T have
+// one buffer per tile parity) and a lane refills the three-stage query ring once the outputs of tile t-1 are done.
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) {
     mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in, 3); mbar_init(&sm.bar_out, 3);
-    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1);
+    mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ld[2], 1); mbar_init(&sm.ldk, 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -914,15 +917,17 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   tc_fence_after();
   const float* stats = p.stats + ((size_t)b * p.H + h) * T * 3;
   const float* delta = reinterpret_cast<const float*>(ws + w.delta) + (size_t)bh * T;
-  // query-side tiles by TMA (thread 0); the per-query statistics by 4-byte cp.async (threads 0..63)
-  auto fetch = [&](int buf, int q0) {
-    if (tid == 0) {
+  // query tile `tile` -> ring stage tile % 3: tiles by TMA (thread `tma_tid`), the per-query statistics by 4-byte cp.async
+  // (threads 0..63); every thread commits exactly one cp.async group per call, `on` or not, so that the group count stays uniform
+  auto fetch = [&](int tile, int tma_tid, bool on) {
+    const int buf = tile % 3, q0 = k0 + 64 * tile;
+    if (on && tid == tma_tid) {
       mbar_expect_tx(&sm.ld[buf], (mx.quart ? 3 : 2) * kT64);
       tma_load_tile_sw(sm.Q[buf], &tmQ, q0, h, b, &sm.ld[buf]);
       if (mx.quart) tma_load_tile_sw(sm.Q2[buf], &tmQ2, q0, h, b, &sm.ld[buf]);
       tma_load_tile_sw(sm.dO[buf], &tmdO, q0, h, b, &sm.ld[buf]);
     }
-    if (tid < 64) {
+    if (on && tid < 64) {
       const int i = min(q0 + tid, T - 1);
       cp_async4(&sm.vec[buf][0][tid], stats + (size_t)i * 3);
       cp_async4(&sm.vec[buf][1][tid], stats + (size_t)i * 3 + 1);
@@ -937,15 +942,32 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
     if (mx.quart) tma_load_tile_sw(sm.K2, &tmKc, k0, 0, (int)BH + bh, &sm.ldk);
     tma_load_tile_sw(sm.V, &tmV, k0, h, b, &sm.ldk);
   }
-  fetch(0, k0);
+  const int ntiles = (T - k0 + 63) >> 6;   // queries i >= j only (k0 is a multiple of 64); >= 1
+  fetch(0, 0, true);
+  fetch(1, 0, ntiles > 1);
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0, ph_in = 0, ph_out = 0;
   float dum0 = 0.f, dum1 = 0.f;
-  const int ntiles = (T - k0 + 63) >> 6;   // queries i >= j only (k0 is a multiple of 64)
+  const bool in_lane = tid == 0 || tid == 32 || tid == 64;
+  auto issue_in = [&](int tile) {   // transposed tiles: rows = keys, columns = queries; one issuing thread per product, all commit
+    const int s = tile % 3;
+    if (tile == 0) mbar_wait(&sm.ldk, 0);
+    mbar_wait(&sm.ld[s], (uint32_t)(tile / 3) & 1u);
+    const uint32_t id = idesc_bf16(128, 64, 0, 0);
+    if (tid == 0) {
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.K1), 16 * ks), desc_k_sw(smem_u32(sm.Q[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
+    } else if (tid == 32) {
+      if (mx.quart)
+        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.K2), 16 * ks), desc_k_sw(smem_u32(sm.Q2[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
+    } else {
+      for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 128, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
+    }
+    mma_commit(&sm.bar_in);
+  };
+  if (in_lane) issue_in(0);
   for (int it = 0; it < ntiles; ++it) {
-    const int q0 = k0 + it * 64, buf = it & 1;
-    if (it > 0) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after(); }   // output MMAs of tile it-1 have read their tiles
-    if (it + 1 < ntiles) { fetch(buf ^ 1, q0 + 64); cp_async_wait<1>(); } else cp_async_wait<0>();
+    const int q0 = k0 + it * 64, buf = it % 3, par = it & 1;
+    cp_async_wait<1>();   // groups 0 .. it+1 are committed: the statistics of tile `it` have landed
     if (tid < 64) {   // sigma -> 1 / (sigma + eps), in place (each thread converts the values it fetched itself)
       sm.vec[buf][0][tid] = 1.f / (sm.vec[buf][0][tid] + mx.eps);
       sm.vec[buf][1][tid] = mx.quart ? 1.f / (sm.vec[buf][1][tid] + mx.eps) : 0.f;
@@ -956,20 +978,6 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       sm.vec[buf][7][tid] = -sm.vec[buf][3][tid];
     }
     __syncthreads();   // the per-query vectors of this tile are visible to every thread
-    if (tid == 0 || tid == 32 || tid == 64) {   // transposed tiles: rows = keys, columns = queries; one issuing thread per product
-      if (it == 0) mbar_wait(&sm.ldk, 0);
-      mbar_wait(&sm.ld[buf], (uint32_t)(it >> 1) & 1u);
-      const uint32_t id = idesc_bf16(128, 64, 0, 0);
-      if (tid == 0) {
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb, desc_k_sw(smem_u32(sm.K1), 16 * ks), desc_k_sw(smem_u32(sm.Q[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      } else if (tid == 32) {
-        if (mx.quart)
-          for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 64, desc_k_sw(smem_u32(sm.K2), 16 * ks), desc_k_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      } else {
-        for (int ks = 0; ks < dks; ++ks) mma_ss(tb + 128, desc_k_sw(smem_u32(sm.V), 16 * ks), desc_k_sw(smem_u32(sm.dO[buf]), 16 * ks), id, ks > 0 ? 1u : 0u);
-      }
-      mma_commit(&sm.bar_in);
-    }
     mbar_wait(&sm.bar_in, ph_in); ph_in ^= 1; tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -1017,36 +1025,41 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
         w2[e] = o.dn2 * i2;
       }
       const int ch = colb >> 3;
-      *reinterpret_cast<uint4*>(sm.PT + ch * (128 * 16) + t * 16) = pack8(pt);
-      *reinterpret_cast<uint4*>(sm.PT + (ch + 1) * (128 * 16) + t * 16) = pack8(pt + 8);
-      *reinterpret_cast<uint4*>(sm.W1T + ch * (128 * 16) + t * 16) = pack8(w1);
-      *reinterpret_cast<uint4*>(sm.W1T + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
+      *reinterpret_cast<uint4*>(sm.PT[par] + ch * (128 * 16) + t * 16) = pack8(pt);   // free: the outputs of tile it-2 completed before
+      *reinterpret_cast<uint4*>(sm.PT[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(pt + 8);   // the barrier of tile it-1
+      *reinterpret_cast<uint4*>(sm.W1T[par] + ch * (128 * 16) + t * 16) = pack8(w1);
+      *reinterpret_cast<uint4*>(sm.W1T[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(w1 + 8);
       if (mx.quart) {
-        *reinterpret_cast<uint4*>(sm.W2T + ch * (128 * 16) + t * 16) = pack8(w2);
-        *reinterpret_cast<uint4*>(sm.W2T + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
+        *reinterpret_cast<uint4*>(sm.W2T[par] + ch * (128 * 16) + t * 16) = pack8(w2);
+        *reinterpret_cast<uint4*>(sm.W2T[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(w2 + 8);
       }
     }
-    publish();
+    if (tid == 96 && it >= 1) { mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; }   // outputs of tile it-1 (issued a tile ago): stage (it-1) % 3 is free
+    fetch(it + 2, 96, it + 2 < ntiles);
+    publish();   // P^T / W^T visible to the tensor pipe; the input columns have been read; every thread knows the outputs of tile it-1 are done
+    if (in_lane && it + 1 < ntiles) issue_in(it + 1);   // queued ahead of this tile's output products
     if (tid == 128 || tid == 160 || tid == 192) {   // K index = queries of this tile; one issuing thread per product
       const uint32_t id = idesc_bf16(128, 64, 0, 1);
       const uint32_t acc0 = it > 0 ? 1u : 0u;
       if (tid == 128) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+          mma_ss(tb + 192, desc_kmajor(smem_u32(sm.PT[par]), 128, 16 * ks), desc_mn_sw(smem_u32(sm.dO[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       } else if (tid == 160) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+          mma_ss(tb + 256, desc_kmajor(smem_u32(sm.W1T[par]), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       } else if (mx.quart) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
+          mma_ss(tb + 320, desc_kmajor(smem_u32(sm.W2T[par]), 128, 16 * ks), desc_mn_sw(smem_u32(sm.Q2[buf]), 16 * ks), id, (acc0 || ks > 0) ? 1u : 0u);
       }
       mma_commit(&sm.bar_out);
     }
   }
-  mbar_wait(&sm.bar_out, ph_out); ph_out ^= 1; tc_fence_after();
+  cp_async_wait<0>();
+  // the outputs of tile ntiles-2 completed before the last barrier, so the parity of the last phase is unambiguous for every thread
+  mbar_wait(&sm.bar_out, (uint32_t)(ntiles - 1) & 1u); tc_fence_after();
   // dV: this warpgroup's 32 columns
   __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + at(p, b, key_ok ? gj : 0, h);
 #pragma unroll
