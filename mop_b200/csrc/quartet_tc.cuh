@@ -177,11 +177,18 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = 0.f;
     if (ch * 8 < dk)
-      for (int t = r0; t < T; t += 32) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8), f);
+      for (int t = r0; t < T; t += 128) {   // four independent 16-byte loads in flight per thread (the loop is latency bound)
+        uint4 u[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] += f[e];
+        for (int j = 0; j < 4; ++j)
+          u[j] = t + 32 * j < T ? *reinterpret_cast<const uint4*>(k + (size_t)(t + 32 * j) * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+          unpack8(u[j], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
       }
 #pragma unroll
     for (int e = 0; e < 8; ++e) part[r0][ch * 8 + e] = s[e];
@@ -198,14 +205,24 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
   const uint32_t tb = gp.tmem_slot;
   uint32_t phases = 0;
   const int nchunks = (T + 63) >> 6;
+  auto load_rows = [&](int c, uint4* u) {   // this thread's two 16-byte pieces of chunk c (zero outside the tensor)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int t = c * 64 + r0 + 32 * it;
+      u[it] = (c < nchunks && t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 cur[2], nxt[2];
+  load_rows(0, cur);
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c % kGramBufs;
+    load_rows(c + 1, nxt);   // in flight while this chunk is converted, staged and multiplied
     if (c >= kGramBufs) { mbar_wait(&gp.bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; }   // the MMAs that read this buffer are done
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int r = r0 + 32 * it, t = c * 64 + r;
       float f[8];
-      unpack8((t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0), f);
+      unpack8(cur[it], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = (t < T && ch * 8 + e < dk) ? f[e] - kbar[ch * 8 + e] : 0.f;
       const uint4 u = pack8(f);
@@ -219,6 +236,7 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
       for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(tl, 64, 16 * ks), desc_mnmajor(tl, 64, 16 * ks), id, (c > 0 || ks > 0) ? 1u : 0u);
       mma_commit(&gp.bar[buf]);
     }
+    cur[0] = nxt[0]; cur[1] = nxt[1];
   }
   {   // the last commit covers every MMA issued before it
     const int buf = (nchunks - 1) % kGramBufs;
@@ -832,15 +850,27 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
   const int r0 = tid >> 3, ch = tid & 7;
   uint32_t phases = 0;
   const int nchunks = (T + 63) >> 6;
+  auto load_rows = [&](int c, uint4* u, float* gg) {   // this thread's two 16-byte pieces of chunk c and their row coefficients
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int t = c * 64 + r0 + 32 * it;
+      const bool in = c < nchunks && t < T;
+      u[it] = (in && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(q + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+      gg[it] = in ? gv[t] : 0.f;
+    }
+  };
+  uint4 cur[2], nxt[2];
+  float gcur[2], gnxt[2];
+  load_rows(0, cur, gcur);
   for (int c = 0; c < nchunks; ++c) {
     const int buf = 0;
+    load_rows(c + 1, nxt, gnxt);   // in flight while this chunk is converted, staged and multiplied
     if (c >= 1) { mbar_wait(&gp.bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int r = r0 + 32 * it, t = c * 64 + r;
-      const bool ok = t < T && ch * 8 < dk;
-      const uint4 raw = ok ? *reinterpret_cast<const uint4*>(q + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
-      const float g = t < T ? gv[t] : 0.f;
+      const int r = r0 + 32 * it;
+      const uint4 raw = cur[it];
+      const float g = gcur[it];
       float f[8], hi[8], lo[8];
       unpack8(raw, f);
 #pragma unroll
@@ -863,6 +893,7 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
       for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(tlo, 64, 16 * ks), desc_mnmajor(tq, 64, 16 * ks), id, 1u);
       mma_commit(&gp.bar[buf]);
     }
+    cur[0] = nxt[0]; cur[1] = nxt[1]; gcur[0] = gnxt[0]; gcur[1] = gnxt[1];
   }
   mbar_wait(&gp.bar[0], phases & 1u);
   tc_fence_after();
@@ -1113,19 +1144,31 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
 
 // grid: B*H*nm, 256 threads.  dk = dkc - mean_j dkc ; map 0 also reduces the scalar partials of its (b,h)
 __global__ void __launch_bounds__(256) finish_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
-  __shared__ float part[4][64];
+  __shared__ float part[16][64];
   __shared__ float mean[64];
   const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
   const size_t BH = (size_t)p.B * p.H;
   const float* dkc = reinterpret_cast<const float*>(ws + w.dkc) + ((size_t)map * BH + bh) * T * 64;
-  {
-    const int d = tid & 63, sl = tid >> 6;
-    float s = 0.f;
-    for (int t = sl; t < T; t += 4) s += dkc[(size_t)t * 64 + d];
-    part[sl][d] = s;
+  {   // column sums: thread = (row slot, four columns), four independent 16-byte loads in flight (the loop is latency bound)
+    const int c4 = (tid & 15) * 4, sl = tid >> 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = sl; t < T; t += 64) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = t + 16 * j < T ? *reinterpret_cast<const float4*>(dkc + (size_t)(t + 16 * j) * 64 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    part[sl][c4] = s.x; part[sl][c4 + 1] = s.y; part[sl][c4 + 2] = s.z; part[sl][c4 + 3] = s.w;
   }
   __syncthreads();
-  if (tid < 64) mean[tid] = (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) / (float)T;
+  if (tid < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += part[i][tid];
+    mean[tid] = s / (float)T;
+  }
   __syncthreads();
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(map ? p.dk2 : p.dk_) + at(p, b, 0, h);
   const size_t stride = (size_t)p.H * dk;
