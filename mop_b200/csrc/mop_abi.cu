@@ -427,7 +427,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     (hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>)<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
     qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
     (hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>)<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws, tmQs, tmQ2s, tmdOs, tmKcL, tmVL);
-    qtc::finish_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+    qtc::finish_kernel<<<BH * w.nm * ((p->T + 63) / 64), 256, 0, st>>>(*p, w, ws);
   }
   MOP_CHECK_CUDA(cudaGetLastError());
   p->impl_used = MOP_IMPL_TCGEN05;

@@ -50,7 +50,7 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 struct Ws {  // byte offsets into the workspace
-  size_t kc, gram, gvec, mmat, dkc, spart, delta, total;
+  size_t kc, gram, gvec, mmat, dkc, dksum, spart, delta, total;
   int nm, nqb;
 };
 __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
@@ -62,11 +62,12 @@ __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
   w.kc = take(w.nm * BH * T * 64 * 2);       // bf16 [nm][BH][T][64] (columns >= dk are zero)
   w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
-  w.gvec = w.mmat = w.dkc = w.spart = w.delta = 0;
+  w.gvec = w.mmat = w.dkc = w.dksum = w.spart = w.delta = 0;
   if (backward) {
     w.gvec = take(w.nm * BH * T * 4);
     w.mmat = take(w.nm * BH * 2 * kT64);     // bf16 hi / lo tile images of sum_i g_i q_i q_i^T
     w.dkc = take(w.nm * BH * T * 64 * 4);    // fp32 [nm][BH][T][64]
+    w.dksum = take(w.nm * BH * 64 * 4);      // fp32 [nm][BH][64]: column sums of dkc (zeroed by prep, accumulated by bwd_dkdv)
     w.spart = take(BH * w.nqb * 2 * 4);
     w.delta = take(BH * T * 4);              // fp32 [BH][T]: dO . y per query (bwd_dq -> bwd_dkdv)
   }
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
   __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(ws + w.kc) + ((size_t)map * BH + bh) * T * 64;
   if (tid < 32) tmem_alloc<64>(&gp.tmem_slot);
   if (tid == 0) { for (int i = 0; i < kGramBufs; ++i) mbar_init(&gp.bar[i], 1); fence_mbar_init(); }
+  if (w.dksum && tid < 64) (reinterpret_cast<float*>(ws + w.dksum) + ((size_t)map * BH + bh) * 64)[tid] = 0.f;   // backward only
   const int r0 = tid >> 3, ch = tid & 7;   // this thread: rows r0, r0 + 32, ... and the 8 columns of chunk ch
   {
     float s[8];
@@ -1128,12 +1130,25 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
       tmem_ld_32x32b_x16(tl + (map ? 320 : 256) + col, acc);
       tmem_ld_32x32b_x16(tl + (map ? 64 : 0) + col, wv);
       tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = key_ok ? p.scale * acc[e] - p.scale * p.scale * wv[e] : 0.f;
       if (key_ok) {
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4)
-          *reinterpret_cast<float4*>(out + col + 4 * e4) =
-              make_float4(p.scale * acc[4 * e4] - p.scale * p.scale * wv[4 * e4], p.scale * acc[4 * e4 + 1] - p.scale * p.scale * wv[4 * e4 + 1],
-                          p.scale * acc[4 * e4 + 2] - p.scale * p.scale * wv[4 * e4 + 2], p.scale * acc[4 * e4 + 3] - p.scale * p.scale * wv[4 * e4 + 3]);
+          *reinterpret_cast<float4*>(out + col + 4 * e4) = make_float4(acc[4 * e4], acc[4 * e4 + 1], acc[4 * e4 + 2], acc[4 * e4 + 3]);
+      }
+      // column sums of this warp's 32 key rows -> global (finish_kernel subtracts the mean over all T keys)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float v = acc[e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[e] = v;
+      }
+      if ((tid & 31) == 0) {
+        float* sum = reinterpret_cast<float*>(ws + w.dksum) + ((size_t)map * BH + bh) * 64 + col;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) atomicAdd(sum + e, acc[e]);
       }
     }
   }
@@ -1142,45 +1157,27 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
   if (tid < 32) tmem_dealloc<512>(tb);
 }
 
-// grid: B*H*nm, 256 threads.  dk = dkc - mean_j dkc ; map 0 also reduces the scalar partials of its (b,h)
+// grid: (B*H*nm) * ceil(T/64), 256 threads: dk = dkc - mean_j dkc for 64 keys, the column sums come from bwd_dkdv (w.dksum);
+// the first chunk of map 0 also folds the scalar partials of the query blocks
 __global__ void __launch_bounds__(256) finish_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
-  __shared__ float part[16][64];
   __shared__ float mean[64];
-  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
+  const int nm = w.nm, T = p.T, nch = (T + 63) >> 6, dk = p.dk, tid = threadIdx.x;
+  const int chunk = blockIdx.x % nch, bm = blockIdx.x / nch, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;
   const size_t BH = (size_t)p.B * p.H;
   const float* dkc = reinterpret_cast<const float*>(ws + w.dkc) + ((size_t)map * BH + bh) * T * 64;
-  {   // column sums: thread = (row slot, four columns), four independent 16-byte loads in flight (the loop is latency bound)
-    const int c4 = (tid & 15) * 4, sl = tid >> 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = sl; t < T; t += 64) {
-      float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        v[j] = t + 16 * j < T ? *reinterpret_cast<const float4*>(dkc + (size_t)(t + 16 * j) * 64 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
-    }
-    part[sl][c4] = s.x; part[sl][c4 + 1] = s.y; part[sl][c4 + 2] = s.z; part[sl][c4 + 3] = s.w;
-  }
-  __syncthreads();
-  if (tid < 64) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += part[i][tid];
-    mean[tid] = s / (float)T;
-  }
+  if (tid < 64) mean[tid] = (reinterpret_cast<const float*>(ws + w.dksum) + ((size_t)map * BH + bh) * 64)[tid] / (float)T;
   __syncthreads();
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(map ? p.dk2 : p.dk_) + at(p, b, 0, h);
   const size_t stride = (size_t)p.H * dk;
-  for (int idx = tid; idx < T * 8; idx += 256) {
-    const int t = idx >> 3, ch = idx & 7;
-    if (ch * 8 >= dk) continue;
+  for (int idx = tid; idx < 64 * 8; idx += 256) {
+    const int t = chunk * 64 + (idx >> 3), ch = idx & 7;
+    if (t >= T || ch * 8 >= dk) continue;
     const float4 a = *reinterpret_cast<const float4*>(dkc + (size_t)t * 64 + ch * 8), c = *reinterpret_cast<const float4*>(dkc + (size_t)t * 64 + ch * 8 + 4);
     const float f[8] = {a.x - mean[ch * 8], a.y - mean[ch * 8 + 1], a.z - mean[ch * 8 + 2], a.w - mean[ch * 8 + 3],
                         c.x - mean[ch * 8 + 4], c.y - mean[ch * 8 + 5], c.z - mean[ch * 8 + 6], c.w - mean[ch * 8 + 7]};
     *reinterpret_cast<uint4*>(out + (size_t)t * stride + ch * 8) = pack8(f);
   }
-  if (map == 0 && tid < 2 && p.dscalar_part) {
+  if (chunk == 0 && map == 0 && tid < 2 && p.dscalar_part) {
     float s = 0.f;
     const float* sp = reinterpret_cast<const float*>(ws + w.spart) + (size_t)bh * w.nqb * 2;
     for (int c = 0; c < w.nqb; ++c) s += sp[c * 2 + tid];
