@@ -402,7 +402,15 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   const size_t smem_q = sizeof(qtc::SmemQ) + 128 > one_per_sm ? sizeof(qtc::SmemQ) + 128 : one_per_sm;
   const size_t smem_k = sizeof(qtc::SmemK) + 128 > one_per_sm ? sizeof(qtc::SmemK) + 128 : one_per_sm;
   int rc;
-  qtc::prep_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  if (BH * w.nm >= 2 * sm_count()) {   // enough (b, h, map) problems to fill the GPU: one CTA each, one launch
+    qtc::prep_fused_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  } else {   // key-side preparation split over groups of kPrepRows keys (quartet_tc.cuh)
+    const int groups = (p->T + qtc::kPrepRows - 1) / qtc::kPrepRows;
+    MOP_CHECK_CUDA(cudaMemsetAsync(ws + w.ksum, 0, w.gacc + (size_t)w.nm * BH * 64 * 64 * 4 - w.ksum, st));   // ksum and gacc are adjacent
+    qtc::prep_sum_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws);
+    qtc::prep_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws);
+    qtc::prep_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+  }
   const bool hm = p->add_mask != nullptr;
   // TMA tensor maps: activations [B,T,H,dk] (contiguous) and the centred keys in the workspace ([nm*B*H, T, 1, 64])
   const int64_t sT = (int64_t)p->H * p->dk, sB = (int64_t)p->T * sT;

@@ -50,7 +50,7 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 struct Ws {  // byte offsets into the workspace
-  size_t kc, gram, gvec, mmat, dkc, dksum, spart, delta, total;
+  size_t kc, gram, ksum, gacc, gvec, mmat, dkc, dksum, spart, delta, total;
   int nm, nqb;
 };
 __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
@@ -62,6 +62,8 @@ __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
   w.kc = take(w.nm * BH * T * 64 * 2);       // bf16 [nm][BH][T][64] (columns >= dk are zero)
   w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
+  w.ksum = take(w.nm * BH * 64 * 4);         // fp32 column sums of k          } zeroed by one memset before the prep kernels,
+  w.gacc = take(w.nm * BH * 64 * 64 * 4);    // fp32 Kc^T Kc accumulators      } accumulated with atomics by their row groups
   w.gvec = w.mmat = w.dkc = w.dksum = w.spart = w.delta = 0;
   if (backward) {
     w.gvec = take(w.nm * BH * T * 4);
@@ -158,9 +160,126 @@ __device__ inline void gram_readout(uint32_t tb, float* G) {
   }
 }
 
+// The key-side preparation is split over row groups of kPrepRows keys so that it fills the GPU at every (B, T) - one CTA per
+// (b, h, map) left 96 CTAs with 64 serial chunks each at T = 4096, B = 4:
+//   prep_sum_kernel    grid (B*H*nm) * groups: column sums of k -> atomics into w.ksum
+//   prep_kernel        grid (B*H*nm) * groups: kc = bf16(k - kbar) (workspace), partial Kc^T Kc of the group's rounded rows on
+//                      the tensor core -> atomics into w.gacc
+//   prep_tiles_kernel  grid B*H*nm: w.gacc -> bf16 hi / lo tile images
+constexpr int kPrepRows = 256;
+__global__ void __launch_bounds__(256) prep_sum_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ float part[32][64];
+  const int nm = w.nm, T = p.T, ngr = (T + kPrepRows - 1) / kPrepRows, dk = p.dk, tid = threadIdx.x;
+  const int grp = blockIdx.x % ngr, bm = blockIdx.x / ngr, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(map ? p.k2 : p.k) + at(p, b, 0, h);
+  const int r0 = tid >> 3, ch = tid & 7;   // rows r0 + 32 j of the group, the 8 columns of chunk ch
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  uint4 u[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // eight independent 16-byte loads in flight
+    const int t = grp * kPrepRows + r0 + 32 * j;
+    u[j] = (t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float f[8];
+    unpack8(u[j], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[r0][ch * 8 + e] = s[e];
+  __syncthreads();
+  if (tid < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += part[i][tid];
+    atomicAdd(reinterpret_cast<float*>(ws + w.ksum) + ((size_t)map * BH + bh) * 64 + tid, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ __align__(128) unsigned char tiles[kGramBufs][kT64];
+  __shared__ __align__(16) float G[64 * 64];
+  __shared__ float kbar[64];
+  __shared__ GramPipe gp;
+  const int nm = w.nm, T = p.T, ngr = (T + kPrepRows - 1) / kPrepRows, dk = p.dk, tid = threadIdx.x;
+  const int grp = blockIdx.x % ngr, bm = blockIdx.x / ngr, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;
+  const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(map ? p.k2 : p.k) + at(p, b, 0, h);
+  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(ws + w.kc) + ((size_t)map * BH + bh) * T * 64;
+  if (tid < 32) tmem_alloc<64>(&gp.tmem_slot);
+  if (tid == 0) { for (int i = 0; i < kGramBufs; ++i) mbar_init(&gp.bar[i], 1); fence_mbar_init(); }
+  if (w.dksum && grp == 0 && tid < 64) (reinterpret_cast<float*>(ws + w.dksum) + ((size_t)map * BH + bh) * 64)[tid] = 0.f;   // backward only
+  if (tid < 64) kbar[tid] = (reinterpret_cast<const float*>(ws + w.ksum) + ((size_t)map * BH + bh) * 64)[tid] / (float)T;
+  const int r0 = tid >> 3, ch = tid & 7;   // this thread: rows r0, r0 + 32 of a chunk and the 8 columns of chunk ch
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = gp.tmem_slot;
+  uint32_t phases = 0;
+  const int c_lo = grp * (kPrepRows / 64), nchunks = min(kPrepRows / 64, ((T + 63) >> 6) - c_lo);   // this group's 64-row chunks
+  auto load_rows = [&](int c, uint4* u) {   // this thread's two 16-byte pieces of chunk c (zero outside the tensor / the group)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int t = (c_lo + c) * 64 + r0 + 32 * it;
+      u[it] = (c < nchunks && t < T && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(k + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 cur[2], nxt[2];
+  load_rows(0, cur);
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c % kGramBufs;
+    load_rows(c + 1, nxt);   // in flight while this chunk is converted, staged and multiplied
+    if (c >= kGramBufs) { mbar_wait(&gp.bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; }   // the MMAs that read this buffer are done
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = r0 + 32 * it, t = (c_lo + c) * 64 + r;
+      float f[8];
+      unpack8(cur[it], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = (t < T && ch * 8 + e < dk) ? f[e] - kbar[ch * 8 + e] : 0.f;
+      const uint4 u = pack8(f);
+      if (t < T) *reinterpret_cast<uint4*>(kc + (size_t)t * 64 + ch * 8) = u;
+      *reinterpret_cast<uint4*>(tiles[buf] + ch * 1024 + r * 16) = u;
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t id = idesc_bf16(64, 64, 1, 1), tl = smem_u32(tiles[buf]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_ss(tb, desc_mnmajor(tl, 64, 16 * ks), desc_mnmajor(tl, 64, 16 * ks), id, (c > 0 || ks > 0) ? 1u : 0u);
+      mma_commit(&gp.bar[buf]);
+    }
+    cur[0] = nxt[0]; cur[1] = nxt[1];
+  }
+  {   // the last commit covers every MMA issued before it
+    const int buf = (nchunks - 1) % kGramBufs;
+    mbar_wait(&gp.bar[buf], (phases >> buf) & 1u);
+    tc_fence_after();
+  }
+  gram_readout(tb, G);
+  tc_fence_before();
+  __syncthreads();
+  float* acc = reinterpret_cast<float*>(ws + w.gacc) + ((size_t)map * BH + bh) * 64 * 64;
+  for (int i = tid; i < 64 * 64; i += 256) atomicAdd(acc + i, G[i]);
+  if (tid < 32) tmem_dealloc<64>(tb);
+}
+
+__global__ void __launch_bounds__(256) prep_tiles_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+  __shared__ __align__(16) float G[64 * 64];
+  const float* acc = reinterpret_cast<const float*>(ws + w.gacc) + (size_t)blockIdx.x * 64 * 64;   // blockIdx.x = map * BH + bh
+  for (int i = threadIdx.x; i < 64 * 64 / 4; i += 256) reinterpret_cast<float4*>(G)[i] = reinterpret_cast<const float4*>(acc)[i];
+  __syncthreads();
+  write_hilo_tiles(G, ws + w.gram + (size_t)blockIdx.x * 2 * kT64);
+}
+
+// One CTA per (b, h, map): used when B*H*nm alone fills the GPU (fewer launches, no atomics).
 // grid: B*H*nm, 256 threads.  kbar, kc = bf16(k - kbar) (written to the workspace and staged for the MMA),
 // G = Kc^T Kc from that rounded kc -> bf16 hi / lo tile images.
-__global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+__global__ void __launch_bounds__(256) prep_fused_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ __align__(128) unsigned char tiles[kGramBufs][kT64];
   __shared__ __align__(16) float G[64 * 64];
   __shared__ float part[32][64];

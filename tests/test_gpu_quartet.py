@@ -84,6 +84,7 @@ def test_causal_logic_bit_exact():
     (2, 2, 200, 64, False, False),    # use_quartet = False: single z-scored map
     (1, 2, 1024, 64, True, False),    # GPT-1024 shape (one batch entry)
     (3, 1, 40, 16, True, False),      # smaller than one tile
+    (10, 15, 70, 16, True, False),    # 300 (batch, head, map) problems >= 2 x SMs: the one-CTA-per-problem key preparation
 ])
 def test_tcgen05_vs_oracle_and_simt(B, H, T, dk, quart, mask):
     """tcgen05 Quartet forward + backward: against the fp64 oracle on the same bf16 inputs and the fp32-math SIMT kernels."""
