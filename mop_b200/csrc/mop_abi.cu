@@ -409,7 +409,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     MOP_CHECK_CUDA(cudaMemsetAsync(ws + w.ksum, 0, w.gacc + (size_t)w.nm * BH * 64 * 64 * 4 - w.ksum, st));   // ksum and gacc are adjacent
     qtc::prep_sum_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws);
     qtc::prep_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws);
-    qtc::prep_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+    qtc::acc_to_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(ws, w.gacc, w.gram);
   }
   const bool hm = p->add_mask != nullptr;
   // TMA tensor maps: activations [B,T,H,dk] (contiguous) and the centred keys in the workspace ([nm*B*H, T, 1, 64])
@@ -433,7 +433,14 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     if ((rc = make_tile_map_sw(&tmKcL, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
     (hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>)<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
-    qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
+    const int nct = (p->T + 63) / 64, cpg = 4, groups = (nct + cpg - 1) / cpg;
+    if (BH * w.nm >= 2 * sm_count() || groups == 1) {
+      qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws, 1, nct);
+    } else {   // split over groups of four 64-row chunks: partial sums by atomics, then the tile images
+      MOP_CHECK_CUDA(cudaMemsetAsync(ws + w.macc, 0, (size_t)w.nm * BH * 64 * 64 * 4, st));
+      qtc::gmat_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws, groups, cpg);
+      qtc::acc_to_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(ws, w.macc, w.mmat);
+    }
     (hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>)<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws, tmQs, tmQ2s, tmdOs, tmKcL, tmVL);
     qtc::finish_kernel<<<BH * w.nm * ((p->T + 63) / 64), 256, 0, st>>>(*p, w, ws);
   }

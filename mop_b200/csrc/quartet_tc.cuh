@@ -50,7 +50,7 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 struct Ws {  // byte offsets into the workspace
-  size_t kc, gram, ksum, gacc, gvec, mmat, dkc, dksum, spart, delta, total;
+  size_t kc, gram, ksum, gacc, gvec, mmat, macc, dkc, dksum, spart, delta, total;
   int nm, nqb;
 };
 __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
@@ -64,10 +64,11 @@ __host__ __device__ inline Ws layout(const MopQuartetParams* p, int backward) {
   w.gram = take(w.nm * BH * 2 * kT64);       // bf16 hi / lo tile images of Kc^T Kc: [nm][BH][2][8 KB]
   w.ksum = take(w.nm * BH * 64 * 4);         // fp32 column sums of k          } zeroed by one memset before the prep kernels,
   w.gacc = take(w.nm * BH * 64 * 64 * 4);    // fp32 Kc^T Kc accumulators      } accumulated with atomics by their row groups
-  w.gvec = w.mmat = w.dkc = w.dksum = w.spart = w.delta = 0;
+  w.gvec = w.mmat = w.macc = w.dkc = w.dksum = w.spart = w.delta = 0;
   if (backward) {
     w.gvec = take(w.nm * BH * T * 4);
     w.mmat = take(w.nm * BH * 2 * kT64);     // bf16 hi / lo tile images of sum_i g_i q_i q_i^T
+    w.macc = take(w.nm * BH * 64 * 64 * 4);  // fp32 accumulators of the same when gmat is split over row groups (memset, atomics)
     w.dkc = take(w.nm * BH * T * 64 * 4);    // fp32 [nm][BH][T][64]
     w.dksum = take(w.nm * BH * 64 * 4);      // fp32 [nm][BH][64]: column sums of dkc (zeroed by prep, accumulated by bwd_dkdv)
     w.spart = take(BH * w.nqb * 2 * 4);
@@ -165,7 +166,7 @@ __device__ inline void gram_readout(uint32_t tb, float* G) {
 //   prep_sum_kernel    grid (B*H*nm) * groups: column sums of k -> atomics into w.ksum
 //   prep_kernel        grid (B*H*nm) * groups: kc = bf16(k - kbar) (workspace), partial Kc^T Kc of the group's rounded rows on
 //                      the tensor core -> atomics into w.gacc
-//   prep_tiles_kernel  grid B*H*nm: w.gacc -> bf16 hi / lo tile images
+//   acc_to_tiles_kernel  grid B*H*nm: w.gacc -> bf16 hi / lo tile images
 constexpr int kPrepRows = 256;
 __global__ void __launch_bounds__(256) prep_sum_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ float part[32][64];
@@ -268,12 +269,13 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
   if (tid < 32) tmem_dealloc<64>(tb);
 }
 
-__global__ void __launch_bounds__(256) prep_tiles_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+// fp32 64x64 accumulators (byte offset acc_off) -> bf16 hi / lo tile images (byte offset tiles_off); blockIdx.x = map * BH + bh
+__global__ void __launch_bounds__(256) acc_to_tiles_kernel(unsigned char* ws, size_t acc_off, size_t tiles_off) {
   __shared__ __align__(16) float G[64 * 64];
-  const float* acc = reinterpret_cast<const float*>(ws + w.gacc) + (size_t)blockIdx.x * 64 * 64;   // blockIdx.x = map * BH + bh
+  const float* acc = reinterpret_cast<const float*>(ws + acc_off) + (size_t)blockIdx.x * 64 * 64;
   for (int i = threadIdx.x; i < 64 * 64 / 4; i += 256) reinterpret_cast<float4*>(G)[i] = reinterpret_cast<const float4*>(acc)[i];
   __syncthreads();
-  write_hilo_tiles(G, ws + w.gram + (size_t)blockIdx.x * 2 * kT64);
+  write_hilo_tiles(G, ws + tiles_off + (size_t)blockIdx.x * 2 * kT64);
 }
 
 // One CTA per (b, h, map): used when B*H*nm alone fills the GPU (fewer launches, no atomics).
@@ -954,11 +956,14 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
 }
 
 // grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T = (g q)^T q on the tensor core, g q split into bf16 hi + lo
-__global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+// groups > 1: the queries of one (b, h, map) are split over `groups` CTAs of `cpg` 64-row chunks each; partial sums go to
+// w.macc with atomics and acc_to_tiles_kernel writes the tile images (used when B*H*nm alone does not fill the GPU)
+__global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws, int groups, int cpg) {
   __shared__ __align__(128) unsigned char tiles[1][3][kT64];   // [g q hi | g q lo | q] (single buffer: several CTAs share an SM)
   __shared__ GramPipe gp;
   float* G = reinterpret_cast<float*>(&tiles[0][0][0]);        // 16 KB: read out once every MMA has completed
-  const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, T = p.T, tid = threadIdx.x;
+  const int nm = w.nm, grp = blockIdx.x % groups, bm = blockIdx.x / groups, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;
+  const int dk = p.dk, T = p.T, tid = threadIdx.x;
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(map ? p.q2 : p.q) + at(p, b, 0, h);
   const float* gv = reinterpret_cast<const float*>(ws + w.gvec) + ((size_t)map * BH + bh) * T;
@@ -970,11 +975,11 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
   const uint32_t tb = gp.tmem_slot;
   const int r0 = tid >> 3, ch = tid & 7;
   uint32_t phases = 0;
-  const int nchunks = (T + 63) >> 6;
+  const int c_lo = grp * cpg, nchunks = min(cpg, ((T + 63) >> 6) - c_lo);   // this CTA's 64-row chunks (>= 1)
   auto load_rows = [&](int c, uint4* u, float* gg) {   // this thread's two 16-byte pieces of chunk c and their row coefficients
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const int t = c * 64 + r0 + 32 * it;
+      const int t = (c_lo + c) * 64 + r0 + 32 * it;
       const bool in = c < nchunks && t < T;
       u[it] = (in && ch * 8 < dk) ? *reinterpret_cast<const uint4*>(q + (size_t)t * stride + ch * 8) : make_uint4(0, 0, 0, 0);
       gg[it] = in ? gv[t] : 0.f;
@@ -1021,7 +1026,12 @@ __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, uns
   gram_readout(tb, G);
   tc_fence_before();
   __syncthreads();
-  write_hilo_tiles(G, ws + w.mmat + ((size_t)map * BH + bh) * 2 * kT64);
+  if (groups == 1) {
+    write_hilo_tiles(G, ws + w.mmat + ((size_t)map * BH + bh) * 2 * kT64);
+  } else {
+    float* acc = reinterpret_cast<float*>(ws + w.macc) + ((size_t)map * BH + bh) * 64 * 64;
+    for (int i = tid; i < 64 * 64; i += 256) atomicAdd(acc + i, G[i]);
+  }
   if (tid < 32) tmem_dealloc<64>(tb);
 }
 
