@@ -1,0 +1,153 @@
+// libmop_b200.so - C ABI entry points (see include/mop_b200.h): Edgewise attention
+// Host side only validates, sizes scratch and enqueues kernels on the caller's stream.
+#include "abi_host.h"
+#include "edgewise_simt.cuh"
+#include "edgewise_tc.cuh"
+#include "edgewise_tc_bwd2.cuh"
+#include "edgewise_tc_large.cuh"
+#include "edgewise_tc_large_bwd.cuh"
+
+namespace mop {
+// ---------------------------------------------------------------------------
+static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
+  MOP_REQUIRE(p != nullptr, MOP_EINVAL, "params is NULL");
+  MOP_REQUIRE(p->struct_bytes == (int32_t)sizeof(MopEdgewiseParams), MOP_EABI,
+              "MopEdgewiseParams size mismatch: caller %d, library %d", p->struct_bytes, (int)sizeof(MopEdgewiseParams));
+  MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "bad dtype %d", p->dtype);
+  MOP_REQUIRE(p->B > 0 && p->H > 0 && p->N > 0 && p->dk > 0, MOP_EINVAL, "bad shape B=%d H=%d N=%d dk=%d", p->B, p->H, p->N, p->dk);
+  MOP_REQUIRE(p->V >= 2 && p->V <= ew::kMaxViews, MOP_EUNSUPPORTED, "n_views=%d outside [2,%d]", p->V, ew::kMaxViews);
+  MOP_REQUIRE(p->Vp == 1 || p->Vp == p->V, MOP_EINVAL, "Vp must be 1 or V");
+  MOP_REQUIRE(p->gate_mode == MOP_GATE_DENSE || p->gate_mode == MOP_GATE_LOWRANK, MOP_EINVAL, "bad gate_mode %d", p->gate_mode);
+  MOP_REQUIRE(p->qkv && p->y && p->chain_value_logit, MOP_EINVAL, "qkv / y / chain_value_logit must be set");
+  MOP_REQUIRE((p->q_scale != nullptr) == (p->k_scale != nullptr) && (p->q_scale != nullptr) == (p->v_scale != nullptr),
+              MOP_EINVAL, "q/k/v_scale must be all set or all NULL");
+  if (p->gate_mode == MOP_GATE_LOWRANK) {
+    MOP_REQUIRE(p->gate_rank >= 1 && p->gate_rank <= ew::kMaxRank, MOP_EUNSUPPORTED, "gate_rank=%d outside [1,%d]", p->gate_rank, ew::kMaxRank);
+    MOP_REQUIRE(p->row_w && p->row_b && p->col_w && p->col_b, MOP_EINVAL, "lowrank head tensors missing");
+  } else {
+    MOP_REQUIRE(p->hidden >= 1 && p->hidden <= ew::kMaxHidden, MOP_EUNSUPPORTED, "hidden=%d outside [1,%d]", p->hidden, ew::kMaxHidden);
+    MOP_REQUIRE(p->conv1_w && p->conv1_b && p->conv2_w && p->conv2_b, MOP_EINVAL, "dense head tensors missing");
+    MOP_REQUIRE(!p->use_k3 || (p->mid3_w && p->mid3_b), MOP_EINVAL, "use_k3 set but mid3 tensors missing");
+  }
+  if (bwd) {
+    MOP_REQUIRE(p->dy && p->dqkv && p->dhead_part && p->dlogit_part, MOP_EINVAL, "backward buffers missing");
+    MOP_REQUIRE((p->q_scale == nullptr) || p->dscale_part, MOP_EINVAL, "dscale_part missing");
+  }
+  return MOP_OK;
+}
+
+static int edgewise_grid(const MopEdgewiseParams* p) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;  // sizing only (no device): B200
+  int G = p->B * p->H;
+  return G < 2 * sms ? G : 2 * sms;
+}
+
+static ew::Layout edgewise_layout(const MopEdgewiseParams* p, int bwd) {
+  ew::Layout L;
+  const bool dense = p->gate_mode == MOP_GATE_DENSE;
+  L.build(p->N, p->dk, p->V, p->Vp, dense ? 1 : p->gate_rank, dense ? p->hidden : 1, dense ? 1 : 0,
+          dense && p->use_k3 ? 1 : 0, bwd);
+  return L;
+}
+
+}  // namespace mop
+
+using namespace mop;
+
+extern "C" {
+
+size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
+  if (!p) return 0;
+  const bool dense = p->gate_mode == MOP_GATE_DENSE;
+  return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3);
+}
+
+int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  return (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) ? 1 : 0;
+}
+
+size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  if (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) {
+    // per-CTA scratch slots of bf16 map images (forward: the V per-view softmax maps; backward: see edgewise_tc_large_bwd.cuh)
+    if (!backward) return (size_t)ewl::grid_size(p) * ewtc::kMaxV * ewl::kBufA;
+    if (p->row_stats && p->y_base) return (size_t)ewl::grid_size(p) * ewl::kBwdSlots * ewl::kBufA;
+  }
+  ew::Layout L = edgewise_layout(p, backward ? 1 : 0);
+  return (size_t)edgewise_grid(p) * L.total * sizeof(float);
+}
+
+static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
+  int rc = check_edgewise(p, bwd);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = ewtc::supported(p);
+  // token counts up to 200 (ViT-B/16: 196); the backward needs the row statistics saved by the forward
+  const bool large_ok = !tc_ok && (bwd ? ewl::supported_bwd(p) : ewl::supported(p));
+  MOP_REQUIRE(p->impl == MOP_IMPL_AUTO || p->impl == MOP_IMPL_SIMT || (p->impl == MOP_IMPL_TCGEN05 && (tc_ok || large_ok)), MOP_EUNSUPPORTED,
+              "impl %d not available for this shape (tcgen05 path: bf16, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4; "
+              "N=64 forward+backward, N<=200 forward)", p->impl);
+  if (large_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t smem = sizeof(ewl::Smem) + 128, smem_b = sizeof(ewl::SmemBwd) + 128;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MOP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      configured_dev = dev;
+    }
+    const size_t need = (size_t)ewl::grid_size(p) * (bwd ? ewl::kBwdSlots : ewtc::kMaxV) * ewl::kBufA;
+    MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+    MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, MOP_EINVAL, "workspace must be 16-byte aligned");
+    if (bwd) ewl::edgewise_bwd_kernel<<<ewl::grid_size(p), 256, smem_b, st>>>(*p);
+    else ewl::edgewise_fwd_kernel<<<ewl::grid_size(p), 256, smem, st>>>(*p);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
+    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
+    static const bool one_wg = getenv("MOP_EW_BWD_1WG") != nullptr;   // A/B switch: single-warpgroup backward
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MOP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b2));
+      configured_dev = dev;
+    }
+    const int G = p->B * p->H, sms = sm_count();
+    const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
+    if (bwd && !one_wg) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
+    else if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
+    else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
+    MOP_CHECK_CUDA(cudaGetLastError());
+    p->impl_used = MOP_IMPL_TCGEN05;
+    return MOP_OK;
+  }
+  ew::Layout L = edgewise_layout(p, bwd ? 1 : 0);
+  const int grid = edgewise_grid(p);
+  const size_t need = (size_t)grid * L.total * sizeof(float);
+  MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
+  float* ws = reinterpret_cast<float*>(p->workspace);
+  if (p->dtype == MOP_F32) {
+    if (bwd) ew::bwd_kernel<float><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+    else ew::fwd_kernel<float><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+  } else {
+    if (bwd) ew::bwd_kernel<__nv_bfloat16><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+    else ew::fwd_kernel<__nv_bfloat16><<<grid, simt::kThreads, 0, st>>>(*p, L, ws);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  p->impl_used = MOP_IMPL_SIMT;
+  return MOP_OK;
+}
+
+int mop_edgewise_fwd(MopEdgewiseParams* p, void* stream) { return edgewise_launch(p, stream, false); }
+int mop_edgewise_bwd(MopEdgewiseParams* p, void* stream) { return edgewise_launch(p, stream, true); }
+
+}  // extern "C"

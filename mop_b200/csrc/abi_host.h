@@ -1,0 +1,16 @@
+// Host-side helpers shared by the translation units of libmop_b200.so.
+#pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint)
+
+#include "common.cuh"
+
+namespace mop {
+// bf16 tensor [B][N][H][dk] with element strides (sb, sn, sh), last dimension contiguous, described to the TMA unit as
+// (column, token, head, batch); box = 64 columns x box_rows tokens, 128-byte swizzle (tc_common.cuh: tma_load_tile_sw)
+int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows);
+
+template <typename K> static int allow_smem(K kernel, size_t bytes) {
+  MOP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MOP_OK;
+}
+}  // namespace mop

@@ -274,7 +274,7 @@ __device__ void forward_maps(Ctx& c) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads, 2) fwd_kernel(MopEdgewiseParams p, Layout L, float* ws_base) {
+static __global__ void __launch_bounds__(simt::kThreads, 2) fwd_kernel(MopEdgewiseParams p, Layout L, float* ws_base) {
   __shared__ simt::GemmSmem gs;
   __shared__ float red[32];
   const int G = p.B * p.H;
@@ -508,7 +508,7 @@ __device__ __forceinline__ float dfeat_at(const Ctx& c, int ch, int i, int j) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewiseParams p, Layout L, float* ws_base) {
+static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewiseParams p, Layout L, float* ws_base) {
   __shared__ simt::GemmSmem gs;
   __shared__ float red[32];
   const int G = p.B * p.H;

@@ -202,7 +202,7 @@ __device__ __forceinline__ float cta_sum(float v, float* scratch4) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseParams p) {
+static __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEdgewiseParams p) {
   using SL = Slots<BWD>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem<BWD>& sm = *reinterpret_cast<Smem<BWD>*>(smem_raw);

@@ -32,7 +32,7 @@ struct __align__(1024) SmemBwd2 {
   SmemBwd2Extra x;
 };
 
-__global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams p) {
+static __global__ void __launch_bounds__(256, 1) edgewise_bwd2_kernel(MopEdgewiseParams p) {
   using SB = Slots<true>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemBwd2& sm = *reinterpret_cast<SmemBwd2*>(smem_raw);

@@ -113,7 +113,7 @@ __device__ __forceinline__ void pack16(const float* v, float sc, uint4& lo, uint
 }
 
 
-__global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams p) {
+static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;

@@ -91,7 +91,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams p) {
+static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewiseParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;

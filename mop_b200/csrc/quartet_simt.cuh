@@ -57,7 +57,7 @@ __device__ __forceinline__ size_t at(const MopQuartetParams& p, int b, int t, in
 
 // grid: B*H*nm.  kc = k - mean(k), qf = q (fp32 copies), gram = kc^T kc.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) prep_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) prep_kernel(MopQuartetParams p, Ws w, float* ws) {
   __shared__ simt::GemmSmem gs;
   __shared__ float kbar[kMaxDk];
   const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, Tn = p.T;
@@ -137,7 +137,7 @@ __device__ __forceinline__ float mix_score(const MopQuartetParams& p, const Mix&
 
 // grid: (b,h,q-block)
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetParams p, Ws w, float* ws) {
   extern __shared__ __align__(16) unsigned char raw[];
   Tiles t = carve(raw, p.dk);
   const int dk = p.dk, Tn = p.T, nqb = w.nqb;
@@ -289,7 +289,7 @@ __device__ inline void load_q_side(const MopQuartetParams& p, const Tiles& t, co
 
 // grid: (b,h,q-block).  Owns dq, dq2, the row coefficients g and the scalar partials of its rows.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) bwd_dq_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) bwd_dq_kernel(MopQuartetParams p, Ws w, float* ws) {
   extern __shared__ __align__(16) unsigned char raw[];
   __shared__ float red[32];
   Tiles t = carve(raw, p.dk);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(simt::kThreads) bwd_dq_kernel(MopQuartetParams
 }
 
 // grid: B*H*nm.  mmat = sum_i g_i q_i q_i^T
-__global__ void __launch_bounds__(simt::kThreads) gmat_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) gmat_kernel(MopQuartetParams p, Ws w, float* ws) {
   __shared__ simt::GemmSmem gs;
   const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, dk = p.dk, Tn = p.T;
   const size_t BH = (size_t)p.B * p.H;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(simt::kThreads) gmat_kernel(MopQuartetParams p
 
 // grid: (b,h,k-block).  Owns dv and the centred-key gradients dkc of its keys.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopQuartetParams p, Ws w, float* ws) {
   extern __shared__ __align__(16) unsigned char raw[];
   Tiles t = carve(raw, p.dk);
   const int dk = p.dk, Tn = p.T, nkb = w.nqb;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopQuartetPara
 
 // grid: B*H*nm.  dk = dkc - mean_j dkc ; map 0 of each (b,h) also reduces the scalar partials.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) finish_kernel(MopQuartetParams p, Ws w, float* ws) {
+static __global__ void __launch_bounds__(simt::kThreads) finish_kernel(MopQuartetParams p, Ws w, float* ws) {
   __shared__ float mean[kMaxDk];
   const int nm = w.nm, bh = blockIdx.x / nm, map = blockIdx.x % nm, b = bh / p.H, h = bh % p.H, dk = p.dk, Tn = p.T;
   const size_t BH = (size_t)p.B * p.H;

@@ -168,7 +168,7 @@ __device__ inline void gram_readout(uint32_t tb, float* G) {
 //                      the tensor core -> atomics into w.gacc
 //   acc_to_tiles_kernel  grid B*H*nm: w.gacc -> bf16 hi / lo tile images
 constexpr int kPrepRows = 256;
-__global__ void __launch_bounds__(256) prep_sum_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+static __global__ void __launch_bounds__(256) prep_sum_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ float part[32][64];
   const int nm = w.nm, T = p.T, ngr = (T + kPrepRows - 1) / kPrepRows, dk = p.dk, tid = threadIdx.x;
   const int grp = blockIdx.x % ngr, bm = blockIdx.x / ngr, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) prep_sum_kernel(MopQuartetParams p, Ws w,
   }
 }
 
-__global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+static __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ __align__(128) unsigned char tiles[kGramBufs][kT64];
   __shared__ __align__(16) float G[64 * 64];
   __shared__ float kbar[64];
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) prep_kernel(MopQuartetParams p, Ws w, uns
 }
 
 // fp32 64x64 accumulators (byte offset acc_off) -> bf16 hi / lo tile images (byte offset tiles_off); blockIdx.x = map * BH + bh
-__global__ void __launch_bounds__(256) acc_to_tiles_kernel(unsigned char* ws, size_t acc_off, size_t tiles_off) {
+static __global__ void __launch_bounds__(256) acc_to_tiles_kernel(unsigned char* ws, size_t acc_off, size_t tiles_off) {
   __shared__ __align__(16) float G[64 * 64];
   const float* acc = reinterpret_cast<const float*>(ws + acc_off) + (size_t)blockIdx.x * 64 * 64;
   for (int i = threadIdx.x; i < 64 * 64 / 4; i += 256) reinterpret_cast<float4*>(G)[i] = reinterpret_cast<const float4*>(acc)[i];
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) acc_to_tiles_kernel(unsigned char* ws, si
 // One CTA per (b, h, map): used when B*H*nm alone fills the GPU (fewer launches, no atomics).
 // grid: B*H*nm, 256 threads.  kbar, kc = bf16(k - kbar) (written to the workspace and staged for the MMA),
 // G = Kc^T Kc from that rounded kc -> bf16 hi / lo tile images.
-__global__ void __launch_bounds__(256) prep_fused_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+static __global__ void __launch_bounds__(256) prep_fused_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ __align__(128) unsigned char tiles[kGramBufs][kT64];
   __shared__ __align__(16) float G[64 * 64];
   __shared__ float part[32][64];
@@ -413,7 +413,7 @@ struct __align__(128) SmemF {
 #endif
 constexpr float kLazy = MOP_QLAZY;   // the running maximum is raised only when a tile exceeds it by 2^kLazy
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                      const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmKc,
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -729,7 +729,7 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
 // buffer, so they run during tile t's element math; dQ += W K of tile t (two lanes) runs during tile t+1's element math (W has one
 // buffer per tile parity); one lane refills the three-stage key / value ring once dQ(t-1) is done.
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
                                                         const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w
 // grid: B*H*nm, 256 threads.  M = sum_i g_i q_i q_i^T = (g q)^T q on the tensor core, g q split into bf16 hi + lo
 // groups > 1: the queries of one (b, h, map) are split over `groups` CTAs of `cpg` 64-row chunks each; partial sums go to
 // w.macc with atomics and acc_to_tiles_kernel writes the tile images (used when B*H*nm alone does not fill the GPU)
-__global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws, int groups, int cpg) {
+static __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws w, unsigned char* ws, int groups, int cpg) {
   __shared__ __align__(128) unsigned char tiles[1][3][kT64];   // [g q hi | g q lo | q] (single buffer: several CTAs share an SM)
   __shared__ GramPipe gp;
   float* G = reinterpret_cast<float*>(&tiles[0][0][0]);        // 16 KB: read out once every MMA has completed
@@ -1054,7 +1054,7 @@ struct __align__(128) SmemK {
 // t (ahead of the output products in the tensor pipe's queue); the output products of tile t run during tile t+1 (P^T / W^T have
 // one buffer per tile parity) and a lane refills the three-stage query ring once the outputs of tile t-1 are done.
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
                                                           const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1288,7 +1288,7 @@ __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws
 
 // grid: (B*H*nm) * ceil(T/64), 256 threads: dk = dkc - mean_j dkc for 64 keys, the column sums come from bwd_dkdv (w.dksum);
 // the first chunk of map 0 also folds the scalar partials of the query blocks
-__global__ void __launch_bounds__(256) finish_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
+static __global__ void __launch_bounds__(256) finish_kernel(MopQuartetParams p, Ws w, unsigned char* ws) {
   __shared__ float mean[64];
   const int nm = w.nm, T = p.T, nch = (T + 63) >> 6, dk = p.dk, tid = threadIdx.x;
   const int chunk = blockIdx.x % nch, bm = blockIdx.x / nch, bh = bm / nm, map = bm % nm, b = bh / p.H, h = bh % p.H;

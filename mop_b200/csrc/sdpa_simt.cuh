@@ -63,7 +63,7 @@ __device__ __forceinline__ float apply_masks(const MopSdpaParams& p, int b, int 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopSdpaParams p) {
+static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopSdpaParams p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Tiles t = carve(raw, p.dk);
   const int dk = p.dk;
@@ -171,7 +171,7 @@ __device__ inline void load_row_stats(const MopSdpaParams& p, const Tiles& t, in
 
 // grid: (b,h,k-block).  Owns dK, dV of its keys.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopSdpaParams p, float* pbuf_base) {
+static __global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopSdpaParams p, float* pbuf_base) {
   extern __shared__ __align__(16) unsigned char raw[];
   Tiles t = carve(raw, p.dk);
   const int dk = p.dk;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(simt::kThreads) bwd_dkdv_kernel(MopSdpaParams 
 
 // grid: (b,h,q-block).  Owns dQ of its queries.
 template <typename T>
-__global__ void __launch_bounds__(simt::kThreads) bwd_dq_kernel(MopSdpaParams p, float* pbuf_base) {
+static __global__ void __launch_bounds__(simt::kThreads) bwd_dq_kernel(MopSdpaParams p, float* pbuf_base) {
   extern __shared__ __align__(16) unsigned char raw[];
   Tiles t = carve(raw, p.dk);
   const int dk = p.dk;

@@ -69,7 +69,7 @@ struct __align__(128) SmemF {
 // raised when a tile exceeds it by more than 2^8 (exponentials stay <= 256; fp32 sums and bf16 products keep their relative
 // precision), which removes nearly all rescales of O.
 template <bool EXTRA>
-__global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
@@ -308,7 +308,7 @@ struct __align__(128) SmemQ {
 
 // grid: B*H*ceil(Nq/128), 256 threads; TMEM 256 columns (S | dP | dQ): two CTAs per SM
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* delta, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* delta, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
                                                         const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -454,7 +454,7 @@ struct __align__(128) SmemK {
 // grid: B*H*ceil(Nk/128), 256 threads (thread per key row; two warpgroups split the 64 query columns); TMEM 256 columns
 // (S^T | dP^T | dV | dK): two CTAs per SM
 template <bool EXTRA>
-__global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const float* delta, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const float* delta, const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
                                                           const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];

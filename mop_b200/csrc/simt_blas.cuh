@@ -23,7 +23,7 @@ struct GemmSmem {
 
 // C[M x Nc] (ldc) = (acc ? C : 0) + alpha * nscale[n] * sum_k A(m,k) * kscale[k] * B(k,n)
 //   A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn];  kscale / nscale may be null.
-__device__ __noinline__ void gemm(float* C, int ldc, const float* A, int sam, int sak, const float* B, int sbk,
+static __device__ __noinline__ void gemm(float* C, int ldc, const float* A, int sam, int sak, const float* B, int sbk,
                                   int sbn, int M, int Nc, int K, const float* kscale, const float* nscale,
                                   float alpha, bool acc, GemmSmem& sm) {
   const int tid = threadIdx.x;

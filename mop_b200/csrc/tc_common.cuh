@@ -39,7 +39,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(a, parity)) {
     if (clock64() - t0 > 4000000000LL) {

@@ -7,7 +7,7 @@
 namespace mop {
 namespace tc {
 
-__global__ void __launch_bounds__(128, 1) selftest_kernel(const float* A, const float* B, float* D, float* D2, int a_mn,
+static __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* A, const float* B, float* D, float* D2, int a_mn,
                                                           int b_mn, int lane_off, int col_off) {
   __shared__ __align__(128) unsigned char tA[64 * 64 * 2];
   __shared__ __align__(128) unsigned char tB[64 * 64 * 2];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* A, const 
 //   b_mn = 0: B is [Nn x K] row-major (tile rows = N index, K-major operand)
 //   b_mn = 1: B is [Kb x Nn] row-major (tile rows = K index, MN-major operand); the GEMM uses rows
 //             [b_k0, b_k0 + K) of it.
-__global__ void __launch_bounds__(256, 1) selftest128_kernel(const float* A, const float* B, float* D, int Ma, int Nn, int K,
+static __global__ void __launch_bounds__(256, 1) selftest128_kernel(const float* A, const float* B, float* D, int Ma, int Nn, int K,
                                                              int b_mn, int Ra, int Rb, int Kb, int b_k0) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256, 1) selftest128_kernel(const float* A, con
 
 // Bring-up of the TMA tile load: rows [row0, row0 + R) of head `head`, batch `batch` of a [B][N][H][dk] bf16 tensor -> 128-byte
 // swizzled tile in shared memory -> copied out verbatim (R * 128 bytes) for comparison on the host.
-__global__ void __launch_bounds__(128, 1) selftest_tma_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int R, int row0,
+static __global__ void __launch_bounds__(128, 1) selftest_tma_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int R, int row0,
                                                               int head, int batch) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
