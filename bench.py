@@ -105,22 +105,44 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's eager path, on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_port_throughput(steps: int, warmup: int, sample_batch: int):
+def _cpu_step_fn(sample_batch: int):
+    """One eager fp32 fwd + CE + bwd + AdamW step of the bench model on the host cores.  Returns (run, kind).
+
+    kind "reference": the UNMODIFIED reference modules from baseline/_ref (baseline/ref_models.py); kind "port": the
+    oracle restatement (oracle/vit_edgewise_ref.py) when the reference package is not staged on this machine."""
+    import mop_b200
+    torch.manual_seed(0)
+    x = torch.randn(sample_batch, 3, IMG, IMG)
+    y = torch.randint(0, MODEL["n_classes"], (sample_batch,))
+    try:
+        from baseline.ref_models import reference_vit_edgewise
+        model = reference_vit_edgewise(num_tokens=NTOK, patch=PATCH, **MODEL)
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
+
+        def run():
+            opt.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(model(x), y)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        return run, "reference"
+    except ImportError:
+        pass
     from oracle.edgewise import EdgewiseConfig
     from oracle.vit_edgewise_ref import train_step_cpu
-    import mop_b200
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    kw = {k: v for k, v in MODEL.items()}
-    skeleton = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **kw)  # parameters only (same init as the GPU arm)
+    skeleton = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **MODEL)  # parameters only (same init as the GPU arm)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in skeleton.state_dict().items()}
     cfg = EdgewiseConfig(dim=MODEL["dim"], heads=MODEL["heads"], n_views=MODEL["n_views"], share_qkv=True, use_k3=True,
                          gate_mode="lowrank", gate_rank=MODEL["gate_rank"], gate_init="mix5")
     opt = torch.optim.AdamW([p for p in sd.values() if p.requires_grad], lr=1e-3, weight_decay=0.05)
-    x = torch.randn(sample_batch, 3, IMG, IMG)
-    y = torch.randint(0, MODEL["n_classes"], (sample_batch,))
-    run = lambda: train_step_cpu(sd, cfg, x, y, depth=MODEL["depth"], patch=PATCH, drop_path_rate=MODEL["drop_path"], opt=opt)
+    return (lambda: train_step_cpu(sd, cfg, x, y, depth=MODEL["depth"], patch=PATCH, drop_path_rate=MODEL["drop_path"], opt=opt)), "port"
+
+
+def cpu_throughput(steps: int, warmup: int, sample_batch: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run, kind = _cpu_step_fn(sample_batch)
     for _ in range(warmup):
         run()
     times = []
@@ -128,23 +150,24 @@ def cpu_port_throughput(steps: int, warmup: int, sample_batch: int):
         t0 = time.perf_counter()
         run()
         times.append(time.perf_counter() - t0)
-    best = min(times)
-    return dict(value=sample_batch / best, unit="images/s", cores=cores, kind="port",
-                sample=f"{steps} eager fp32 fwd+bwd+AdamW steps of the same model at batch {sample_batch} (of {BATCH}), best step, "
-                       f"torch CPU {cores} threads"), sum(times) / len(times)
+    mean_s = sum(times) / len(times)
+    what = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port of the reference eager path"
+    return dict(value=sample_batch / mean_s, unit="images/s", cores=cores, kind=kind,
+                sample=f"{steps} eager fp32 fwd+bwd+AdamW steps of the same model at batch {sample_batch} (of {BATCH}) after {warmup} "
+                       f"warm-up, mean step, {what}, torch CPU {cores} threads"), mean_s
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path at the bench config (batch 256), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 32
-    steps = max(1, min(args.steps, 5))
-    cb, mean_s = cpu_port_throughput(steps, min(args.warmup, 1), sample)
+    cb, mean_s = cpu_throughput(args.steps, args.warmup, BATCH)
     line = {"impl": "reference", "metric": "vit_mop_train_images_per_sec", "value": cb["value"], "unit": "images/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": mean_s * 1e3 * BATCH / sample,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU port of the reference eager path (oracle/), host cores only"},
+            "config": {"workload": WORKLOAD, "global_batch": BATCH,
+                       "note": "reference eager path on the host cores only (kind: see cpu_baseline); no GPU work"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -311,7 +334,7 @@ def run_ours(args):
         attn_ms = MODEL["depth"] * (kern_ms.get("edgewise_fwd", 0) + kern_ms.get("edgewise_bwd", 0))
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_port_throughput(steps=2, warmup=1, sample_batch=32)
+            cb, _ = cpu_throughput(steps=4, warmup=1, sample_batch=64)
         line = {
             "metric": "vit_mop_train_images_per_sec", "value": world * BATCH / (step_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,

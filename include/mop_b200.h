@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 2
+#define MOP_ABI_VERSION 3
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -163,6 +163,9 @@ typedef struct MopQuartetParams {
   const float* add_mask; int64_t am_sb, am_sh, am_sq, am_sk; /* optional additive mask :115-116 */
   void* y;              /* [B,T,H,dk] */
   float* stats;         /* [B,H,T,3]: sigma1, sigma2, lse  (fwd out, bwd in) */
+  float* y_f32;         /* [B,T,H,dk] fp32, optional (fwd out, bwd in): the output before rounding to `dtype`.  When set, the
+                           backward forms delta = dO . y from it; the mixture / quartet_scale gradients are heavily
+                           cancelling sums whose accuracy is bounded by that of delta */
   /* backward */
   const void* dy;
   void *dq, *dk_, *dv, *dq2, *dk2;

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 2
+MOP_ABI_VERSION = 3
 MOP_F32, MOP_BF16 = 0, 1
 MOP_GATE_DENSE, MOP_GATE_LOWRANK = 0, 1
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
@@ -61,7 +61,7 @@ class QuartetParams(C.Structure):
         ("q", vp), ("k", vp), ("v", vp), ("q2", vp), ("k2", vp),
         ("mixture", vp), ("quartet_scale", vp),
         ("add_mask", vp), ("am_sb", i64), ("am_sh", i64), ("am_sq", i64), ("am_sk", i64),
-        ("y", vp), ("stats", vp),
+        ("y", vp), ("stats", vp), ("y_f32", vp),
         ("dy", vp), ("dq", vp), ("dk_", vp), ("dv", vp), ("dq2", vp), ("dk2", vp),
         ("dscalar_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),

@@ -110,21 +110,18 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
     return MOP_OK;
   }
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b = sizeof(ewtc::Smem<true>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
-    static const bool one_wg = getenv("MOP_EW_BWD_1WG") != nullptr;   // A/B switch: single-warpgroup backward
+    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOP_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b2));
       configured_dev = dev;
     }
     const int G = p->B * p->H, sms = sm_count();
     const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
-    if (bwd && !one_wg) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
-    else if (bwd) ewtc::edgewise_kernel<true><<<grid, 128, smem_b, st>>>(*p);
+    if (bwd) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
     else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;

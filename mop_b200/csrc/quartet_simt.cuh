@@ -217,6 +217,7 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetPa
   for (int idx = threadIdx.x; idx < rows * dk; idx += simt::kThreads) {
     int r = idx / dk, d = idx % dk;
     y[at(p, b, q0 + r, h) + d] = from_f32<T>(o[idx] / t.l[r]);
+    if (p.y_f32) p.y_f32[at(p, b, q0 + r, h) + d] = o[idx] / t.l[r];
   }
   if (p.stats)
     for (int r = threadIdx.x; r < rows; r += simt::kThreads) {
@@ -277,7 +278,7 @@ __device__ inline void load_q_side(const MopQuartetParams& p, const Tiles& t, co
   for (int r = warp; r < TQ; r += nw) {
     float s = 0.f;
     if (r < rows)
-      for (int d = lane; d < dk; d += 32) s = fmaf(t.dy[r * dk + d], to_f32<T>(y[at(p, b, q0 + r, h) + d]), s);
+      for (int d = lane; d < dk; d += 32) s = fmaf(t.dy[r * dk + d], p.y_f32 ? p.y_f32[at(p, b, q0 + r, h) + d] : to_f32<T>(y[at(p, b, q0 + r, h) + d]), s);
     s = warp_sum(s);
     if (lane == 0) {
       const float* st = p.stats + (((size_t)b * p.H + h) * Tn + min(q0 + r, Tn - 1)) * 3;

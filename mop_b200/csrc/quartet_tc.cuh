@@ -665,6 +665,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
     tc_fence_after();
     const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
+    float* y32 = p.y_f32 ? p.y_f32 + at(p, b, row_ok ? gi : 0, h) : nullptr;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float o[16];
@@ -675,6 +676,11 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
       if (row_ok) {
         if (16 * c < dk) *reinterpret_cast<uint4*>(y + 16 * c) = pack8(o);
         if (16 * c + 8 < dk) *reinterpret_cast<uint4*>(y + 16 * c + 8) = pack8(o + 8);
+        if (y32) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            if (16 * c + e < dk) *reinterpret_cast<float4*>(y32 + 16 * c + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+        }
       }
     }
     if (p.stats && row_ok) {
@@ -777,9 +783,15 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   if (row_ok) {
     const __nv_bfloat16* yr = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, gi, h);
     const __nv_bfloat16* dr = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, gi, h);
+    const float* y32 = p.y_f32 ? p.y_f32 + at(p, b, gi, h) : nullptr;
     for (int d0 = 0; d0 < dk; d0 += 8) {
       float a[8], c[8];
-      unpack8(*reinterpret_cast<const uint4*>(yr + d0), a);
+      if (y32) {
+        const float4 u0 = *reinterpret_cast<const float4*>(y32 + d0), u1 = *reinterpret_cast<const float4*>(y32 + d0 + 4);
+        a[0] = u0.x; a[1] = u0.y; a[2] = u0.z; a[3] = u0.w; a[4] = u1.x; a[5] = u1.y; a[6] = u1.z; a[7] = u1.w;
+      } else {
+        unpack8(*reinterpret_cast<const uint4*>(yr + d0), a);
+      }
       unpack8(*reinterpret_cast<const uint4*>(dr + d0), c);
 #pragma unroll
       for (int e = 0; e < 8; ++e) dlt = fmaf(a[e], c[e], dlt);

@@ -42,6 +42,21 @@ def _compat(cls):
     return _Compat
 
 
+_ORIGINALS: Dict[tuple, type] = {}
+
+
+def unpatch_reference() -> int:
+    """Undo patch_reference(): restore the reference's own classes.  Returns how many names were restored."""
+    n = 0
+    for (modname, name), cls in list(_ORIGINALS.items()):
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, name, cls)
+            n += 1
+    _ORIGINALS.clear()
+    return n
+
+
 def patch_reference(verbose: bool = False) -> Dict[str, List[str]]:
     """Rebind the attention classes in every loaded `mop.*` module and experiment script.  Returns what was replaced."""
     done: Dict[str, List[str]] = {}
@@ -58,6 +73,7 @@ def patch_reference(verbose: bool = False) -> Dict[str, List[str]]:
                 continue
             if is_exp and name in ("EdgewiseMSA", "EdgewiseGateHead"):
                 repl = _compat(repl)
+            _ORIGINALS[(modname, name)] = cur
             setattr(mod, name, repl)
             done.setdefault(modname, []).append(name)
     if verbose:

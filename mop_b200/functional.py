@@ -365,10 +365,12 @@ class _Quartet(torch.autograd.Function):
         B, T, H, dk = q.shape
         y = torch.empty_like(q)
         stats = torch.empty(B, H, T, 3, dtype=torch.float32, device=q.device)
+        # bf16 storage: the backward forms delta = dO . y from an fp32 copy of y (the scalar gradients cancel heavily)
+        y32 = torch.empty(B, T, H, dk, dtype=torch.float32, device=q.device) if (q.dtype != torch.float32 and quart and any(ctx.needs_input_grad)) else None
         with torch.cuda.device(q.device):
             p = _lib.new_params(_lib.QuartetParams)
             _fill_quartet(p, q, k, v, q2, k2, mix32, gam32, add_mask, cfg)
-            p.y, p.stats = _ptr(y), _ptr(stats)
+            p.y, p.stats, p.y_f32 = _ptr(y), _ptr(stats), _ptr(y32)
             nbytes = lib.mop_quartet_workspace_bytes(C.byref(p), 0)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=q.device)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
@@ -379,6 +381,9 @@ class _Quartet(torch.autograd.Function):
         ctx.cfg, ctx.quart, ctx.has_mask = cfg, quart, add_mask is not None
         ctx.scalar_dtypes = (None, None) if not quart else (mixture.dtype, gamma.dtype)
         saved = [q, k, v, y, stats] + ([q2, k2, mix32, gam32] if quart else []) + ([add_mask] if add_mask is not None else [])
+        ctx.has_y32 = y32 is not None
+        if y32 is not None:
+            saved.append(y32)
         ctx.save_for_backward(*saved)
         return y
 
@@ -386,6 +391,7 @@ class _Quartet(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.load()
         saved = list(ctx.saved_tensors)
+        y32 = saved.pop() if ctx.has_y32 else None
         q, k, v, y, stats = saved[:5]
         rest = saved[5:]
         q2 = k2 = mix32 = gam32 = add_mask = None
@@ -405,7 +411,7 @@ class _Quartet(torch.autograd.Function):
         with torch.cuda.device(dev):
             p = _lib.new_params(_lib.QuartetParams)
             _fill_quartet(p, q, k, v, q2, k2, mix32, gam32, add_mask, ctx.cfg)
-            p.y, p.stats, p.dy = _ptr(y), _ptr(stats), _ptr(dy_c)
+            p.y, p.stats, p.dy, p.y_f32 = _ptr(y), _ptr(stats), _ptr(dy_c), _ptr(y32)
             p.dq, p.dk_, p.dv, p.dq2, p.dk2, p.dscalar_part = _ptr(dq), _ptr(dk_), _ptr(dv), _ptr(dq2), _ptr(dk2), _ptr(dsc)
             nbytes = lib.mop_quartet_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)

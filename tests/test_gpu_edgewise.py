@@ -273,3 +273,57 @@ def test_tcgen05_large_backward_vs_oracle_and_simt(B, H, N, dk, V, r):
         worst[k] = (rel_to_max(g_tc[k].reshape(rv.shape), rv), rel_to_max(g_simt[k].reshape(rv.shape), rv))
     bad = {k: v for k, v in worst.items() if not (v[0] <= BF16_TOL)}
     assert not bad, f"tcgen05 grads off (tc_err, simt_err): {worst}"
+
+
+# ---- persistent loop of the N=64 kernels: more (batch, head) problems than CTAs, incl. the exact bench shape ------------------
+@pytest.mark.parametrize("B,H,dk,V,r", [(150, 4, 56, 5, 4), (256, 4, 56, 5, 4)])
+def test_tcgen05_n64_many_problems_vs_simt_and_oracle(B, H, dk, V, r):
+    """B*H >= 600 problems on <= 296 CTAs: TMEM columns, mbarrier phases and shared-memory slots are reused across problems.
+    Every output / gradient against the fp32-math SIMT kernel on all problems, and against the fp64 oracle on 2 batch entries
+    (8 (b,h) slices) picked from the middle and the end of the persistent loop."""
+    from mop_b200 import functional as MF
+    N = 64
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, True, "lowrank", False, r, seed=B + dk)
+    qkv, dy = bf16_round(qkv), bf16_round(dy)
+    y_tc, g_tc = _run_gpu(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5, False, torch.bfloat16, impl="tcgen05")
+    assert MF.last_impl["edgewise_fwd"] == "tcgen05" and MF.last_impl["edgewise_bwd"] == "tcgen05"
+    y_s, g_s = _run_gpu(qkv, scales, head, logit, dy, V, "lowrank", r, 0.5, False, torch.bfloat16, impl="simt")
+    torch.cuda.synchronize()
+    assert torch.isfinite(y_tc.float()).all()
+    assert rel_to_max(y_tc, y_s) <= BF16_TOL
+    worst = {k: rel_to_max(g_tc[k], g_s[k]) for k in g_s}
+    assert all(v <= BF16_TOL for v in worst.values()), worst
+    # per-problem check of y / dqkv: the worst single (b,h) slice, not only the global maximum
+    e_y = ((y_tc.double() - y_s.double()).abs().amax(dim=(1, 3)) / y_s.double().abs().amax(dim=(1, 3)).clamp_min(1e-30)).max().item()
+    assert e_y <= 2 * BF16_TOL, e_y
+    pick = [B // 2, B - 1]
+    sub = qkv[pick], [s for s in scales], head, logit, dy[pick]
+    y_ref, g_ref = _oracle(*sub, V, "lowrank", r, 0.5)
+    assert rel_to_max(y_tc[pick], y_ref) <= BF16_TOL
+    assert rel_to_max(g_tc["qkv"][pick], g_ref["qkv"]) <= BF16_TOL
+
+
+def test_core_dense_k3_bf16_vs_oracle():
+    """Dense gate head with the 3x3 stage on bf16 storage (the case CORE_CASES[:5] leaves out)."""
+    B, H, N, dk, V, shared, mode, k3, r = 2, 2, 40, 16, 5, True, "dense", True, 4
+    qkv, scales, head, logit, dy = _rand_problem(B, H, N, dk, V, shared, mode, k3, r, seed=4242)
+    qkv, dy = bf16_round(qkv), bf16_round(dy)
+    y_ref, g_ref = _oracle(qkv, scales, head, logit, dy, V, mode, r, 0.5)
+    y, g = _run_gpu(qkv, scales, head, logit, dy, V, mode, r, 0.5, k3, torch.bfloat16)
+    assert rel_to_max(y, y_ref) <= BF16_TOL
+    for k, ref in g_ref.items():
+        assert rel_to_max(g[k].reshape(ref.shape), ref) <= BF16_TOL, k
+
+
+def test_unified_msa_mode_e_matches_edgewise_module():
+    """UnifiedMSA("E") forwards its kwargs to EdgewiseMSA (reference :609-622): same weights -> same output, fp32 mode."""
+    from mop_b200 import EdgewiseMSA, UnifiedMSA
+    kw = dict(n_views=3, share_qkv=True, gate_mode="lowrank", gate_rank=2, gate_init="or", beta_not=0.3, use_k3=True)
+    torch.manual_seed(11); u = UnifiedMSA("E", 48, heads=3, **kw).cuda()
+    torch.manual_seed(11); e = EdgewiseMSA(48, heads=3, **kw).cuda()
+    assert list(u.impl.state_dict()) == list(e.state_dict())
+    x = torch.randn(2, 20, 48, device="cuda")
+    assert torch.equal(u(x), e(x))
+    for mode in ("A", "B"):
+        b = UnifiedMSA(mode, 48, heads=3).cuda()
+        assert b(x).shape == x.shape

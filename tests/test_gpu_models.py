@@ -1,0 +1,132 @@
+"""Model-level parity on the GPU: multi-layer ViTEdgewise against the oracle port, and reference models with their attention
+classes swapped in place (mop_b200.dropin) against the same unpatched reference models on the CPU (needs baseline/_ref)."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import max_abs, rel_to_max
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_layer_vit_edgewise_logits_and_grads_vs_oracle():
+    import mop_b200
+    from oracle.edgewise import EdgewiseConfig
+    from oracle.vit_edgewise_ref import vit_edgewise_forward
+    kw = dict(dim=64, depth=2, heads=2, n_classes=10, mlp_ratio=2.0, n_views=3, share_qkv=True, use_k3=True, gate_mode="lowrank",
+              gate_rank=4, gate_init="mix5", drop_path=0.0)
+    torch.manual_seed(0)
+    model = mop_b200.ViTEdgewise(num_tokens=64, patch=4, compat_experiments_init=False, **kw)
+    sd = {k: v.detach().double().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    cfg = EdgewiseConfig(dim=64, heads=2, n_views=3, share_qkv=True, use_k3=True, gate_mode="lowrank", gate_rank=4, gate_init="mix5")
+    x = torch.randn(4, 3, 32, 32)
+    lab = torch.randint(0, 10, (4,))
+    logits_ref = vit_edgewise_forward(x.double(), sd, cfg, depth=2, patch=4)
+    F.cross_entropy(logits_ref, lab).backward()
+    model = model.cuda()
+    logits = model(x.cuda())
+    F.cross_entropy(logits, lab.cuda()).backward()
+    assert max_abs(logits, logits_ref) <= 2e-5
+    for k, p in model.named_parameters():
+        ref = sd[k].grad
+        assert max_abs(p.grad, ref) <= 5e-5 * max(1.0, ref.abs().max().item()), k
+
+
+# ---- the unmodified reference package (baseline/_ref), patched in place ---------------------------------------------------------
+def _ref():
+    sys.path.insert(0, ROOT)
+    from baseline import ref_models
+    try:
+        return ref_models.import_reference()
+    except ImportError as e:
+        pytest.skip(f"reference package not staged: {e}")
+
+
+@pytest.fixture()
+def patched():
+    mods = _ref()
+    import mop_b200.dropin as dropin
+    yield mods, dropin
+    dropin.unpatch_reference()
+
+
+def _twin(build, patched):
+    """Build the reference model unpatched (CPU, fp32) and again after patch_reference() with the same weights (GPU)."""
+    mods, dropin = patched
+    torch.manual_seed(0)
+    ref_model = build()
+    done = dropin.patch_reference()
+    assert done, "nothing was patched"
+    ours = build()
+    ours.load_state_dict(ref_model.state_dict(), strict=True)
+    return ref_model.eval(), ours.cuda().eval()
+
+
+def _grads_close(ref_model, ours, tol):
+    bad = {}
+    for (k, p), (_, q) in zip(ref_model.named_parameters(), ours.named_parameters()):
+        if p.grad is None:
+            continue
+        e = max_abs(q.grad, p.grad) / max(1.0, p.grad.abs().max().item())
+        if e > tol:
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_patched_reference_vit_baseline_and_vit_mop(patched):
+    """Models A and B of the reference (components.MSA inside ViTEncoder blocks) with MSA swapped for the fused kernel."""
+    from mop.models import ViT_Baseline, ViT_MoP
+    for build in (lambda: ViT_Baseline(dim=64, depth=2, heads=2, n_classes=10),
+                  lambda: ViT_MoP(dim=60, depth=2, heads=2, n_classes=10, n_views=3, n_kernels=2)):
+        patched[1].unpatch_reference()
+        ref_model, ours = _twin(build, patched)
+        assert any(type(m).__module__.startswith("mop_b200") for m in ours.modules())
+        assert not any(type(m).__module__.startswith("mop_b200") for m in ref_model.modules())
+        x = torch.randn(3, 3, 32, 32)
+        y_ref = ref_model(x)
+        y = ours(x.cuda())
+        assert max_abs(y, y_ref) <= 2e-5
+        y_ref.square().sum().backward(); y.square().sum().backward()
+        _grads_close(ref_model, ours, 5e-5)
+
+
+def test_patched_reference_gpt_quartet(patched):
+    """create_gpt_quartet with the reference's own default config fields except dropout (eval-mode comparison)."""
+    from mop.models import create_gpt_quartet
+    from mop.models.quartet_attn_patch import TransformerConfig
+    cfg = TransformerConfig(n_layer=2, n_head=2, n_embd=32, dropout=0.1, block_size=48)
+    ref_model, ours = _twin(lambda: create_gpt_quartet(97, cfg), patched)
+    ids = torch.randint(0, 97, (2, 40))
+    out_ref = ref_model(ids)
+    out = ours(ids.cuda())
+    lr, lo = (o[0] if isinstance(o, (tuple, list)) else o for o in (out_ref, out))
+    assert max_abs(lo, lr) <= 5e-5
+    lr.square().mean().backward(); lo.square().mean().backward()
+    _grads_close(ref_model, ours, 1e-4)
+
+
+def test_patched_reference_whisper(patched):
+    from mop.models import WhisperConfig, create_whisper_mop
+    cfg = WhisperConfig(n_mels=16, n_audio_ctx=64, vocab_size=50, n_text_ctx=16, n_embd=32, n_head=2, n_layer_enc=2, n_layer_dec=2,
+                        dropout=0.0, n_views=3, n_kernels=2, kernel_size=3)
+    ref_model, ours = _twin(lambda: create_whisper_mop(cfg), patched)
+    mel = torch.randn(2, 40, cfg.n_mels)
+    tok = torch.randint(0, cfg.vocab_size, (2, 8))
+    out_ref = ref_model(mel, tok)
+    out = ours(mel.cuda(), tok.cuda())
+    lr, lo = (o[0] if isinstance(o, (tuple, list)) else o for o in (out_ref, out))
+    assert max_abs(lo, lr) <= 5e-5 * max(1.0, lr.abs().max().item())
+
+
+def test_patched_reference_unified_msa_e(patched):
+    from mop.models import UnifiedMSA
+    kw = dict(n_views=3, share_qkv=True, gate_mode="lowrank", gate_rank=2, gate_init="mix5", use_k3=True)
+    ref_model, ours = _twin(lambda: UnifiedMSA("E", 32, heads=2, **kw), patched)
+    x = torch.randn(2, 24, 32)
+    y_ref, y = ref_model(x), ours(x.cuda())
+    assert max_abs(y, y_ref) <= 1e-5
