@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 3
+#define MOP_ABI_VERSION 4
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -97,6 +97,10 @@ typedef struct MopEdgewiseParams {
                            tcgen05 backward for N != 64 needs it as an input */
   float* y_base;        /* [B,N,H,dk] fp32, optional, same life cycle as row_stats: A V_1 (the output without the chain
                            value term) in full precision, from which the backward forms rowsum(dA . A) */
+  float* aux;           /* [mop_edgewise_aux_floats()] fp32, optional (fwd out, bwd in).  The N = 64 tcgen05 kernels hand their
+                           small per-(b,h) vectors from the forward to the backward instead of recomputing them: per-view and
+                           mixed-map softmax row statistics, row/column feature means, low-rank gate factors (17 KB per (b,h)).
+                           mop_edgewise_aux_floats() == 0: not used by this configuration (may be NULL) */
   /* backward only */
   const void* dy;       /* [B,N,H,dk] `dtype` */
   void* dqkv;           /* [B,N,Vp,3,H,dk] `dtype`, fully overwritten */
@@ -113,6 +117,8 @@ size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);
 /* 1 if mop_edgewise_fwd with these params would run the kernel whose backward wants `row_stats` and `y_base`: allocate
  * them, pass them to the forward and hand them back to the backward; 0 otherwise (both may be NULL) */
 int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p);
+/* number of floats of `aux` the forward would write / the backward needs for these params (0: none) */
+size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p);
 /* bytes of workspace needed by mop_edgewise_fwd (backward=0) / mop_edgewise_bwd (backward=1) */
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward);
 int mop_edgewise_fwd(MopEdgewiseParams* p, void* cuda_stream);

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 3
+MOP_ABI_VERSION = 4
 MOP_F32, MOP_BF16 = 0, 1
 MOP_GATE_DENSE, MOP_GATE_LOWRANK = 0, 1
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
@@ -32,7 +32,7 @@ class EdgewiseParams(C.Structure):
         ("q_scale", vp), ("k_scale", vp), ("v_scale", vp), ("chain_value_logit", vp),
         ("row_w", vp), ("row_b", vp), ("col_w", vp), ("col_b", vp),
         ("conv1_w", vp), ("conv1_b", vp), ("mid3_w", vp), ("mid3_b", vp), ("conv2_w", vp), ("conv2_b", vp),
-        ("row_stats", vp), ("y_base", vp),
+        ("row_stats", vp), ("y_base", vp), ("aux", vp),
         ("dy", vp), ("dqkv", vp), ("dscale_part", vp), ("dhead_part", vp), ("dlogit_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),
     ]
@@ -98,6 +98,8 @@ def load():
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
         lib.mop_edgewise_needs_row_stats.restype = C.c_int
         lib.mop_edgewise_needs_row_stats.argtypes = [C.POINTER(EdgewiseParams)]
+        lib.mop_edgewise_aux_floats.restype = C.c_size_t
+        lib.mop_edgewise_aux_floats.argtypes = [C.POINTER(EdgewiseParams)]
         lib.mop_edgewise_head_param_count.restype = C.c_size_t
         lib.mop_edgewise_head_param_count.argtypes = [C.POINTER(EdgewiseParams)]
         if lib.mop_abi_version() != MOP_ABI_VERSION:

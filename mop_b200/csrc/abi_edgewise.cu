@@ -68,6 +68,11 @@ int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p) {
   return (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) ? 1 : 0;
 }
 
+size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  return (p->impl != MOP_IMPL_SIMT && ewtc::supported(p)) ? (size_t)p->B * p->H * ewtc::kAuxFloats : 0;
+}
+
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {
   if (check_edgewise(p, false) != MOP_OK) return 0;
   if (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) {
@@ -121,6 +126,11 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
     }
     const int G = p->B * p->H, sms = sm_count();
     const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
+    if (bwd && edgewise_n64_bwd_supported(p)) {   // the forward handed its row statistics / feature means / gate factors on (aux)
+      if ((rc = edgewise_n64_bwd_launch(p, st))) return rc;
+      p->impl_used = MOP_IMPL_TCGEN05;
+      return MOP_OK;
+    }
     if (bwd) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
     else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());

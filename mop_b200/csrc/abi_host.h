@@ -23,4 +23,8 @@ template <typename K> static int allow_smem(K kernel, size_t bytes) {
   if (n_seen < 64) seen[n_seen++] = SmemOptIn{key, dev, bytes};
   return MOP_OK;
 }
+
+// third-generation N = 64 Edgewise backward (abi_edgewise64.cu)
+bool edgewise_n64_bwd_supported(const MopEdgewiseParams* p);
+int edgewise_n64_bwd_launch(MopEdgewiseParams* p, cudaStream_t st);
 }  // namespace mop

@@ -34,6 +34,17 @@ constexpr int kMaxC = 2 * kMaxV + 2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// ---- `aux`: small per-(b,h) vectors handed from the forward to the backward (MopEdgewiseParams::aux), in floats -----------
+//   stats [(kMaxV+1)][64][2]  per row of S_k (k < V) and of the mixed map (k = V): max * log2(e), 1 / sum exp
+//   rho   [kMaxC][64], kap [kMaxC][64]   row / column feature means (rows c < V and 2V, 2V+1 are used)
+//   a     [kMaxQ][64], b [kMaxQ][64]     low-rank gate factors, slot q = 4 * gate + k (unused slots 0)
+constexpr int kAuxStats = 0;
+constexpr int kAuxRho = (kMaxV + 1) * 64 * 2;
+constexpr int kAuxKap = kAuxRho + kMaxC * 64;
+constexpr int kAuxA = kAuxKap + kMaxC * 64;
+constexpr int kAuxB = kAuxA + kMaxQ * 64;
+constexpr int kAuxFloats = kAuxB + kMaxQ * 64;   // 4352 floats = 17 KB
+
 // ---- TMEM tile map: tile i -> lane offset 16*(i/8), column 64*(i%8) ---------------------------------
 // backward: 16 tiles in 512 columns (tile i -> lane offset 16*(i/8), column 64*(i%8));
 // forward: 8 tiles in 256 columns (lane offset 16*(i/4), column 64*(i%4)) so that two CTAs fit on one SM.
@@ -139,8 +150,8 @@ __device__ __forceinline__ void colsum_to(float (*red)[64], const Frag& f, const
   }
 }
 
-// row softmax of a fragment in place (fp32); returns nothing, v becomes probabilities
-__device__ __forceinline__ void frag_softmax(float* v) {
+// row softmax of a fragment in place (fp32): v becomes probabilities; st4 (optional) receives max_lo, max_hi, 1/sum_lo, 1/sum_hi
+__device__ __forceinline__ void frag_softmax(float* v, float* st4 = nullptr) {
   float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
@@ -161,6 +172,7 @@ __device__ __forceinline__ void frag_softmax(float* v) {
   const float ilo = 1.f / quad_sum(elo), ihi = 1.f / quad_sum(ehi);
 #pragma unroll
   for (int n = 0; n < 8; ++n) { v[4 * n] *= ilo; v[4 * n + 1] *= ilo; v[4 * n + 2] *= ihi; v[4 * n + 3] *= ihi; }
+  if (st4) { st4[0] = mlo; st4[1] = mhi; st4[2] = ilo; st4[3] = ihi; }
 }
 
 // in place: x = P (.) (x - rowsum(x (.) P))   (softmax backward on fragments)
@@ -260,6 +272,14 @@ static __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEd
   const int hw_bias = 4 * r * C;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
+    float* aux = nullptr;
+    if constexpr (!BWD) aux = p.aux ? p.aux + (size_t)g * kAuxFloats : nullptr;
+    auto put_stats = [&](int k, const float* st4) {   // row statistics of map k for the backward
+      if (aux && (f.lane & 3) == 0) {
+        *reinterpret_cast<float2*>(aux + kAuxStats + (k * 64 + f.row_lo) * 2) = make_float2(st4[0] * kLog2e, st4[2]);
+        *reinterpret_cast<float2*>(aux + kAuxStats + (k * 64 + f.row_hi) * 2) = make_float2(st4[1] * kLog2e, st4[3]);
+      }
+    };
     // =================================================================================================
     // stage 0: scales and operand tiles
     // =================================================================================================
@@ -319,7 +339,9 @@ static __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEd
       slo = quad_sum(slo); shi = quad_sum(shi);
       if ((f.lane & 3) == 0) { sv_.rho[i][f.row_lo] = slo * (1.f / 64.f); sv_.rho[i][f.row_hi] = shi * (1.f / 64.f); }
       colsum_to(sv_.red[i], f, v);
-      frag_softmax(v);
+      float st4[4];
+      frag_softmax(v, st4);
+      put_stats(i, st4);
       frag_store_bf16(tile(SL::A + i), f, v);
     }
     // chain products F = A_0..A_{V-1}, R = A_{V-1}..A_0
@@ -396,9 +418,15 @@ static __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEd
           acc = fmaf(W[q * C + 2 * V + 1], own[2 * V + 1][tok], acc);
         }
         (which ? sv_.b : sv_.a)[qq][tok] = acc;
+        if (aux) aux[(which ? kAuxB : kAuxA) + qq * 64 + tok] = acc;
         if constexpr (BWD)
           if (which == 0) *reinterpret_cast<__nv_bfloat16*>(bv_.a_bf + tile_off(64, tok, qq)) = __float2bfloat16_rn(acc);
       }
+      if (aux)   // feature means (rows c < V and 2V, 2V+1 are the ones in use)
+        for (int idx = tid; idx < 2 * C * 64; idx += 128) {
+          const int hf = idx / (C * 64), rem = idx % (C * 64);
+          aux[(hf ? kAuxKap : kAuxRho) + rem] = (hf ? &sv_.kap[0][0] : &sv_.rho[0][0])[rem];
+        }
     }
     __syncthreads();
     // =================================================================================================
@@ -436,7 +464,11 @@ static __global__ void __launch_bounds__(128, BWD ? 1 : 2) edgewise_kernel(MopEd
         amix[8 * blk + e] = s0 + fast_sigmoid(z[0]) * U + fast_sigmoid(z[1]) * O - fast_sigmoid(z[2]) * bn * U + fast_sigmoid(z[3]) * lf;
       }
     }
-    frag_softmax(amix);
+    {
+      float st4[4];
+      frag_softmax(amix, st4);
+      put_stats(V, st4);
+    }
     frag_store_bf16(tile(SL::AMIX), f, amix);
 
     if constexpr (!BWD) {

@@ -128,6 +128,12 @@ class _Edgewise(torch.autograd.Function):
                 stats = torch.empty(B, H, N, 2, dtype=torch.float32, device=qkv_c.device)
                 ybase = torch.empty(B, N, H, dk, dtype=torch.float32, device=qkv_c.device)
                 p.row_stats, p.y_base = _ptr(stats), _ptr(ybase)
+            # the N = 64 tcgen05 kernels hand their small per-(b,h) vectors (softmax statistics, feature means, gate factors) on
+            aux = None
+            n_aux = lib.mop_edgewise_aux_floats(C.byref(p))
+            if n_aux and any(ctx.needs_input_grad):
+                aux = torch.empty(n_aux, dtype=torch.float32, device=qkv_c.device)
+                p.aux = _ptr(aux)
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 0)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv_c.device)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
@@ -141,7 +147,9 @@ class _Edgewise(torch.autograd.Function):
         ctx.in_dtypes = [None if t is None else t.dtype for t in (q_scale, k_scale, v_scale, logit, *head)]
         ctx.scale_shape = None if q_scale is None else q_scale.shape
         ctx.has_stats = stats is not None
-        ctx.save_for_backward(qkv_c, logit32, *(scales or ()), *head32, *((ybase, stats) if stats is not None else ()))
+        ctx.has_aux = aux is not None
+        ctx.save_for_backward(qkv_c, logit32, *(scales or ()), *head32, *((ybase, stats) if stats is not None else ()),
+                              *((aux,) if aux is not None else ()))
         return y
 
     @staticmethod
@@ -149,7 +157,9 @@ class _Edgewise(torch.autograd.Function):
         lib = _lib.load()
         cfg = ctx.cfg
         saved = ctx.saved_tensors
-        ybase = stats = None
+        ybase = stats = aux = None
+        if ctx.has_aux:
+            aux, saved = saved[-1], saved[:-1]
         if ctx.has_stats:
             ybase, stats = saved[-2], saved[-1]
             saved = saved[:-2]
@@ -167,6 +177,7 @@ class _Edgewise(torch.autograd.Function):
             p.y = _ptr(dqkv)  # the forward output is not needed by the backward kernels
             if stats is not None:
                 p.row_stats, p.y_base = _ptr(stats), _ptr(ybase)
+            p.aux = _ptr(aux)
             nhead = lib.mop_edgewise_head_param_count(C.byref(p))
             G = B * H
             dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev)
