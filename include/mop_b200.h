@@ -183,6 +183,43 @@ size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward);
 int mop_quartet_fwd(MopQuartetParams* p, void* cuda_stream);
 int mop_quartet_bwd(MopQuartetParams* p, void* cuda_stream);
 
+/* ------------------------------------------------------------------------- */
+/* Fused residual-add + DropPath scale + LayerNorm              */
+/* ------------------------------------------------------------------------- */
+/* The elementwise neighbours of the attention call in every reference block:
+ *   x = x + dp(attn(ln1(x)));  x = x + dp(mlp(ln2(x)))     experiments/cifar100_edgewise_gates.py:371-374,
+ *   DropPath (per-sample mask / keep)                       mop/models/components.py:14-27
+ * forward : x_new = x + scale[row / rows_per_sample] * r (r optional), y = LayerNorm(x_new) * gamma + beta
+ * backward: dx = LN'(dy) + dx_new (optional), dr = scale * dx, per-CTA partials of dgamma / dbeta */
+typedef struct MopLnParams {
+  int32_t struct_bytes;
+  int32_t rows, D;          /* x is [rows, D] fp32 contiguous, D <= 1024 */
+  int32_t r_dtype, y_dtype; /* MOP_F32 | MOP_BF16: type of r / dr and of y / dy */
+  int32_t rows_per_sample;  /* tokens per sample (rows sharing one DropPath scale) */
+  int32_t nparts;           /* rows of dgamma_part / dbeta_part (>= mop_ln_partial_rows(rows)) */
+  float eps;
+  const void* x;            /* residual stream in, fp32 */
+  const void* r;            /* branch output to add, or NULL */
+  const float* scale;       /* [rows / rows_per_sample] per-sample factor (mask / keep), or NULL (= 1) */
+  const float* gamma;
+  const float* beta;
+  void* x_new;              /* fp32 [rows, D]: x + scale r (fwd out when r != NULL; bwd in: the normalised tensor) */
+  void* y;                  /* [rows, D] y_dtype */
+  float* mean;              /* [rows] fwd out, bwd in */
+  float* rstd;              /* [rows] */
+  const void* dy;           /* [rows, D] y_dtype */
+  const void* dx_new;       /* optional fp32 [rows, D]: gradient reaching x_new through the residual stream */
+  void* dx;                 /* fp32 [rows, D] */
+  void* dr;                 /* optional [rows, D] r_dtype */
+  float* dgamma_part;       /* [nparts, D] */
+  float* dbeta_part;        /* [nparts, D] */
+} MopLnParams;
+
+/* number of per-CTA partial rows the backward writes for a [rows, D] problem on the current device */
+int mop_ln_partial_rows(int rows);
+int mop_ln_fwd(MopLnParams* p, void* cuda_stream);
+int mop_ln_bwd(MopLnParams* p, void* cuda_stream);
+
 /* Bring-up check of the tcgen05 building blocks: D = (a_mn ? A^T : A) * (b_mn ? B : B^T) on 64x64 fp32
  * device matrices (rounded to bf16), accumulator at TMEM lane offset {0,16} / column offset; D2 = D + 1
  * after a tcgen05.st/ld round trip. */

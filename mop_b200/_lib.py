@@ -68,6 +68,16 @@ class QuartetParams(C.Structure):
     ]
 
 
+class LnParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("rows", i32), ("D", i32), ("r_dtype", i32), ("y_dtype", i32), ("rows_per_sample", i32),
+        ("nparts", i32), ("eps", f32),
+        ("x", vp), ("r", vp), ("scale", vp), ("gamma", vp), ("beta", vp),
+        ("x_new", vp), ("y", vp), ("mean", vp), ("rstd", vp),
+        ("dy", vp), ("dx_new", vp), ("dx", vp), ("dr", vp), ("dgamma_part", vp), ("dbeta_part", vp),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -96,6 +106,12 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_ln_partial_rows.restype = C.c_int
+        lib.mop_ln_partial_rows.argtypes = [C.c_int]
+        for d in ("fwd", "bwd"):
+            fn = getattr(lib, f"mop_ln_{d}")
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(LnParams), C.c_void_p]
         lib.mop_edgewise_needs_row_stats.restype = C.c_int
         lib.mop_edgewise_needs_row_stats.argtypes = [C.POINTER(EdgewiseParams)]
         lib.mop_edgewise_aux_floats.restype = C.c_size_t

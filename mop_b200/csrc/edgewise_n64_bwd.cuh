@@ -78,10 +78,11 @@ struct __align__(1024) Smem {
   unsigned char bhl[4][64 * 16 * 2];   // per gate: [token][b_hi(4) b_hi(4) b_lo(4) 0(4)]
   float aux[kAuxFloats];               // stats | rho | kap | a | b  (one bulk copy per problem)
   float da[kMaxQ][64], db[kMaxQ][64];
-  float drho[kMaxC][64], dkap[kMaxC][64];
+  float rt[kMaxV][64], ct[kMaxV][64];  // feature-mean gradients as they enter dS_k: row term drho_k + dkap_{V+k}, column term dkap_k + drho_{V+k}
+  float sd[4][64];                     // chain-seed terms: drho_{2V}, dkap_{2V}, drho_{2V+1}, dkap_{2V+1}
   float cvec[kMaxV][64], vs1[64], vsL[64];
   float part[4][64];                   // row-term exchange between the four column blocks
-  float red[kMaxV][4][64];             // per-view row dots (final pass) / column-sum partials per sub-partition
+  float red[kMaxV][4][64];             // column-sum partials per sub-partition / row dots of the final pass (two buffers)
   float hw[2][kMaxQ * kMaxC + kMaxQ];  // gate-head weights + biases (row / column projection), staged once per CTA
   float wsum[16];
   uint64_t bar_mma, bar_in;
@@ -144,21 +145,21 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
       mma_ss(tbase + ewtc::ttile<true>(dt) + dcol, op_desc(a_kind, a_tile, k), op_desc(b_kind, b_tile, k), id, (acc || k > 0) ? 1u : 0u);
   };
   auto wait_mma = [&]() { mbar_wait(&sm.bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
-  // my 8 values of a 64x64 map as bf16 into a chunk-major tile
-  auto put_bf16 = [&](unsigned char* tile, int col0, const float* v) {
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      *reinterpret_cast<uint32_t*>(tile + tile_off(64, row_lo, col0 + 8 * n + cq)) = pack_bf16(v[4 * n + 0], v[4 * n + 1]);
-      *reinterpret_cast<uint32_t*>(tile + tile_off(64, row_hi, col0 + 8 * n + cq)) = pack_bf16(v[4 * n + 2], v[4 * n + 3]);
-    }
+  // my 8 values of a 64x64 map as bf16 into / from a chunk-major tile: element (row, 16 cblk + 8n + cq) sits at
+  // (2 cblk + n) * 1024 + row * 16 + 2 cq
+  const uint32_t o_lo = (uint32_t)(row_lo * 16 + 2 * cq), o_hi = o_lo + 128;
+  auto put_bf16 = [&](unsigned char* tile, int cblk, const float* v) {
+    unsigned char* t = tile + cblk * 2048;
+    *reinterpret_cast<uint32_t*>(t + o_lo) = pack_bf16(v[0], v[1]);
+    *reinterpret_cast<uint32_t*>(t + o_hi) = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint32_t*>(t + 1024 + o_lo) = pack_bf16(v[4], v[5]);
+    *reinterpret_cast<uint32_t*>(t + 1024 + o_hi) = pack_bf16(v[6], v[7]);
   };
-  auto get_bf16 = [&](const unsigned char* tile, int col0, float* v) {
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(tile + tile_off(64, row_lo, col0 + 8 * n + cq)));
-      const float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(tile + tile_off(64, row_hi, col0 + 8 * n + cq)));
-      v[4 * n + 0] = a.x; v[4 * n + 1] = a.y; v[4 * n + 2] = b.x; v[4 * n + 3] = b.y;
-    }
+  auto get_bf16 = [&](const unsigned char* tile, int cblk, float* v) {
+    const unsigned char* t = tile + cblk * 2048;
+    const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(t + o_lo)), b = unpack_bf16(*reinterpret_cast<const uint32_t*>(t + o_hi));
+    const float2 c = unpack_bf16(*reinterpret_cast<const uint32_t*>(t + 1024 + o_lo)), d = unpack_bf16(*reinterpret_cast<const uint32_t*>(t + 1024 + o_hi));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   };
 
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
@@ -271,7 +272,7 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         v[4 * n + 2] = fast_exp2(fmaf(v[4 * n + 2], kLog2e, -shi.x)) * shi.y;
         v[4 * n + 3] = fast_exp2(fmaf(v[4 * n + 3], kLog2e, -shi.x)) * shi.y;
       }
-      put_bf16(sm.A[k], c0, v);
+      put_bf16(sm.A[k], cb, v);
     }
     // chain products F = A_0..A_{V-1}, R = A_{V-1}..A_0, prefixes / suffixes kept as bf16 tiles for the sweep
     uint32_t sF;
@@ -288,12 +289,12 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         float v[8];
         tmem_ld_16x256b_x2(tcol(tF), v);
         tmem_ld_wait();
-        put_bf16(sm.P[s - 1], c0, v);
+        put_bf16(sm.P[s - 1], cb, v);
         xf = sa(sm.P[s - 1]);
         if (s < V - 1) {
           tmem_ld_16x256b_x2(tcol(tR), v);
           tmem_ld_wait();
-          put_bf16(sm.R[s - 1], c0, v);
+          put_bf16(sm.R[s - 1], cb, v);
           xr = sa(sm.R[s - 1]);
         }
       }
@@ -362,9 +363,8 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         tmem_st_x1(tcol(tW4) + off, fv);
         tmem_st_x1(tcol(tT1) + off, da4);
         tmem_st_x1(tcol(tT2) + off, a4);
-        const int c = c0 + 8 * n + cq;
-        *reinterpret_cast<uint32_t*>(sm.AMIX + tile_off(64, row_lo, c)) = pack_bf16(a4[0], a4[1]);
-        *reinterpret_cast<uint32_t*>(sm.AMIX + tile_off(64, row_hi, c)) = pack_bf16(a4[2], a4[3]);
+        *reinterpret_cast<uint32_t*>(sm.AMIX + (2 * cb + n) * 1024 + o_lo) = pack_bf16(a4[0], a4[1]);
+        *reinterpret_cast<uint32_t*>(sm.AMIX + (2 * cb + n) * 1024 + o_hi) = pack_bf16(a4[2], a4[3]);
       }
       dl_lo = quad_sum(dl_lo);
       dl_hi = quad_sum(dl_hi);
@@ -414,7 +414,7 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 8; ++e) gq[e] = fmaf((e & 2) ? -dhi : -dlo, t2[e], gq[e]) * wv[e];
-          put_bf16(sm.X[t], 16 * ch, gq);
+          put_bf16(sm.X[t], ch, gq);
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
             const int c = 16 * ch + 8 * n + cq;
@@ -495,54 +495,71 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         ds[idx] = val;
       }
     }
-    // feature-mean gradients
-    for (int idx = tid; idx < C * 64; idx += kThreads) {
-      const int c = idx >> 6, tok = idx & 63;
-      float sr = 0.f, sc = 0.f;
-      for (int qq = 0; qq < kMaxQ; ++qq) {
-        const int t = qq >> 2, k = qq & 3;
-        if (k < r) {
-          const int q = t * r + k;
-          sr = fmaf(hw_row[q * C + c], sm.da[qq][tok], sr);
-          sc = fmaf(hw_col[q * C + c], sm.db[qq][tok], sc);
-        }
-      }
-      sm.drho[c][tok] = sr * (1.f / 64.f);
-      sm.dkap[c][tok] = sc * (1.f / 64.f);
-    }
+    // feature-mean gradients, already combined the way dS_k and the chain seeds use them.  thread = (token, output group):
+    // outputs o < V: row term of view o; V <= o < 2V: column term of view o - V; 2V .. 2V+3: seed terms
     {
-      // gate-head parameter partials: <da_q, feature_c> / <db_q, feature_c> and the bias sums
-      const int nW = 4 * r * C, nP = nW + 4 * r;
-      float* dh = p.dhead_part + (size_t)g * 2 * nP;
-      for (int idx = tid; idx < 2 * nP; idx += kThreads) {
-        const int half = idx / nP, rem = idx % nP;
-        float (*dv)[64] = half ? sm.db : sm.da;
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rem < nW) {
-          const int q = rem / C, c = rem % C, qq = 4 * (q / r) + (q % r);
-          const float* ft;   // feature of channel c as seen by the row (half 0) / column (half 1) projection
-          if (c < V) ft = half ? kap[c] : rho[c];
-          else if (c < 2 * V) ft = half ? rho[c - V] : kap[c - V];
-          else ft = half ? kap[c] : rho[c];
-          const float4* dp = reinterpret_cast<const float4*>(dv[qq]);
-          const float4* fp = reinterpret_cast<const float4*>(ft);
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const float4 d4 = dp[i], f4 = fp[i];
-            a4.x = fmaf(d4.x, f4.x, a4.x); a4.y = fmaf(d4.y, f4.y, a4.y); a4.z = fmaf(d4.z, f4.z, a4.z); a4.w = fmaf(d4.w, f4.w, a4.w);
+      const int tok = tid & 63, grp = tid >> 6;
+      float dav[kMaxQ], dbv[kMaxQ];
+#pragma unroll
+      for (int qq = 0; qq < kMaxQ; ++qq) { dav[qq] = sm.da[qq][tok]; dbv[qq] = sm.db[qq][tok]; }
+      for (int o = grp; o < 2 * V + 4; o += 8) {
+        // out = (1/64) sum_q ( hw_row[q][cr] da[q] [+ hw_col[q][cc] db[q]] )
+        int cr = -1, cc = -1;
+        if (o < V) { cr = o; cc = V + o; }
+        else if (o < 2 * V) { cc = o - V; cr = o; }
+        else if (o == 2 * V) cr = 2 * V;
+        else if (o == 2 * V + 1) cc = 2 * V;
+        else if (o == 2 * V + 2) cr = 2 * V + 1;
+        else cc = 2 * V + 1;
+        float acc = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < kMaxQ; ++qq) {
+          const int t = qq >> 2, k = qq & 3;
+          if (k < r) {
+            const int q = t * r + k;
+            if (cr >= 0) acc = fmaf(hw_row[q * C + cr], dav[qq], acc);
+            if (cc >= 0) acc = fmaf(hw_col[q * C + cc], dbv[qq], acc);
           }
-        } else {
-          const int q = rem - nW, qq = 4 * (q / r) + (q % r);
-          const float4* dp = reinterpret_cast<const float4*>(dv[qq]);
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) { const float4 d4 = dp[i]; a4.x += d4.x; a4.y += d4.y; a4.z += d4.z; a4.w += d4.w; }
         }
-        dh[idx] = (a4.x + a4.y) + (a4.z + a4.w);
+        acc *= (1.f / 64.f);
+        if (o < V) sm.rt[o][tok] = acc;
+        else if (o < 2 * V) sm.ct[o - V][tok] = acc;
+        else sm.sd[o - 2 * V][tok] = acc;
       }
     }
     __syncthreads();
-    // V, dY and the aux vectors of this problem are consumed: fetch the next problem's
-    if (tid == 0 && g + (int)gridDim.x < G) load_vdy(g + gridDim.x);
+    // gate-head parameter partials <da_q, feature_c>, <db_q, feature_c> and the bias sums: thread = (projection, slot q, channel
+    // half, 8-token group); runs while the first sweep step's MMAs are in flight
+    auto head_partials = [&]() {
+      const int tg = tid & 7, chalf = (tid >> 3) & 1, qq = (tid >> 4) & 15, half = tid >> 8;
+      const int t = qq >> 2, k = qq & 3;
+      const bool live = k < r;   // unused slots hold zeros; no early exit: the shuffles below need every lane
+      const int q = t * r + k, nW = 4 * r * C, nP = nW + 4 * r;
+      float* dh = p.dhead_part + (size_t)g * 2 * nP + (size_t)half * nP;
+      const float* dv = (half ? sm.db[qq] : sm.da[qq]) + 8 * tg;
+      const float4 d0 = *reinterpret_cast<const float4*>(dv), d1 = *reinterpret_cast<const float4*>(dv + 4);
+      auto tg_sum = [&](float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        return v;
+      };
+      const int cbeg = chalf ? (C + 1) / 2 : 0, cend = chalf ? C : (C + 1) / 2;
+      for (int c = cbeg; c < cend; ++c) {
+        const float* ft;   // feature of channel c as seen by the row (half 0) / column (half 1) projection
+        if (c < V) ft = half ? kap[c] : rho[c];
+        else if (c < 2 * V) ft = half ? rho[c - V] : kap[c - V];
+        else ft = half ? kap[c] : rho[c];
+        const float4 f0 = *reinterpret_cast<const float4*>(ft + 8 * tg), f1 = *reinterpret_cast<const float4*>(ft + 8 * tg + 4);
+        float a = d0.x * f0.x;
+        a = fmaf(d0.y, f0.y, a); a = fmaf(d0.z, f0.z, a); a = fmaf(d0.w, f0.w, a);
+        a = fmaf(d1.x, f1.x, a); a = fmaf(d1.y, f1.y, a); a = fmaf(d1.z, f1.z, a); a = fmaf(d1.w, f1.w, a);
+        a = tg_sum(a);
+        if (tg == 0 && live) dh[q * C + c] = a;
+      }
+      const float bsum = tg_sum(((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w)));
+      if (chalf && tg == 0 && live) dh[nW + q] = bsum;
+    };
     // =========================================================================================================================
     // chain seeds X_F = Hf + G + dfeat_{2V} / (F + eps), X_R = dfeat_{2V+1} / (R + eps);  d logit = (1 - w) sum F (.) G
     // =========================================================================================================================
@@ -558,11 +575,11 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
       for (int e = 0; e < 8; ++e) {
         const int col = c0 + 8 * (e >> 2) + cq + (e & 1), row = (e & 2) ? row_hi : row_lo;
         dot = fmaf(Fv[e], gg[e], dot);
-        hf[e] = hf[e] + gg[e] + (sm.drho[2 * V][row] + sm.dkap[2 * V][col]) * fast_rcp(Fv[e] + eps);
-        Rv[e] = (sm.drho[2 * V + 1][row] + sm.dkap[2 * V + 1][col]) * fast_rcp(Rv[e] + eps);
+        hf[e] = hf[e] + gg[e] + (sm.sd[0][row] + sm.sd[1][col]) * fast_rcp(Fv[e] + eps);
+        Rv[e] = (sm.sd[2][row] + sm.sd[3][col]) * fast_rcp(Rv[e] + eps);
       }
-      put_bf16(sm.X[0], c0, hf);
-      put_bf16(sm.X[2], c0, Rv);
+      put_bf16(sm.X[0], cb, hf);
+      put_bf16(sm.X[2], cb, Rv);
       dot = warp_sum(dot);
       if (lane == 0) sm.wsum[wid] = dot;
     }
@@ -597,6 +614,7 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
           mma_commit(&sm.bar_mma);
         }
         touched |= (1u << kF) | (1u << kR);
+        if (s == 0) head_partials();
         wait_mma();
         if (s < V - 2) {
           xf ^= 1;
@@ -604,10 +622,10 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
           float v[8];
           tmem_ld_16x256b_x2(tcol(tXF), v);
           tmem_ld_wait();
-          put_bf16(sm.X[xf], c0, v);
+          put_bf16(sm.X[xf], cb, v);
           tmem_ld_16x256b_x2(tcol(tXR), v);
           tmem_ld_wait();
-          put_bf16(sm.X[xr], c0, v);
+          put_bf16(sm.X[xr], cb, v);
         }
       }
     }
@@ -616,7 +634,7 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
     // =========================================================================================================================
     auto load_dA = [&](int k, float* x, float* pk) {
       tmem_ld_16x256b_x2(tcol(tdA + k), x);
-      get_bf16(sm.A[k], c0, pk);
+      get_bf16(sm.A[k], cb, pk);
       tmem_ld_wait();
       if (k == 0 || k == V - 1) {   // last links of the two chains (fp32 accumulators of the last sweep step)
         float y2[8];
@@ -635,34 +653,35 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
       }
     };
     for (int k = 0; k < V; ++k) {
-      float x[8], pk[8];
+      float x[8], pk[8], cd[8];
+      tmem_ld_16x256b_x2(tcol(tS + k), cd);
       load_dA(k, x, pk);
       float lo = 0.f, hi = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) { if (e & 2) hi = fmaf(x[e], pk[e], hi); else lo = fmaf(x[e], pk[e], lo); }
       lo = quad_sum(lo);
       hi = quad_sum(hi);
-      if ((lane & 3) == 0) { sm.red[k][cb][row_lo] = lo; sm.red[k][cb][row_hi] = hi; }
-    }
-    __syncthreads();
-    for (int k = 0; k < V; ++k) {
-      float x[8], pk[8], cd[8];
-      tmem_ld_16x256b_x2(tcol(tS + k), cd);
-      load_dA(k, x, pk);
-      const float dlo = (sm.red[k][0][row_lo] + sm.red[k][1][row_lo]) + (sm.red[k][2][row_lo] + sm.red[k][3][row_lo]);
-      const float dhi = (sm.red[k][0][row_hi] + sm.red[k][1][row_hi]) + (sm.red[k][2][row_hi] + sm.red[k][3][row_hi]);
+      float (*rd)[64] = sm.red[k & 1];   // two buffers: a warp is at most one barrier ahead of its three partners
+      if ((lane & 3) == 0) { rd[cb][row_lo] = lo; rd[cb][row_hi] = hi; }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + sp) : "memory");   // the four warps (one per column block) that share these rows
+      const float dlo = (rd[0][row_lo] + rd[1][row_lo]) + (rd[2][row_lo] + rd[3][row_lo]);
+      const float dhi = (rd[0][row_hi] + rd[1][row_hi]) + (rd[2][row_hi] + rd[3][row_hi]);
+      const float rlo = sm.rt[k][row_lo], rhi = sm.rt[k][row_hi];
+      const float2 c01 = *reinterpret_cast<const float2*>(&sm.ct[k][c0 + cq]), c23 = *reinterpret_cast<const float2*>(&sm.ct[k][c0 + 8 + cq]);
+      const float ctv[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int col = c0 + 8 * (e >> 2) + cq + (e & 1), row = (e & 2) ? row_hi : row_lo;
-        const float ft = (sm.drho[k][row] + sm.dkap[k][col]) + (sm.drho[V + k][col] + sm.dkap[V + k][row]);
+        const float ft = ((e & 2) ? rhi : rlo) + ctv[2 * (e >> 2) + (e & 1)];
         x[e] = fmaf(pk[e], x[e] - ((e & 2) ? dhi : dlo), cd[e] + ft);
       }
-      put_bf16(sm.A[k], c0, x);
+      put_bf16(sm.A[k], cb, x);
     }
     // =========================================================================================================================
     // batch 3: T_k = dS_k K, U_k = dS_k^T Q; dQ = sum_k T_k (.) c_k, dK = sum_k U_k (.) c_k, scale partials
     // =========================================================================================================================
     publish();
+    // V, dY and the aux vectors of this problem are consumed (every thread is past the head partials): fetch the next problem's
+    if (tid == 0 && g + (int)gridDim.x < G) load_vdy(g + gridDim.x);
     if (leader) {
       for (int k = 0; k < V; ++k) {
         if (mine(2 * k)) gemm(tS + k, 0, sa(sm.A[k]), CM_K, sa(sm.Kr), SW_MN, false, 4, 64);

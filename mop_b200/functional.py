@@ -25,6 +25,11 @@ last_impl: Dict[str, str] = {}
 abi_calls: Dict[str, int] = {"edgewise_fwd": 0, "edgewise_bwd": 0, "sdpa_fwd": 0, "sdpa_bwd": 0, "quartet_fwd": 0, "quartet_bwd": 0}
 
 
+# Test hook: when `keep_partials` is True the un-reduced per-(batch, head) contributions to scalar parameter gradients that the
+# kernels write are kept here (cloned) after each backward: "edgewise_dlogit" [B*H], "quartet_dscalar" [B*H, 2]
+keep_partials = False
+last_partials: Dict[str, torch.Tensor] = {}
+
 # Optional per-launch device timing: when `kernel_timing` is True every ABI call is bracketed by
 # CUDA events on the launching stream; bench.py reads `kernel_events` after a synchronize.
 kernel_timing = False
@@ -198,6 +203,8 @@ class _Edgewise(torch.autograd.Function):
             dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:
             dq_s = dk_s = dv_s = None
+        if keep_partials:
+            last_partials["edgewise_dlogit"] = dlogit_part.detach().clone()
         dlogit = dlogit_part.sum().reshape(()).to(dts[3])
         flat = dhead_part.sum(0)
         dheads, off = [], 0
@@ -433,6 +440,8 @@ class _Quartet(torch.autograd.Function):
         abi_calls["quartet_bwd"] += 1
         dmix = dgam = None
         if ctx.quart:
+            if keep_partials:
+                last_partials["quartet_dscalar"] = dsc.detach().clone()
             tot = dsc.sum(0)
             dmix = tot[0].reshape(1).to(ctx.scalar_dtypes[0])
             dgam = tot[1].reshape(1).to(ctx.scalar_dtypes[1])
@@ -453,3 +462,101 @@ def quartet_attention(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=Non
             raise NotImplementedError("gradient w.r.t. the additive attention mask is not provided")
         add_mask = _as4(add_mask.detach().float(), B, H, T, T, "attention_mask")
     return _Quartet.apply(dict(eps=float(eps), impl=impl), q, k, v, q2, k2, mixture, quartet_scale, add_mask)
+
+
+# ----------------------------------------------------------------------------
+# Fused residual-add + DropPath scale + LayerNorm
+# ----------------------------------------------------------------------------
+def _ln_params(x2, r2, scale, gamma, beta, eps, rows_per_sample, y_dtype):
+    p = _lib.new_params(_lib.LnParams)
+    p.rows, p.D = x2.shape
+    p.r_dtype = _DT[r2.dtype] if r2 is not None else _lib.MOP_F32
+    p.y_dtype = _DT[y_dtype]
+    p.rows_per_sample = int(rows_per_sample)
+    p.eps = float(eps)
+    p.x, p.r, p.scale, p.gamma, p.beta = _ptr(x2), _ptr(r2), _ptr(scale), _ptr(gamma), _ptr(beta)
+    return p
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(x, r, scale) -> (x_new = x + scale[b] r, y = LayerNorm(x_new)); r may be None (then x_new is not produced)."""
+
+    @staticmethod
+    def forward(ctx, x, r, scale, gamma, beta, eps, rows_per_sample, y_dtype):
+        lib = _lib.load()
+        _need_cuda(x, "x")
+        D = x.shape[-1]
+        x2 = x.detach().reshape(-1, D)
+        if x2.dtype != torch.float32 or not x2.is_contiguous():
+            x2 = x2.float().contiguous()
+        r2 = None
+        if r is not None:
+            r2 = r.detach().reshape(-1, D)
+            if r2.dtype not in _DT or not r2.is_contiguous():
+                r2 = r2.contiguous() if r2.dtype in _DT else r2.float().contiguous()
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        sc32 = None if scale is None else scale.detach().float().contiguous()
+        rows = x2.shape[0]
+        dev = x2.device
+        y = torch.empty(rows, D, dtype=y_dtype, device=dev)
+        x_new = torch.empty(rows, D, dtype=torch.float32, device=dev) if r2 is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            p = _ln_params(x2, r2, sc32, g32, b32, eps, rows_per_sample, y_dtype)
+            p.x_new, p.y, p.mean, p.rstd = _ptr(x_new), _ptr(y), _ptr(mean), _ptr(rstd)
+            _lib.check(lib.mop_ln_fwd(C.byref(p), _stream()), "mop_ln_fwd")
+        abi_calls["ln_fwd"] = abi_calls.get("ln_fwd", 0) + 1
+        ctx.save_for_backward(x_new if x_new is not None else x2, mean, rstd, g32, sc32 if sc32 is not None else mean)
+        ctx.meta = (eps, rows_per_sample, y_dtype, r2 is not None, None if r2 is None else r2.dtype, sc32 is not None,
+                    x.shape, None if r is None else r.dtype, gamma.dtype, beta.dtype)
+        shp = x.shape
+        if x_new is None:
+            ctx.mark_non_differentiable()
+            return None, y.view(shp)
+        return x_new.view(shp), y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dx_new, dy):
+        lib = _lib.load()
+        xs, mean, rstd, g32, sc = ctx.saved_tensors
+        eps, rps, y_dtype, has_r, r_dtype, has_scale, shp, r_in_dtype, g_dt, b_dt = ctx.meta
+        rows, D = xs.shape
+        dev = xs.device
+        if dy is None:
+            dy = torch.zeros(rows, D, dtype=y_dtype, device=dev)
+        dy2 = dy.detach().reshape(rows, D).to(y_dtype).contiguous()
+        dxn = None
+        if has_r and dx_new is not None:
+            dxn = dx_new.detach().reshape(rows, D).float().contiguous()
+        dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        dr = torch.empty(rows, D, dtype=r_dtype, device=dev) if has_r else None
+        with torch.cuda.device(dev):
+            nparts = lib.mop_ln_partial_rows(rows)
+            parts = torch.empty(2, nparts, D, dtype=torch.float32, device=dev)
+            p = _ln_params(xs, dr, sc if has_scale else None, g32, g32, eps, rps, y_dtype)
+            p.r = _ptr(dr)          # only its presence / dtype matters to the backward
+            p.x_new = _ptr(xs) if has_r else None
+            p.mean, p.rstd = _ptr(mean), _ptr(rstd)
+            p.dy, p.dx_new, p.dx, p.dr = _ptr(dy2), _ptr(dxn), _ptr(dx), _ptr(dr)
+            p.dgamma_part, p.dbeta_part, p.nparts = _ptr(parts[0]), _ptr(parts[1]), nparts
+            _lib.check(lib.mop_ln_bwd(C.byref(p), _stream()), "mop_ln_bwd")
+        abi_calls["ln_bwd"] = abi_calls.get("ln_bwd", 0) + 1
+        sums = parts.sum(1)
+        d_r = None if not has_r else dr.view(shp).to(r_in_dtype)
+        return dx.view(shp), d_r, None, sums[0].to(g_dt), sums[1].to(b_dt), None, None, None
+
+
+def add_layer_norm(x: torch.Tensor, r: Optional[torch.Tensor], scale: Optional[torch.Tensor], gamma: torch.Tensor,
+                   beta: torch.Tensor, eps: float = 1e-5, *, out_dtype: Optional[torch.dtype] = None):
+    """``x_new = x + scale[b] * r`` (per-sample DropPath factor, optional) and ``y = LayerNorm(x_new)`` in one pass.
+
+    x ``[B, N, D]`` fp32 residual stream; r ``[B, N, D]`` branch output (bf16 / fp32) or None; scale ``[B]`` or None.
+    Returns ``(x_new, y)`` (``x_new is x`` when r is None).  ``out_dtype`` defaults to the CUDA autocast dtype when autocast
+    is on (what the Linear that consumes y would cast to), else fp32.
+    """
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+    rows_per_sample = x.shape[-2] if x.dim() >= 2 else 1
+    x_new, y = _AddLayerNorm.apply(x, r, scale, gamma, beta, float(eps), rows_per_sample, out_dtype)
+    return (x if r is None else x_new), y

@@ -17,6 +17,7 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import functional as MF
 from .attention_variants import EdgewiseMSA
 from .components import MLP, DropPath, PatchEmbed
 
@@ -43,6 +44,23 @@ class BlockEdgewise(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x + self.dp1(self.attn(self.ln1(x)))
         return x + self.dp2(self.mlp(self.ln2(x)))
+
+    # ---- fused residual stream: `x + dp(branch)` is folded into the LayerNorm that follows it -------------------
+    @staticmethod
+    def _dp_scale(dp: DropPath, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """Per-sample DropPath factor mask / keep (reference components.py:14-27), or None when DropPath is the identity."""
+        if not dp.training or dp.drop_prob == 0.0:
+            return None
+        keep = 1.0 - dp.drop_prob
+        return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep) / keep
+
+    def forward_fused(self, x: torch.Tensor, branch: Optional[torch.Tensor], scale: Optional[torch.Tensor]):
+        """Same math as ``forward`` with the residual adds deferred: takes the residual stream and the not-yet-added branch
+        of the previous block, returns the stream and this block's not-yet-added MLP branch ``(x, branch, scale)``."""
+        x, h = MF.add_layer_norm(x, branch, scale, self.ln1.weight, self.ln1.bias, self.ln1.eps)
+        a = self.attn(h)
+        x, h = MF.add_layer_norm(x, a, self._dp_scale(self.dp1, x), self.ln2.weight, self.ln2.bias, self.ln2.eps)
+        return x, self.mlp(h), self._dp_scale(self.dp2, x)
 
 
 class ViTEdgewise(nn.Module):
@@ -72,6 +90,14 @@ class ViTEdgewise(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         tok, _ = self.patch(x)
         tok = tok + self.pos
+        if tok.is_cuda and tok.dtype == torch.float32 and tok.shape[-1] <= 1024:
+            # fused residual stream: every `x + dp(branch)` rides on the LayerNorm that follows it (one pass, one kernel)
+            tok = tok.contiguous()
+            branch = scale = None
+            for blk in self.blocks:
+                tok, branch, scale = blk.forward_fused(tok, branch, scale)
+            _, h = MF.add_layer_norm(tok, branch, scale, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps, out_dtype=torch.float32)
+            return self.head(h.mean(dim=1))
         for blk in self.blocks:
             tok = blk(tok)
         return self.head(self.ln_f(tok).mean(dim=1))

@@ -14,10 +14,16 @@ ap.add_argument("--top", type=int, default=45)
 a = ap.parse_args()
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(a.so)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-# locate function
-start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and a.kernel in l)
+# one cubin per translation unit: take the one that holds the kernel
+sass, start = None, None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    cand = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    hit = [i for i, l in enumerate(cand) if l.startswith(".text.") and a.kernel in l]
+    if hit:
+        sass, start = cand, hit[0]
+        break
+if sass is None:
+    sys.exit(f"kernel {a.kernel!r} not found in {a.so}")
 lines = []  # (file, line) per instruction
 cur = ("?", 0)
 for l in sass[start + 1:]:
