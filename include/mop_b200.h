@@ -42,11 +42,11 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 4
+#define MOP_ABI_VERSION 6
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
-enum { MOP_GATE_DENSE = 0, MOP_GATE_LOWRANK = 1 };
+enum { MOP_GATE_DENSE = 0, MOP_GATE_LOWRANK = 1, MOP_GATE_CONST = 2 };   /* CONST: fixed scalar gates (MultiHopMSA) */
 /* which implementation ran (written to `impl_used` by the *_fwd / *_bwd calls) */
 enum { MOP_IMPL_SIMT = 1, MOP_IMPL_TCGEN05 = 2 };
 /* `impl` request: AUTO picks tcgen05 when the shape/dtype is covered, else SIMT */
@@ -111,6 +111,11 @@ typedef struct MopEdgewiseParams {
   /* scratch */
   void* workspace;
   size_t workspace_bytes;
+  /* gate_mode == MOP_GATE_CONST (variant D, MultiHopMSA attention_variants.py:163-231): the four gates are the fixed scalars
+     {and_, or_, not_, chain} instead of a gate head, the chain product is A_1 A_2^(hops-1) (views 0,1,1,..) and there is no
+     reverse chain; dhead_part is not written */
+  float const_gates[4];
+  int32_t hops;         /* chain length >= 2 (CONST mode); ignored otherwise */
 } MopEdgewiseParams;
 
 size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);
@@ -146,6 +151,10 @@ typedef struct MopSdpaParams {
   const void* dy;       /* [B,Nq,H,dk] */
   void *dq, *dk_, *dv;  /* contiguous [B,Nq,H,dk], [B,Nk,H,dk], [B,Nk,H,dk] */
   void* workspace; size_t workspace_bytes;
+  /* attention dropout on the probabilities (attention_variants.py:45, whisper_mop.py:173,217): p = 0 -> off.  The keep mask is
+     a function of (dropout_seed, dropout_offset, b, h, i, j) regenerated by every kernel; pass the forward's pair to the backward */
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
 } MopSdpaParams;
 
 size_t mop_sdpa_workspace_bytes(const MopSdpaParams* p, int backward);
@@ -177,6 +186,9 @@ typedef struct MopQuartetParams {
   void *dq, *dk_, *dv, *dq2, *dk2;
   float* dscalar_part;  /* [B*H,2] partial grads of (mixture, quartet_scale) */
   void* workspace; size_t workspace_bytes;
+  /* attention dropout (quartet_attn_patch.py:24,118-119; TransformerConfig.dropout defaults to 0.1): see MopSdpaParams */
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
 } MopQuartetParams;
 
 size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward);
@@ -219,6 +231,10 @@ typedef struct MopLnParams {
 int mop_ln_partial_rows(int rows);
 int mop_ln_fwd(MopLnParams* p, void* cuda_stream);
 int mop_ln_bwd(MopLnParams* p, void* cuda_stream);
+
+/* The dropout factor every attention kernel applies to P[b,h,i,j] for (p, seed, offset): out[bh, i, j] = 0 or 1 / (1 - p)
+ * (fp32, [BH, Nq, Nk]).  Test infrastructure: lets the CPU oracle be evaluated under the kernels' own mask. */
+int mop_dropout_mask(float* out, int BH, int Nq, int Nk, float p, uint64_t seed, uint64_t offset, void* cuda_stream);
 
 /* Bring-up check of the tcgen05 building blocks: D = (a_mn ? A^T : A) * (b_mn ? B : B^T) on 64x64 fp32
  * device matrices (rounded to bf16), accumulator at TMEM lane offset {0,16} / column offset; D2 = D + 1

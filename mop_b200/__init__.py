@@ -4,7 +4,7 @@ Drop-in ``nn.Module`` replacements for the attention classes of Eran-BA/MoP,
 backed by hand-written CUDA kernels behind a C ABI (``libmop_b200.so``,
 ``include/mop_b200.h``).  There is no CPU fallback.
 """
-from .attention_variants import BaselineMSA, EdgewiseGateHead, EdgewiseMSA, UnifiedMSA
+from .attention_variants import BaselineMSA, CrossViewMixerMSA, EdgewiseGateHead, EdgewiseMSA, MultiHopMSA, UnifiedMSA
 from .components import MLP, MSA, Block, DropPath, PatchEmbed
 from .functional import edgewise_attention, quartet_attention, sdpa
 from .quartet_attn_patch import CausalSelfAttention, TransformerConfig
@@ -12,7 +12,7 @@ from .vit_edgewise import BlockEdgewise, ViTEdgewise
 from .whisper_mop import MultiheadCrossAttention, MultiheadSelfAttention
 
 __all__ = [
-    "BaselineMSA", "EdgewiseGateHead", "EdgewiseMSA", "UnifiedMSA", "MSA", "MLP", "Block", "DropPath", "PatchEmbed",
+    "BaselineMSA", "CrossViewMixerMSA", "MultiHopMSA", "EdgewiseGateHead", "EdgewiseMSA", "UnifiedMSA", "MSA", "MLP", "Block", "DropPath", "PatchEmbed",
     "BlockEdgewise", "ViTEdgewise", "MultiheadSelfAttention", "MultiheadCrossAttention",
     "CausalSelfAttention", "TransformerConfig", "edgewise_attention", "quartet_attention", "sdpa",
 ]

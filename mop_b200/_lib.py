@@ -13,9 +13,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 4
+MOP_ABI_VERSION = 6
 MOP_F32, MOP_BF16 = 0, 1
-MOP_GATE_DENSE, MOP_GATE_LOWRANK = 0, 1
+MOP_GATE_DENSE, MOP_GATE_LOWRANK, MOP_GATE_CONST = 0, 1, 2
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
 IMPL_NAMES = {MOP_IMPL_SIMT: "simt", MOP_IMPL_TCGEN05: "tcgen05"}
 
@@ -35,6 +35,7 @@ class EdgewiseParams(C.Structure):
         ("row_stats", vp), ("y_base", vp), ("aux", vp),
         ("dy", vp), ("dqkv", vp), ("dscale_part", vp), ("dhead_part", vp), ("dlogit_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("const_gates", f32 * 4), ("hops", i32),
     ]
 
 
@@ -51,6 +52,7 @@ class SdpaParams(C.Structure):
         ("lse", vp),
         ("dy", vp), ("dq", vp), ("dk_", vp), ("dv", vp),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("dropout_p", f32), ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
     ]
 
 
@@ -65,6 +67,7 @@ class QuartetParams(C.Structure):
         ("dy", vp), ("dq", vp), ("dk_", vp), ("dv", vp), ("dq2", vp), ("dk2", vp),
         ("dscalar_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("dropout_p", f32), ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
     ]
 
 
@@ -106,6 +109,8 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_dropout_mask.restype = C.c_int
+        lib.mop_dropout_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.mop_ln_partial_rows.restype = C.c_int
         lib.mop_ln_partial_rows.argtypes = [C.c_int]
         for d in ("fwd", "bwd"):

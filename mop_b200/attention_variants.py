@@ -41,17 +41,110 @@ class BaselineMSA(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _no_attn_dropout(self)
         B, N, D = x.shape
         t = self.qkv(x).view(B, N, 3, self.h, self.dk)
-        y = MF.sdpa(t[:, :, 0], t[:, :, 1], t[:, :, 2], zero_mask=attn_mask)
+        y = MF.sdpa(t[:, :, 0], t[:, :, 1], t[:, :, 2], zero_mask=attn_mask, dropout_p=self.attn_drop.p if self.training else 0.0)
         return self.proj_drop(self.proj(y.reshape(B, N, D)))
 
 
 def _no_attn_dropout(m: nn.Module):
     if m.training and m.attn_drop.p > 0.0:
         raise NotImplementedError(
-            "attention dropout inside the fused kernel is not provided (every reference caller on this path uses 0.0)")
+            "attention dropout inside the fused Edgewise kernel is not provided (every reference caller of EdgewiseMSA passes "
+            "attn_drop=0.0: experiments/cifar100_edgewise_gates.py:418); MSA / BaselineMSA / CausalSelfAttention / Whisper "
+            "attention do apply it in-kernel")
+
+
+class CrossViewMixerMSA(nn.Module):
+    """Variant C (reference :51-156): two projections, the four score maps q_a k_b^T mixed by a 2x2 parameter, optional
+    transpose cues, softmax, ``A v1``.
+
+    The mixed logits are ONE dot product over concatenated features,
+        S = [m11 q1 + m21 q2 | m12 q1 + m22 q2 | t1 k1 | t2 k2] . [k1 | k2 | q1 | q2] / sqrt(dk)
+    (S1^T[i,j] = k1_i . q1_j), so the module runs on the plain-attention kernels (``functional.sdpa``) with a feature width of
+    2 dk (4 dk with transpose cues); the linear feature mixing and its gradients (``mix`` included) stay in PyTorch.
+    ``enable_per_key_prior`` (an argmax-anchored re-weighting, off by default) raises.
+    """
+
+    def __init__(self, dim: int, heads: int = 4, attn_drop: float = 0.0, proj_drop: float = 0.0, use_transpose_cues: bool = True,
+                 t1: float = 0.0, t2: float = 0.0, enable_per_key_prior: bool = False, prior_weight: float = 0.5,
+                 anchor_mode: str = "argmax_row_sum", fixed_k_star: int = 0):
+        super().__init__()
+        if dim % heads:
+            raise AssertionError("dim must be divisible by heads")
+        self.h, self.dk = heads, dim // heads
+        self.qkv1 = nn.Linear(dim, dim * 3, bias=False)
+        self.qkv2 = nn.Linear(dim, dim * 3, bias=False)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim, bias=False)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.mix = nn.Parameter(torch.tensor([[1.0, 0.0], [0.0, 1.0]]))
+        self.use_transpose_cues = bool(use_transpose_cues)
+        self.t1, self.t2 = float(t1), float(t2)
+        self.enable_per_key_prior = bool(enable_per_key_prior)
+        self.prior_weight = float(prior_weight)
+        self.anchor_mode = str(anchor_mode)
+        self.fixed_k_star = int(fixed_k_star)
+
+    def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.enable_per_key_prior and self.prior_weight > 0.0:
+            raise NotImplementedError("CrossViewMixerMSA: per-key prior sharpening (reference :125-150) is not provided")
+        B, N, D = x.shape
+        H, dk = self.h, self.dk
+        a = self.qkv1(x).view(B, N, 3, H, dk)
+        b = self.qkv2(x).view(B, N, 3, H, dk)
+        q1, k1, v1, q2, k2 = a[:, :, 0], a[:, :, 1], a[:, :, 2], b[:, :, 0], b[:, :, 1]
+        m = self.mix
+        qs = [m[0, 0] * q1 + m[1, 0] * q2, m[0, 1] * q1 + m[1, 1] * q2]
+        ks = [k1, k2]
+        if self.use_transpose_cues:
+            if self.t1 != 0.0:
+                qs.append(self.t1 * k1); ks.append(q1)
+            if self.t2 != 0.0:
+                qs.append(self.t2 * k2); ks.append(q2)
+        nf = len(qs)
+        # the kernel divides by sqrt(nf dk), the reference by sqrt(dk)
+        qc = (torch.cat(qs, dim=-1) * (nf ** 0.5)).to(v1.dtype)
+        kc = torch.cat(ks, dim=-1).to(v1.dtype)
+        vc = F.pad(v1, (0, (nf - 1) * dk))
+        y = MF.sdpa(qc, kc, vc, zero_mask=attn_mask, dropout_p=self.attn_drop.p if self.training else 0.0)[..., :dk]
+        return self.proj_drop(self.proj(y.reshape(B, N, D)))
+
+
+class MultiHopMSA(nn.Module):
+    """Variant D (reference :163-231): two projections, fixed scalar gates, multi-hop chain ``A_1 A_2^(hops-1)`` inside the
+    logits and as value transport.  Runs as the fixed-gate mode of the Edgewise kernel (``gate_mode="const"``: the same
+    score maps, LSE / AND / NOT mix, chain products and value transport, without a gate head or a reverse chain)."""
+
+    def __init__(self, dim: int, heads: int = 4, attn_drop: float = 0.0, proj_drop: float = 0.0, beta_not: float = 0.5,
+                 gates=None, hops: int = 3):
+        super().__init__()
+        if dim % heads:
+            raise AssertionError("dim must be divisible by heads")
+        if hops < 2:
+            raise AssertionError("hops must be >= 2")
+        self.h, self.dk = heads, dim // heads
+        self.hops = int(hops)
+        self.qkv1 = nn.Linear(dim, dim * 3, bias=False)
+        self.qkv2 = nn.Linear(dim, dim * 3, bias=False)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim, bias=False)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.beta_not = float(beta_not)
+        self.gates = gates or dict(and_=1.0, or_=0.0, not_=0.0, chain=0.0, base=1.0)
+        self.chain_value_logit = nn.Parameter(torch.tensor(-2.0))
+
+    def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if attn_mask is not None:
+            raise NotImplementedError("MultiHopMSA: attn_mask is not provided by the fused kernel (no reference caller passes one)")
+        _no_attn_dropout(self)
+        B, N, D = x.shape
+        qkv = torch.stack([self.qkv1(x), self.qkv2(x)], dim=2).view(B, N, 2, 3, self.h, self.dk)
+        g = self.gates
+        y = MF.edgewise_attention(qkv, None, None, None, self.chain_value_logit, {}, n_views=2, beta_not=self.beta_not, gate_mode="const",
+                                  const_gates=(g.get("and_", 1.0), g.get("or_", 0.0), g.get("not_", 0.0), g.get("chain", 0.0)),
+                                  hops=self.hops)
+        return self.proj_drop(self.proj(y.reshape(B, N, D)))
 
 
 class EdgewiseGateHead(nn.Module):
@@ -245,8 +338,16 @@ class UnifiedMSA(nn.Module):
                 n_views=kwargs.get("n_views", 2), share_qkv=kwargs.get("share_qkv", False),
                 gate_mode=kwargs.get("gate_mode", "dense"), gate_rank=kwargs.get("gate_rank", 4),
                 gate_init=kwargs.get("gate_init", "neutral"))
-        elif mode in ("C", "D"):
-            raise NotImplementedError(f"attention mode {mode} is outside the fused hot path (next-row item)")
+        elif mode == "C":
+            self.impl = CrossViewMixerMSA(
+                dim, heads, kwargs.get("attn_drop", 0.0), kwargs.get("proj_drop", 0.0),
+                use_transpose_cues=kwargs.get("use_transpose_cues", True), t1=kwargs.get("t1", 0.0), t2=kwargs.get("t2", 0.0),
+                enable_per_key_prior=kwargs.get("enable_per_key_prior", False), prior_weight=kwargs.get("prior_weight", 0.5),
+                anchor_mode=kwargs.get("anchor_mode", "argmax_row_sum"), fixed_k_star=kwargs.get("fixed_k_star", 0))
+        elif mode == "D":
+            self.impl = MultiHopMSA(
+                dim, heads, kwargs.get("attn_drop", 0.0), kwargs.get("proj_drop", 0.0), beta_not=kwargs.get("beta_not", 0.5),
+                gates=kwargs.get("gates", None), hops=kwargs.get("hops", 3))
         else:
             raise ValueError(f"Unknown attention mode: {mode}")
 

@@ -68,11 +68,9 @@ class MSA(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
 
     def forward(self, x):
-        if self.training and self.attn_drop.p > 0.0:
-            raise NotImplementedError("attention dropout inside the fused kernel is not provided")
         B, N, D = x.shape
         t = self.qkv(x).view(B, N, 3, self.h, self.dk)
-        y = MF.sdpa(t[:, :, 0], t[:, :, 1], t[:, :, 2])
+        y = MF.sdpa(t[:, :, 0], t[:, :, 1], t[:, :, 2], dropout_p=self.attn_drop.p if self.training else 0.0)
         return self.proj_drop(self.proj(y.reshape(B, N, D)))
 
 

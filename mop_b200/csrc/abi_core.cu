@@ -66,9 +66,26 @@ int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int
 }
 }  // namespace mop
 
+namespace mop {
+static __global__ void dropout_mask_kernel(float* out, int BH, int Nq, int Nk, Dropout d) {
+  const size_t n = (size_t)BH * Nq * Nk;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t j = (uint32_t)(idx % Nk), i = (uint32_t)((idx / Nk) % Nq), bh = (uint32_t)(idx / ((size_t)Nk * Nq));
+    out[idx] = d.on ? dropout_factor(d, dropout_row_key(d, bh, i), j) : 1.f;
+  }
+}
+}  // namespace mop
+
 using namespace mop;
 
 extern "C" {
+int mop_dropout_mask(float* out, int BH, int Nq, int Nk, float p, uint64_t seed, uint64_t offset, void* stream) {
+  MOP_REQUIRE(out && BH > 0 && Nq > 0 && Nk > 0 && p >= 0.f && p <= 1.f, MOP_EINVAL, "bad dropout-mask arguments");
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device");
+  dropout_mask_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(out, BH, Nq, Nk, make_dropout(p, seed, offset));
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
 int mop_abi_version(void) { return MOP_ABI_VERSION; }
 const char* mop_last_error(void) { return g_err; }
 int mop_device_sm_count(void) {

@@ -17,11 +17,14 @@ static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
   MOP_REQUIRE(p->B > 0 && p->H > 0 && p->N > 0 && p->dk > 0, MOP_EINVAL, "bad shape B=%d H=%d N=%d dk=%d", p->B, p->H, p->N, p->dk);
   MOP_REQUIRE(p->V >= 2 && p->V <= ew::kMaxViews, MOP_EUNSUPPORTED, "n_views=%d outside [2,%d]", p->V, ew::kMaxViews);
   MOP_REQUIRE(p->Vp == 1 || p->Vp == p->V, MOP_EINVAL, "Vp must be 1 or V");
-  MOP_REQUIRE(p->gate_mode == MOP_GATE_DENSE || p->gate_mode == MOP_GATE_LOWRANK, MOP_EINVAL, "bad gate_mode %d", p->gate_mode);
+  MOP_REQUIRE(p->gate_mode == MOP_GATE_DENSE || p->gate_mode == MOP_GATE_LOWRANK || p->gate_mode == MOP_GATE_CONST, MOP_EINVAL,
+              "bad gate_mode %d", p->gate_mode);
   MOP_REQUIRE(p->qkv && p->y && p->chain_value_logit, MOP_EINVAL, "qkv / y / chain_value_logit must be set");
   MOP_REQUIRE((p->q_scale != nullptr) == (p->k_scale != nullptr) && (p->q_scale != nullptr) == (p->v_scale != nullptr),
               MOP_EINVAL, "q/k/v_scale must be all set or all NULL");
-  if (p->gate_mode == MOP_GATE_LOWRANK) {
+  if (p->gate_mode == MOP_GATE_CONST) {
+    MOP_REQUIRE(p->hops >= 2 && p->hops <= ew::kMaxViews, MOP_EUNSUPPORTED, "hops=%d outside [2,%d]", p->hops, ew::kMaxViews);
+  } else if (p->gate_mode == MOP_GATE_LOWRANK) {
     MOP_REQUIRE(p->gate_rank >= 1 && p->gate_rank <= ew::kMaxRank, MOP_EUNSUPPORTED, "gate_rank=%d outside [1,%d]", p->gate_rank, ew::kMaxRank);
     MOP_REQUIRE(p->row_w && p->row_b && p->col_w && p->col_b, MOP_EINVAL, "lowrank head tensors missing");
   } else {
@@ -30,7 +33,7 @@ static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
     MOP_REQUIRE(!p->use_k3 || (p->mid3_w && p->mid3_b), MOP_EINVAL, "use_k3 set but mid3 tensors missing");
   }
   if (bwd) {
-    MOP_REQUIRE(p->dy && p->dqkv && p->dhead_part && p->dlogit_part, MOP_EINVAL, "backward buffers missing");
+    MOP_REQUIRE(p->dy && p->dqkv && p->dlogit_part && (p->dhead_part || p->gate_mode == MOP_GATE_CONST), MOP_EINVAL, "backward buffers missing");
     MOP_REQUIRE((p->q_scale == nullptr) || p->dscale_part, MOP_EINVAL, "dscale_part missing");
   }
   return MOP_OK;
@@ -45,9 +48,9 @@ static int edgewise_grid(const MopEdgewiseParams* p) {
 
 static ew::Layout edgewise_layout(const MopEdgewiseParams* p, int bwd) {
   ew::Layout L;
-  const bool dense = p->gate_mode == MOP_GATE_DENSE;
-  L.build(p->N, p->dk, p->V, p->Vp, dense ? 1 : p->gate_rank, dense ? p->hidden : 1, dense ? 1 : 0,
-          dense && p->use_k3 ? 1 : 0, bwd);
+  const bool dense = p->gate_mode == MOP_GATE_DENSE, cg = p->gate_mode == MOP_GATE_CONST;
+  L.build(p->N, p->dk, p->V, p->Vp, (dense || cg) ? 1 : p->gate_rank, dense ? p->hidden : 1, dense ? 1 : 0,
+          dense && p->use_k3 ? 1 : 0, bwd, cg ? p->hops : 0, cg ? 1 : 0);
   return L;
 }
 
@@ -59,6 +62,7 @@ extern "C" {
 
 size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
   if (!p) return 0;
+  if (p->gate_mode == MOP_GATE_CONST) return 0;
   const bool dense = p->gate_mode == MOP_GATE_DENSE;
   return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3);
 }

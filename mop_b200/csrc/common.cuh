@@ -62,4 +62,40 @@ __device__ __forceinline__ float dgelu_tanh_(float x) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- attention dropout: counter-based keep mask ----------------------------------------------------------------------------
+// keep(b, h, i, j) is a pure function of (seed, offset, b*H + h, i, j): every kernel (forward, dQ, dK/dV, tensor-core or
+// fp32-math) regenerates the same mask from the two 64-bit numbers the caller passes, nothing is stored.  A 32-bit avalanche
+// hash (xorshift-multiply, "lowbias32") is applied to a per-row key and the column; P(keep) = 1 - p to 2^-32.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+struct Dropout {
+  uint32_t thresh;   // keep iff hash >= thresh
+  uint32_t key;
+  float inv_keep;    // 1 / (1 - p); 0 for p >= 1
+  int on;
+};
+__host__ __device__ inline Dropout make_dropout(float p, uint64_t seed, uint64_t offset) {
+  Dropout d;
+  d.on = p > 0.f ? 1 : 0;
+  const double t = (double)p * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  d.inv_keep = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  d.key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) ^ mix32((uint32_t)offset + 0x9E3779B9u * (uint32_t)(offset >> 32) + 0x7F4A7C15u)));
+  return d;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_row_key(const Dropout& d, uint32_t bh, uint32_t i) {
+  return mix32(mix32(d.key ^ (bh * 0x85EBCA6Bu)) + i * 0xC2B2AE35u);
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t row_key, uint32_t j, uint32_t thresh) {
+  return mix32(row_key ^ (j * 0x9E3779B9u)) >= thresh;
+}
+// the factor an attention probability is multiplied by: 0 or 1 / (1 - p)
+__host__ __device__ __forceinline__ float dropout_factor(const Dropout& d, uint32_t row_key, uint32_t j) {
+  return dropout_keep(row_key, j, d.thresh) ? d.inv_keep : 0.f;
+}
+
 }  // namespace mop

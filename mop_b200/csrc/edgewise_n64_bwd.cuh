@@ -652,20 +652,23 @@ edgewise_bwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         }
       }
     };
-    for (int k = 0; k < V; ++k) {
-      float x[8], pk[8], cd[8];
-      tmem_ld_16x256b_x2(tcol(tS + k), cd);
+    for (int k = 0; k < V; ++k) {   // row dots of every view first: ONE exchange between the four column blocks
+      float x[8], pk[8];
       load_dA(k, x, pk);
       float lo = 0.f, hi = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) { if (e & 2) hi = fmaf(x[e], pk[e], hi); else lo = fmaf(x[e], pk[e], lo); }
       lo = quad_sum(lo);
       hi = quad_sum(hi);
-      float (*rd)[64] = sm.red[k & 1];   // two buffers: a warp is at most one barrier ahead of its three partners
-      if ((lane & 3) == 0) { rd[cb][row_lo] = lo; rd[cb][row_hi] = hi; }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + sp) : "memory");   // the four warps (one per column block) that share these rows
-      const float dlo = (rd[0][row_lo] + rd[1][row_lo]) + (rd[2][row_lo] + rd[3][row_lo]);
-      const float dhi = (rd[0][row_hi] + rd[1][row_hi]) + (rd[2][row_hi] + rd[3][row_hi]);
+      if ((lane & 3) == 0) { sm.red[k][cb][row_lo] = lo; sm.red[k][cb][row_hi] = hi; }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + sp) : "memory");   // the four warps (one per column block) that share these rows
+    for (int k = 0; k < V; ++k) {
+      float x[8], pk[8], cd[8];
+      tmem_ld_16x256b_x2(tcol(tS + k), cd);
+      load_dA(k, x, pk);
+      const float dlo = (sm.red[k][0][row_lo] + sm.red[k][1][row_lo]) + (sm.red[k][2][row_lo] + sm.red[k][3][row_lo]);
+      const float dhi = (sm.red[k][0][row_hi] + sm.red[k][1][row_hi]) + (sm.red[k][2][row_hi] + sm.red[k][3][row_hi]);
       const float rlo = sm.rt[k][row_lo], rhi = sm.rt[k][row_hi];
       const float2 c01 = *reinterpret_cast<const float2*>(&sm.ct[k][c0 + cq]), c23 = *reinterpret_cast<const float2*>(&sm.ct[k][c0 + 8 + cq]);
       const float ctv[4] = {c01.x, c01.y, c23.x, c23.y};

@@ -25,6 +25,8 @@ constexpr int kMaxHidden = 16;
 // Per-CTA scratch layout, in floats.  Shared by host (sizing) and device.
 struct Layout {
   int N, dk, V, Vp, C, r, hid, dense, k3, bwd;
+  int hops;    // length of the chain product: V for the Edgewise modes, `hops` for the fixed-gate multi-hop mode (views 0,1,1,..)
+  int cgate;   // fixed scalar gates (MultiHopMSA): no gate head, no reverse chain
   size_t N2, Nd;
   int n_maps;
   // map indices
@@ -34,15 +36,17 @@ struct Layout {
   size_t o_dyf, o_dv1, o_dvl, o_tt, o_dqa, o_dka, o_da, o_db, o_drho, o_dkap, o_z;
   size_t total;
 
-  __host__ __device__ void build(int N_, int dk_, int V_, int Vp_, int r_, int hid_, int dense_, int k3_, int bwd_) {
+  __host__ __device__ void build(int N_, int dk_, int V_, int Vp_, int r_, int hid_, int dense_, int k3_, int bwd_, int hops_ = 0,
+                                 int cgate_ = 0) {
     N = N_; dk = dk_; V = V_; Vp = Vp_; r = r_; hid = hid_; dense = dense_; k3 = k3_; bwd = bwd_;
+    hops = hops_ > 0 ? hops_ : V_; cgate = cgate_;
     C = 2 * V + 2;
     N2 = (size_t)N * N; Nd = (size_t)N * dk;
     int m = 0;
     mS = m; m += V;
     mA = m; m += V;
-    mP = m; m += V - 1;
-    mR = m; m += V - 1;
+    mP = m; m += hops - 1;
+    mR = m; m += cgate ? 0 : V - 1;
     mM = m; m += 1;
     mG = m; m += 4;
     mZ1 = mH2 = mDH2 = -1;
@@ -100,10 +104,11 @@ struct Ctx {
   __device__ float* map(int idx) const { return ws + L.o_maps + (size_t)idx * L.N2; }
   __device__ float* S(int i) const { return map(L.mS + i); }
   __device__ float* A(int i) const { return map(L.mA + i); }
-  // P(k) = A_1..A_{k+1}, R(k) = A_V..A_{k+1}
+  // P(k) = A_{cv(0)}..A_{cv(k)}, R(k) = A_V..A_{k+1}; cv(k) = view at chain position k
+  __device__ int cv(int k) const { return k < L.V ? k : L.V - 1; }
   __device__ float* P(int k) const { return k == 0 ? A(0) : map(L.mP + k - 1); }
   __device__ float* R(int k) const { return k == L.V - 1 ? A(L.V - 1) : map(L.mR + k); }
-  __device__ float* F() const { return P(L.V - 1); }
+  __device__ float* F() const { return P(L.hops - 1); }
   __device__ float* Rf() const { return R(0); }
   __device__ float* Gm(int t) const { return map(L.mG + t); }
   __device__ float* qb(int i) const { return ws + L.o_qb + (size_t)(L.Vp == 1 ? 0 : i) * L.Nd; }
@@ -251,9 +256,15 @@ __device__ void forward_maps(Ctx& c) {
     simt::gemm(c.S(i), N, c.qb(i), dk, 1, c.kb(i), 1, dk, N, N, dk, c.cvec(i), nullptr, s, false, c.gs);
     simt::softmax_rows(c.A(i), c.S(i), N, N);
   }
-  for (int k = 1; k < V; ++k) simt::gemm(c.P(k), N, c.P(k - 1), N, 1, c.A(k), N, 1, N, N, N, nullptr, nullptr, 1.f, false, c.gs);
-  for (int k = V - 2; k >= 0; --k) simt::gemm(c.R(k), N, c.R(k + 1), N, 1, c.A(k), N, 1, N, N, N, nullptr, nullptr, 1.f, false, c.gs);
-  if (L.dense) dense_head_forward(c); else lowrank_head_forward(c);
+  for (int k = 1; k < L.hops; ++k) simt::gemm(c.P(k), N, c.P(k - 1), N, 1, c.A(c.cv(k)), N, 1, N, N, N, nullptr, nullptr, 1.f, false, c.gs);
+  if (L.cgate) {   // fixed scalar gates (MultiHopMSA, attention_variants.py:207-217): no gate head, no reverse chain
+    for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads)
+      for (int t = 0; t < 4; ++t) c.Gm(t)[idx] = p.const_gates[t];
+    __syncthreads();
+  } else {
+    for (int k = V - 2; k >= 0; --k) simt::gemm(c.R(k), N, c.R(k + 1), N, 1, c.A(k), N, 1, N, N, N, nullptr, nullptr, 1.f, false, c.gs);
+    if (L.dense) dense_head_forward(c); else lowrank_head_forward(c);
+  }
   // mix (attention_variants.py:537-547) then row softmax
   const float bn = p.beta_not / (float)max(1, V - 1);
   float* M = c.map(L.mM);
@@ -498,6 +509,7 @@ __device__ void dense_head_backward(const Ctx& c, float* dhead) {
 // grad of feature channel `ch` at pixel (i,j) (flat idx) for either head
 __device__ __forceinline__ float dfeat_at(const Ctx& c, int ch, int i, int j) {
   const auto& L = c.L;
+  if (L.cgate) return 0.f;
   if (L.dense) {
     size_t q = (size_t)i * L.N + j;
     float s = 0.f;
@@ -548,7 +560,7 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
       if (threadIdx.x == 0) p.dlogit_part[g] = (1.f - w) * tot;
     }
     // gate pre-activation grads dG_t
-    {
+    if (!L.cgate) {
       const float* Fm = c.F();
       for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) {
         float sum = 0.f, mx = -INFINITY, s0 = c.S(0)[idx];
@@ -562,7 +574,7 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
       __syncthreads();
     }
     float* dhead = p.dhead_part + (size_t)g * nhead;
-    if (L.dense) dense_head_backward(c, dhead); else lowrank_head_backward(c, dhead);
+    if (!L.cgate) { if (L.dense) dense_head_backward(c, dhead); else lowrank_head_backward(c, dhead); }
     // dF += (D g_chain + dfeat_{2V}) / (F + eps)
     {
       const float* Fm = c.F();
@@ -573,20 +585,23 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
       }
       __syncthreads();
     }
-    // F chain: F = A_1 .. A_V
+    // F chain: F = A_{cv(0)} .. A_{cv(hops-1)}   (a view that occupies several chain positions accumulates)
     {
       float* X = X0; float* Xn = X1;
-      for (int k = V - 1; k >= 1; --k) {
-        simt::gemm(c.map(L.mdA + k), N, c.P(k - 1), 1, N, X, N, 1, N, N, N, nullptr, nullptr, 1.f, false, gs);
-        simt::gemm(Xn, N, X, N, 1, c.A(k), 1, N, N, N, N, nullptr, nullptr, 1.f, false, gs);  // X A_k^T
+      unsigned written = 0;
+      for (int k = L.hops - 1; k >= 1; --k) {
+        const int vk = c.cv(k);
+        simt::gemm(c.map(L.mdA + vk), N, c.P(k - 1), 1, N, X, N, 1, N, N, N, nullptr, nullptr, 1.f, (written >> vk) & 1u, gs);
+        written |= 1u << vk;
+        simt::gemm(Xn, N, X, N, 1, c.A(vk), 1, N, N, N, N, nullptr, nullptr, 1.f, false, gs);  // X A_k^T
         float* t = X; X = Xn; Xn = t;
       }
       float* dA0 = c.map(L.mdA + 0);
-      for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) dA0[idx] = X[idx];
+      for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) dA0[idx] = ((written & 1u) ? dA0[idx] : 0.f) + X[idx];
       __syncthreads();
     }
     // R chain: R = A_V .. A_1 ; dR = dfeat_{2V+1} / (R + eps)
-    {
+    if (!L.cgate) {
       const float* Rm = c.Rf();
       for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) {
         int i = idx / N, j = idx % N;

@@ -145,6 +145,7 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetPa
   const int q0 = qb * TQ, rows = min(TQ, Tn - q0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = simt::kThreads / 32;
   const Mix mx = load_mix(p);
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const size_t BH = (size_t)p.B * p.H;
   const float* kc1 = ws + w.kc + (size_t)bh * Tn * dk;
   const float* kc2 = ws + w.kc + (BH + bh) * Tn * dk;
@@ -201,10 +202,11 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetPa
       const float m_old = t.m[r], m_new = fmaxf(m_old, vmax);
       const float corr = (m_new == -INFINITY) ? 1.f : expf(m_old - m_new);
       float sum = 0.f;
+      const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)(q0 + r));
       for (int j = lane; j < cols; j += 32) {
         float e = (m_new == -INFINITY) ? 0.f : expf(srow[j] - m_new);
-        srow[j] = e;
-        sum += e;
+        sum += e;   // denominator of the un-dropped row; the kept entries carry 1/(1-p)
+        srow[j] = drop.on ? e * dropout_factor(drop, rkey, (uint32_t)(k0 + j)) : e;
       }
       sum = warp_sum(sum);
       for (int d = lane; d < dk; d += 32) o[r * dk + d] *= corr;
@@ -227,7 +229,7 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopQuartetPa
 }
 
 // Recompute one causal tile for the backward: on return
-//   t.pp = P (probabilities), t.s1 = W1 = dn1/(sigma1+eps), t.s2 = W2, row accumulators g1/g2 += sum_j dn c,
+//   t.pp = M (.) P (probabilities times the dropout factor M: the operand of dV), t.s1 = W1 = dn1/(sigma1+eps), t.s2 = W2, row accumulators g1/g2 += sum_j dn c,
 //   and the two scalar partials (d mixture-logit / d quartet_scale) are added to sc[0], sc[1] (per thread).
 __device__ inline void recompute_tile(const MopQuartetParams& p, const Tiles& t, const Mix& mx, int b, int h, int q0, int rows,
                                       int k0, int cols, bool accumulate_rows, float* sc) {
@@ -236,15 +238,18 @@ __device__ inline void recompute_tile(const MopQuartetParams& p, const Tiles& t,
   simt::gemm(t.s1, TK, t.q, dk, 1, t.k1, 1, dk, rows, cols, dk, nullptr, nullptr, p.scale, false, *t.gs);
   if (mx.quart) simt::gemm(t.s2, TK, t.q2, dk, 1, t.k2, 1, dk, rows, cols, dk, nullptr, nullptr, p.scale, false, *t.gs);
   simt::gemm(t.pp, TK, t.dy, dk, 1, t.v, 1, dk, rows, cols, dk, nullptr, nullptr, 1.f, false, *t.gs);  // dP = dO V^T
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   for (int r = warp; r < rows; r += nw) {
     const float i1 = 1.f / (t.sig1[r] + mx.eps), i2 = mx.quart ? 1.f / (t.sig2[r] + mx.eps) : 0.f;
     float a1 = 0.f, a2 = 0.f;
+    const uint32_t rkey = dropout_row_key(drop, (uint32_t)(b * p.H + h), (uint32_t)(q0 + r));
     for (int j = lane; j < cols; j += 32) {
       const float c1 = t.s1[r * TK + j], c2 = mx.quart ? t.s2[r * TK + j] : 0.f;
       const float n1 = c1 * i1, n2 = c2 * i2;
       const float s = mix_score(p, mx, b, h, q0 + r, k0 + j, n1, n2);
       const float pr = (s == -INFINITY) ? 0.f : expf(s - t.lse[r]);
-      const float D = pr * (t.pp[r * TK + j] - t.dlt[r]);
+      const float mk = drop.on ? dropout_factor(drop, rkey, (uint32_t)(k0 + j)) : 1.f;
+      const float D = pr * (mk * t.pp[r * TK + j] - t.dlt[r]);
       float dn1 = D, dn2 = 0.f;
       if (mx.quart) {
         dn1 = D * ((1.f - mx.m) + mx.m * mx.gam * n2);
@@ -254,7 +259,7 @@ __device__ inline void recompute_tile(const MopQuartetParams& p, const Tiles& t,
       }
       a1 = fmaf(dn1, c1, a1);
       a2 = fmaf(dn2, c2, a2);
-      t.pp[r * TK + j] = pr;
+      t.pp[r * TK + j] = pr * mk;
       t.s1[r * TK + j] = dn1 * i1;
       if (mx.quart) t.s2[r * TK + j] = dn2 * i2;
     }

@@ -579,6 +579,8 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
     const float fa_ = mx.quart ? a1 * (1.f - mx.m) : a1, fb_ = mx.quart ? a1 * mx.m * mx.gam * a2 : 0.f;
     const float2 fA2 = make_float2(fa_, fa_), fB2 = make_float2(fb_, fb_), l2e2 = make_float2(kLog2e, kLog2e);
     float m_ref = -INFINITY, l_run = 0.f;   // m_ref in base-2 units
+    const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
+    const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
     TS_DECL
     for (int it = 0; it < ntiles; ++it) {
       const int k0 = it * 64;
@@ -652,6 +654,11 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
         }
         ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
         ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
+        if (drop.on) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (!dropout_keep(rkey, (uint32_t)(k0 + 8 * c + e), drop.thresh)) pv[e] = 0.f;
+        }
         *reinterpret_cast<uint4*>(sm.P + c * (128 * 16) + tid * 16) = pack8(pv);
       }
       l_run += (ps0.x + ps0.y) + (ps1.x + ps1.y);
@@ -663,7 +670,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
     if (tid == 0) TS_DUMP("softmax", ntiles, 6);
     mbar_wait(&sm.bar_pv, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
-    const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    const float il = (drop.on ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
     float* y32 = p.y_f32 ? p.y_f32 + at(p, b, row_ok ? gi : 0, h) : nullptr;
 #pragma unroll
@@ -779,6 +786,8 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   const float* st = p.stats + (((size_t)b * p.H + h) * T + (row_ok ? gi : T - 1)) * 3;
   const float s1v = st[0], s2v = st[1], lse = st[2];
   const float i1 = 1.f / (s1v + mx.eps), i2 = mx.quart ? 1.f / (s2v + mx.eps) : 0.f;
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
+  const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
   float dlt = 0.f;
   if (row_ok) {
     const __nv_bfloat16* yr = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, gi, h);
@@ -840,6 +849,10 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
       if (mx.quart) tmem_ld_32x32b_x16(tx + 64 + col, v2);
       tmem_ld_32x32b_x16(tx + 128 + col, dp);
       tmem_ld_wait();
+      if (drop.on) {   // D = P (.) (M (.) dP - delta), M = dropout factor of the forward
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dp[e] *= dropout_factor(drop, rkey, (uint32_t)(k0 + col + e));
+      }
       if (!HAS_MASK) {
         const int lim = gi - k0 - col;   // causal: element e of this chunk is masked when e > lim (diagonal tiles only)
         const bool diag = k0 + 63 > q0;
@@ -1050,6 +1063,7 @@ static __global__ void __launch_bounds__(256) gmat_kernel(MopQuartetParams p, Ws
 struct __align__(128) SmemK {
   unsigned char K1[kT128], K2[kT128], V[kT128], PT[2][kT128], W1T[2][kT128], W2T[2][kT128];   // P^T / W^T: one buffer per tile parity
   unsigned char Q[3][kT64], Q2[3][kT64], dO[3][kT64];   // three-stage ring of query-side tiles
+  uint32_t rk[3][64];    // per query of the tile: dropout row key
   float vec[3][8][64];   // per query of the tile: sigma1 -> 1/(sigma1+eps), sigma2 -> .., lse, delta | packed-math constants A1, B1, L, -delta
   uint64_t bar;      // MMA completion (M kc epilogue)
   uint64_t bar_in;   // S1^T, S2^T, dP^T of a tile complete (three issuing threads)
@@ -1074,6 +1088,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();   // the 128-byte-swizzled TMA tiles need a 1024-byte aligned base
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, dk = p.dk, T = p.T, nkb = w.nqb;
   const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb, b = bh / p.H, h = bh % p.H;   // early key blocks (most work) first
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const int k0 = kb * 128, gj = k0 + t;
   const bool key_ok = gj < T;
   const int dks = (dk + 15) >> 4;
@@ -1107,6 +1122,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
       cp_async4(&sm.vec[buf][1][tid], stats + (size_t)i * 3 + 1);
       cp_async4(&sm.vec[buf][2][tid], stats + (size_t)i * 3 + 2);
       cp_async4(&sm.vec[buf][3][tid], delta + i);
+      if (drop.on) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
     }
     cp_async_commit();
   };
@@ -1161,6 +1177,14 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
       if (mx.quart) tmem_ld_32x32b_x16(tl + 64 + colb, v2);
       tmem_ld_32x32b_x16(tl + 128 + colb, dp);
       tmem_ld_wait();
+      uint32_t km = 0xFFFFu;   // keep bits of this thread's 16 (query) columns
+      if (drop.on) {
+        km = 0u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) km |= (dropout_keep(sm.rk[buf][colb + e], (uint32_t)gj, drop.thresh) ? 1u : 0u) << e;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dp[e] = ((km >> e) & 1u) ? dp[e] * drop.inv_keep : 0.f;
+      }
       if (!HAS_MASK) {   // packed fp32 math (zero-filled query rows >= T contribute nothing; causal zeroing on diagonal tiles)
         const bool diag = q0 < k0 + 127;
         const int lim = gj - q0 - colb;   // query column x of this chunk is masked when x < lim
@@ -1199,6 +1223,10 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
         w2[e] = o.dn2 * i2;
       }
       const int ch = colb >> 3;
+      if (drop.on) {   // dV = (M (.) P)^T dO
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pt[e] = ((km >> e) & 1u) ? pt[e] * drop.inv_keep : 0.f;
+      }
       *reinterpret_cast<uint4*>(sm.PT[par] + ch * (128 * 16) + t * 16) = pack8(pt);   // free: the outputs of tile it-2 completed before
       *reinterpret_cast<uint4*>(sm.PT[par] + (ch + 1) * (128 * 16) + t * 16) = pack8(pt + 8);   // the barrier of tile it-1
       *reinterpret_cast<uint4*>(sm.W1T[par] + ch * (128 * 16) + t * 16) = pack8(w1);

@@ -72,6 +72,7 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopSdpaParam
   const int q0 = qb * TQ;
   const int rows = min(TQ, p.Nq - q0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = simt::kThreads / 32;
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const T* qp = reinterpret_cast<const T*>(p.q) + (int64_t)b * p.q_sb + (int64_t)h * p.q_sh;
   const T* kp = reinterpret_cast<const T*>(p.k) + (int64_t)b * p.k_sb + (int64_t)h * p.k_sh;
   const T* vp = reinterpret_cast<const T*>(p.v) + (int64_t)b * p.v_sb + (int64_t)h * p.v_sh;
@@ -100,10 +101,11 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopSdpaParam
       float m_new = fmaxf(m_old, mx);
       float corr = (m_new == -INFINITY) ? 1.f : expf(m_old - m_new);
       float sum = 0.f;
+      const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)(q0 + r));
       for (int j = lane; j < cols; j += 32) {
         float e = (m_new == -INFINITY) ? 0.f : expf(srow[j] - m_new);
-        srow[j] = e;
-        sum += e;
+        sum += e;   // the softmax denominator is that of the un-dropped row; 1/(1-p) rides on the kept entries
+        srow[j] = drop.on ? e * dropout_factor(drop, rkey, (uint32_t)(k0 + j)) : e;
       }
       sum = warp_sum(sum);
       for (int d = lane; d < dk; d += 32) t.o[r * dk + d] *= corr;
@@ -125,7 +127,7 @@ static __global__ void __launch_bounds__(simt::kThreads) fwd_kernel(MopSdpaParam
 
 // Recompute P (into t.s) and dS (into t.s, in place) for the tile (q0.., k0..).
 // Needs t.q, t.k, t.v, t.aux = dO tile, t.l = lse rows, t.dlt = delta rows.
-// After the call: P is gone, t.s = dS; `p_keep` (TQ*TK floats) receives P if non-null.
+// After the call: t.s = dS = P (.) (M (.) dP - delta); `p_keep` (TQ*TK floats) holds M (.) P, the factor of dV (M = dropout factor).
 __device__ inline void recompute_tile(const MopSdpaParams& p, const Tiles& t, int b, int h, int q0, int rows, int k0,
                                       int cols, float* p_keep) {
   const int dk = p.dk;
@@ -142,9 +144,12 @@ __device__ inline void recompute_tile(const MopSdpaParams& p, const Tiles& t, in
   __syncthreads();
   // dP = dO V^T
   simt::gemm(t.s, TK, t.aux, dk, 1, t.v, 1, dk, rows, cols, dk, nullptr, nullptr, 1.f, false, *t.gs);
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   for (int idx = threadIdx.x; idx < rows * TK; idx += simt::kThreads) {
     int r = idx / TK, j = idx % TK;
-    t.s[idx] = (j < cols) ? p_keep[idx] * (t.s[idx] - t.dlt[r]) : 0.f;
+    const float mk = drop.on ? dropout_factor(drop, dropout_row_key(drop, (uint32_t)(b * p.H + h), (uint32_t)(q0 + r)), (uint32_t)(k0 + j)) : 1.f;
+    t.s[idx] = (j < cols) ? p_keep[idx] * (mk * t.s[idx] - t.dlt[r]) : 0.f;
+    p_keep[idx] *= mk;
   }
   __syncthreads();
 }

@@ -158,6 +158,8 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, con
     const int gi = q0 + tid;
     const bool row_ok = gi < Nq;
     const uint32_t tl = tb + ((uint32_t)(32 * warp) << 16);
+    const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
+    const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
     const float coef = EXTRA ? kLog2e : p.scale * kLog2e;   // exponent = score * coef - m_ref (base 2)
     float m_ref = -INFINITY, l_run = 0.f;
     TS_DECL
@@ -234,6 +236,11 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, con
         }
         ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
         ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
+        if (drop.on) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (!dropout_keep(rkey, (uint32_t)(k0 + 8 * c + e), drop.thresh)) pv[e] = 0.f;
+        }
         *reinterpret_cast<uint4*>(sm.P[it & 1] + c * (128 * 16) + tid * 16) = pack8(pv);
       }
       l_run += (ps0.x + ps0.y) + (ps1.x + ps1.y);
@@ -245,7 +252,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, con
     if (tid == 0) TS_DUMP("softmax", ntiles, 6);
     if (ntiles > 1) mbar_wait(&sm.bar_pv[ntiles & 1], (uint32_t)((ntiles - 2) >> 1) & 1u);
     if (ntiles > 0) { mbar_wait(&sm.bar_pv[(ntiles - 1) & 1], (uint32_t)((ntiles - 1) >> 1) & 1u); tc_fence_after(); }
-    const float il = 1.f / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    const float il = (drop.on ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((int64_t)b * Nq + (row_ok ? gi : 0)) * p.H + h) * dk;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -342,6 +349,8 @@ static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, 
     if (ntiles > 0) fetch(0, 0);
   }
   const float lse = p.lse[((int64_t)b * p.H + h) * Nq + (row_ok ? gi : Nq - 1)];
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
+  const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
   float dlt = 0.f;
   if (row_ok) {
     for (int d0 = 0; d0 < dk; d0 += 8) {
@@ -385,6 +394,10 @@ static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, 
       tmem_ld_32x32b_x16(tl + col, v1);
       tmem_ld_32x32b_x16(tl + 64 + col, dp);
       tmem_ld_wait();
+      if (drop.on) {   // dS = P (.) (M (.) dP - delta), M = dropout factor of the forward
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dp[e] *= dropout_factor(drop, rkey, (uint32_t)(k0 + col + e));
+      }
       if (!EXTRA) {
         // zero-filled key rows (>= Nk) contribute nothing to dS K, rows >= Nq are never written: only the causal diagonal masks
         const bool diag = p.causal && k0 + 63 > q0;
@@ -444,6 +457,7 @@ struct __align__(128) SmemK {
   unsigned char K[kT128], V[kT128], PT[kT128], WT[kT128];
   unsigned char Q[2][kT64], dO[2][kT64];
   float vec[2][2][64];   // per query of the tile: lse, delta
+  uint32_t rk[2][64];    // per query of the tile: dropout row key
   uint64_t bar;      // completion of S^T and dP^T (two issuing threads)
   uint64_t bar2;     // completion of dV += P^T dO and dK += dS^T Q (two issuing threads)
   uint64_t ld[2];    // TMA completion of query-side buffer 0 / 1
@@ -470,6 +484,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
   if (tid == 0) { mbar_init(&sm.bar, 2); mbar_init(&sm.bar2, 2); mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ldk, 1); fence_mbar_init(); }
   const float* lsep = p.lse + ((int64_t)b * p.H + h) * Nq;
   const float* dltp = delta + ((int64_t)b * p.H + h) * Nq;
+  const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const int qstart = p.causal ? min(k0, Nq) & ~63 : 0;   // queries i >= j only when causal
   const int ntiles = (Nq - qstart + 63) >> 6;
   tc_fence_before();
@@ -486,6 +501,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
       const int i = min(q0 + tid, Nq - 1);
       cp_async4(&sm.vec[buf][0][tid], lsep + i);
       cp_async4(&sm.vec[buf][1][tid], dltp + i);
+      if (drop.on) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
     }
     cp_async_commit();
   };
@@ -521,6 +537,14 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
       tmem_ld_32x32b_x16(tl + colb, v1);
       tmem_ld_32x32b_x16(tl + 64 + colb, dp);
       tmem_ld_wait();
+      uint32_t km = 0xFFFFu;   // keep bits of this thread's 16 (query) columns
+      if (drop.on) {
+        km = 0u;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) km |= (dropout_keep(sm.rk[buf][colb + e], (uint32_t)gj, drop.thresh) ? 1u : 0u) << e;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dp[e] = ((km >> e) & 1u) ? dp[e] * drop.inv_keep : 0.f;
+      }
       if (!EXTRA) {
         // zero-filled query rows (>= Nq) contribute nothing to P^T dO / dS^T Q, keys >= Nk are never written: only the diagonal masks
         const bool diag = p.causal && q0 < k0 + 127;
@@ -543,6 +567,10 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
           const int col = colb + e, gi = q0 + col;
           elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], sm.vec[buf][0][col], sm.vec[buf][1][col], gi >= Nq || !key_ok, pt[e], wt[e]);
         }
+      }
+      if (drop.on) {   // dV = (M (.) P)^T dO
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pt[e] = ((km >> e) & 1u) ? pt[e] * drop.inv_keep : 0.f;
       }
       const int ch = colb >> 3;
       *reinterpret_cast<uint4*>(sm.PT + ch * (128 * 16) + t * 16) = pack8(pt);

@@ -24,11 +24,13 @@ from . import whisper_mop as wm
 
 _CANONICAL = {
     "EdgewiseMSA": av.EdgewiseMSA, "EdgewiseGateHead": av.EdgewiseGateHead, "BaselineMSA": av.BaselineMSA,
+    "CrossViewMixerMSA": av.CrossViewMixerMSA, "MultiHopMSA": av.MultiHopMSA,
     "MSA": comp.MSA, "CausalSelfAttention": qp.CausalSelfAttention,
     "MultiheadSelfAttention": wm.MultiheadSelfAttention, "MultiheadCrossAttention": wm.MultiheadCrossAttention,
 }
-_EXPERIMENT_MODULES = ("cifar100_edgewise_gates", "cifar10_edgewise_gates", "experiments.cifar100_edgewise_gates",
-                       "experiments.cifar10_edgewise_gates")
+_EXPERIMENT_MODULES = tuple(pre + n for pre in ("", "experiments.") for n in (
+    "cifar100_edgewise_gates", "cifar10_edgewise_gates", "cifar100_crossview_mixer", "cifar10_crossview_mixer",
+    "cifar100_multihop_gates", "cifar10_multihop_gates"))
 
 
 def _compat(cls):

@@ -92,7 +92,11 @@ def _fill_edgewise(p, qkv, scales, logit, head, cfg):
     p.dtype = _dtype_code(qkv)
     p.impl = _IMPL[cfg["impl"]]
     p.B, p.H, p.N, p.dk, p.V, p.Vp = B, H, N, dk, cfg["n_views"], Vp
-    p.gate_mode = _lib.MOP_GATE_LOWRANK if cfg["gate_mode"] == "lowrank" else _lib.MOP_GATE_DENSE
+    p.gate_mode = {"lowrank": _lib.MOP_GATE_LOWRANK, "dense": _lib.MOP_GATE_DENSE, "const": _lib.MOP_GATE_CONST}[cfg["gate_mode"]]
+    if cfg["gate_mode"] == "const":
+        for i, gv in enumerate(cfg["const_gates"]):
+            p.const_gates[i] = float(gv)
+        p.hops = int(cfg["hops"])
     p.gate_rank = cfg["gate_rank"]
     p.hidden = cfg["hidden"]
     p.use_k3 = int(cfg["use_k3"])
@@ -104,7 +108,7 @@ def _fill_edgewise(p, qkv, scales, logit, head, cfg):
     p.chain_value_logit = _ptr(logit)
     if cfg["gate_mode"] == "lowrank":
         p.row_w, p.row_b, p.col_w, p.col_b = (_ptr(h) for h in head)
-    else:
+    elif cfg["gate_mode"] == "dense":
         it = iter(head)
         p.conv1_w, p.conv1_b = _ptr(next(it)), _ptr(next(it))
         if cfg["use_k3"]:
@@ -185,7 +189,7 @@ class _Edgewise(torch.autograd.Function):
             p.aux = _ptr(aux)
             nhead = lib.mop_edgewise_head_param_count(C.byref(p))
             G = B * H
-            dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev)
+            dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev) if nhead else None
             dlogit_part = torch.empty(G, dtype=torch.float32, device=dev)
             dscale_part = torch.empty(G, 3, V, dk, dtype=torch.float32, device=dev) if scales is not None else None
             p.dy, p.dqkv = _ptr(dy_c), _ptr(dqkv)
@@ -206,7 +210,7 @@ class _Edgewise(torch.autograd.Function):
         if keep_partials:
             last_partials["edgewise_dlogit"] = dlogit_part.detach().clone()
         dlogit = dlogit_part.sum().reshape(()).to(dts[3])
-        flat = dhead_part.sum(0)
+        flat = dhead_part.sum(0) if dhead_part is not None else None
         dheads, off = [], 0
         for shp, dt in zip(ctx.head_shapes, dts[4:]):
             n = math.prod(shp)
@@ -217,7 +221,8 @@ class _Edgewise(torch.autograd.Function):
 
 def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value_logit: torch.Tensor,
                        head: Dict[str, torch.Tensor], *, n_views: int, beta_not: float, gate_mode: str,
-                       gate_rank: int = 4, use_k3: bool = False, impl: Optional[str] = None) -> torch.Tensor:
+                       gate_rank: int = 4, use_k3: bool = False, impl: Optional[str] = None,
+                       const_gates=None, hops: Optional[int] = None) -> torch.Tensor:
     """Edgewise Mixture-of-Products attention core (reference attention_variants.py:500-562).
 
     qkv   ``[B, N, Vp, 3, H, dk]``: output of the shared qkv Linear (Vp=1, with
@@ -228,8 +233,15 @@ def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value
     Returns ``y [B, N, H, dk]``; differentiable w.r.t. qkv, the scales,
     ``chain_value_logit`` and every head tensor.
     """
-    if gate_mode not in ("lowrank", "dense"):
+    if gate_mode not in ("lowrank", "dense", "const"):
         raise ValueError(f"gate_mode {gate_mode!r}")
+    if gate_mode == "const":
+        # variant D (MultiHopMSA, reference :163-231): fixed scalar gates (and_, or_, not_, chain), chain A_1 A_2^(hops-1)
+        if const_gates is None or len(const_gates) != 4 or hops is None or hops < 2:
+            raise ValueError("gate_mode='const' needs const_gates=(and_, or_, not_, chain) and hops >= 2")
+        cfg = dict(n_views=int(n_views), beta_not=float(beta_not), gate_mode="const", gate_rank=1, use_k3=False, hidden=16, impl=impl,
+                   const_gates=tuple(float(g) for g in const_gates), hops=int(hops))
+        return _Edgewise.apply(cfg, qkv, q_scale, k_scale, v_scale, chain_value_logit)
     if qkv.dim() != 6 or qkv.shape[3] != 3:
         raise ValueError("qkv must be [B,N,Vp,3,H,dk]")
     dense_k3 = bool(use_k3) and gate_mode == "dense"  # use_k3 has no effect on the low-rank head (:273-278)
@@ -238,6 +250,34 @@ def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value
     cfg = dict(n_views=int(n_views), beta_not=float(beta_not), gate_mode=gate_mode, gate_rank=int(gate_rank),
                use_k3=dense_k3, hidden=int(hidden), impl=impl)
     return _Edgewise.apply(cfg, qkv, q_scale, k_scale, v_scale, chain_value_logit, *[head[k] for k in keys])
+
+
+# ----------------------------------------------------------------------------
+# attention dropout
+# ----------------------------------------------------------------------------
+# (seed, offset) of the most recent dropout-enabled forward (tests evaluate the oracle under the kernels' own mask)
+last_dropout: Dict[str, tuple] = {}
+
+
+def _draw_dropout(p: float):
+    """(p, seed, offset) for one attention call.  The pair comes from torch's CPU generator, so `torch.manual_seed` makes a run
+    reproducible; every kernel of the call (forward, dQ, dK/dV) regenerates the same keep mask from it.  Under CUDA-graph
+    capture the pair is baked into the captured launches (one fixed mask per replay)."""
+    if not (0.0 <= p <= 1.0):
+        raise ValueError(f"dropout probability has to be between 0 and 1, but got {p}")
+    if p == 0.0:
+        return (0.0, 0, 0)
+    seed, offset = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64).tolist()
+    return (float(p), int(seed), int(offset))
+
+
+def dropout_mask(BH: int, Nq: int, Nk: int, p: float, seed: int, offset: int, device="cuda") -> torch.Tensor:
+    """The factor (0 or 1/(1-p)) the attention kernels apply to P[bh, i, j] for (p, seed, offset): fp32 ``[BH, Nq, Nk]``."""
+    lib = _lib.load()
+    out = torch.empty(BH, Nq, Nk, dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.mop_dropout_mask(_ptr(out), BH, Nq, Nk, float(p), int(seed), int(offset), _stream()), "mop_dropout_mask")
+    return out
 
 
 # ----------------------------------------------------------------------------
@@ -275,6 +315,7 @@ def _fill_sdpa(p, q, k, v, causal, bias, zero_mask, cfg):
     if zero_mask is not None:
         p.zero_mask = _ptr(zero_mask)
         p.zm_sb, p.zm_sh, p.zm_sq, p.zm_sk = _bstrides(zero_mask)
+    p.dropout_p, p.dropout_seed, p.dropout_offset = cfg.get("dropout", (0.0, 0, 0))
 
 
 class _Sdpa(torch.autograd.Function):
@@ -330,8 +371,8 @@ class _Sdpa(torch.autograd.Function):
 
 def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = False,
          bias: Optional[torch.Tensor] = None, zero_mask: Optional[torch.Tensor] = None,
-         impl: Optional[str] = None) -> torch.Tensor:
-    """softmax(q k^T / sqrt(dk) [zero_mask==0 -> -inf] [causal] [+ bias]) v.
+         dropout_p: float = 0.0, impl: Optional[str] = None) -> torch.Tensor:
+    """dropout_p(softmax(q k^T / sqrt(dk) [zero_mask==0 -> -inf] [causal] [+ bias])) v.
 
     q ``[B,Nq,H,dk]``, k/v ``[B,Nk,H,dk]`` (any batch/token/head strides, last
     dim contiguous - e.g. slices of a fused qkv projection).  ``bias`` and
@@ -346,7 +387,10 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool = Fa
         bias = _as4(bias.detach().float(), B, H, Nq, Nk, "bias")
     if zero_mask is not None:
         zero_mask = _as4(zero_mask.detach().float(), B, H, Nq, Nk, "zero_mask")
-    return _Sdpa.apply(dict(causal=bool(causal), impl=impl), q, k, v, bias, zero_mask)
+    drop = _draw_dropout(float(dropout_p))
+    if drop[0] > 0.0:
+        last_dropout["sdpa"] = drop
+    return _Sdpa.apply(dict(causal=bool(causal), impl=impl, dropout=drop), q, k, v, bias, zero_mask)
 
 
 # ----------------------------------------------------------------------------
@@ -366,6 +410,7 @@ def _fill_quartet(p, q, k, v, q2, k2, mixture, gamma, add_mask, cfg):
     if add_mask is not None:
         p.add_mask = _ptr(add_mask)
         p.am_sb, p.am_sh, p.am_sq, p.am_sk = _bstrides(add_mask)
+    p.dropout_p, p.dropout_seed, p.dropout_offset = cfg.get("dropout", (0.0, 0, 0))
 
 
 class _Quartet(torch.autograd.Function):
@@ -449,7 +494,7 @@ class _Quartet(torch.autograd.Function):
 
 
 def quartet_attention(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=None, *, eps: float = 1e-5,
-                      add_mask: Optional[torch.Tensor] = None, impl: Optional[str] = None) -> torch.Tensor:
+                      add_mask: Optional[torch.Tensor] = None, dropout_p: float = 0.0, impl: Optional[str] = None) -> torch.Tensor:
     """GPT Quartet causal attention core (reference quartet_attn_patch.py:88-121).
 
     q,k,v,(q2,k2) ``[B,T,H,dk]`` (the Linear outputs viewed as heads).  ``q2 is None`` selects the
@@ -461,7 +506,10 @@ def quartet_attention(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=Non
         if add_mask.requires_grad:
             raise NotImplementedError("gradient w.r.t. the additive attention mask is not provided")
         add_mask = _as4(add_mask.detach().float(), B, H, T, T, "attention_mask")
-    return _Quartet.apply(dict(eps=float(eps), impl=impl), q, k, v, q2, k2, mixture, quartet_scale, add_mask)
+    drop = _draw_dropout(float(dropout_p))
+    if drop[0] > 0.0:
+        last_dropout["quartet"] = drop
+    return _Quartet.apply(dict(eps=float(eps), impl=impl, dropout=drop), q, k, v, q2, k2, mixture, quartet_scale, add_mask)
 
 
 # ----------------------------------------------------------------------------

@@ -66,8 +66,7 @@ class CausalSelfAttention(nn.Module):
     def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, need_weights: bool = False):
         if need_weights:
             raise NotImplementedError("need_weights=True would materialise the [B,H,T,T] map the fused kernel avoids")
-        if self.training and self.attn_drop.p > 0.0:
-            raise NotImplementedError("attention dropout inside the fused kernel is not provided; use dropout=0.0")
+        drop_p = self.attn_drop.p if self.training else 0.0   # applied to the probabilities inside the kernels (:118-119)
         B, T, C = x.shape
         if T > self.config.block_size:
             raise ValueError("sequence longer than block_size")
@@ -75,7 +74,7 @@ class CausalSelfAttention(nn.Module):
         q, k, v = self.q_proj(x).view(shp), self.k_proj(x).view(shp), self.v_proj(x).view(shp)
         if self.config.use_quartet:
             y = MF.quartet_attention(q, k, v, self.q2_proj(x).view(shp), self.k2_proj(x).view(shp), self.mixture,
-                                     self.quartet_scale, eps=self.config.score_norm_eps, add_mask=attention_mask)
+                                     self.quartet_scale, eps=self.config.score_norm_eps, add_mask=attention_mask, dropout_p=drop_p)
         else:
-            y = MF.quartet_attention(q, k, v, eps=1e-5, add_mask=attention_mask)  # reference :110 hard-codes 1e-5
+            y = MF.quartet_attention(q, k, v, eps=1e-5, add_mask=attention_mask, dropout_p=drop_p)  # reference :110 hard-codes 1e-5
         return self.resid_drop(self.o_proj(y.reshape(B, T, C)))

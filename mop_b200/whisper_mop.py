@@ -15,9 +15,9 @@ import torch.nn as nn
 from . import functional as MF
 
 
-def _no_dropout(m):
-    if m.training and m.attn_drop.p > 0.0:
-        raise NotImplementedError("attention dropout inside the fused kernel is not provided; use dropout=0.0")
+def _drop_p(m) -> float:
+    """Probability of the attention dropout (reference :173, :217), applied to the probabilities inside the kernels."""
+    return m.attn_drop.p if m.training else 0.0
 
 
 class MultiheadSelfAttention(nn.Module):
@@ -36,11 +36,10 @@ class MultiheadSelfAttention(nn.Module):
         self.resid_drop = nn.Dropout(dropout)
 
     def forward(self, x: torch.Tensor, attn_bias: Optional[torch.Tensor] = None):
-        _no_dropout(self)
         B, T, D = x.shape
         shp = (B, T, self.n_head, self.head_dim)
         y = MF.sdpa(self.q_proj(x).view(shp), self.k_proj(x).view(shp), self.v_proj(x).view(shp),
-                    causal=self.causal, bias=attn_bias)
+                    causal=self.causal, bias=attn_bias, dropout_p=_drop_p(self))
         return self.resid_drop(self.o_proj(y.reshape(B, T, D)))
 
 
@@ -59,10 +58,9 @@ class MultiheadCrossAttention(nn.Module):
         self.resid_drop = nn.Dropout(dropout)
 
     def forward(self, x_q: torch.Tensor, x_kv: torch.Tensor, attn_mask: Optional[torch.Tensor] = None):
-        _no_dropout(self)
         B, Tq, Dq = x_q.shape
         Tk = x_kv.shape[1]
         H, dh = self.n_head, self.head_dim
         y = MF.sdpa(self.q_proj(x_q).view(B, Tq, H, dh), self.k_proj(x_kv).view(B, Tk, H, dh),
-                    self.v_proj(x_kv).view(B, Tk, H, dh), bias=attn_mask)
+                    self.v_proj(x_kv).view(B, Tk, H, dh), bias=attn_mask, dropout_p=_drop_p(self))
         return self.resid_drop(self.o_proj(y.reshape(B, Tq, Dq)))

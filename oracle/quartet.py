@@ -29,7 +29,7 @@ def _zscore(s, eps):
 
 def quartet_core(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=None, *,
                  eps: float = 1e-5, add_mask: Optional[torch.Tensor] = None,
-                 return_probs: bool = False):
+                 return_probs: bool = False, drop_mask: Optional[torch.Tensor] = None):
     """q,k,v,(q2,k2): [B,H,T,dk].  ``q2 is None`` selects the non-quartet branch.
 
     The non-quartet branch uses a hard-coded 1e-5 (:110) - pass ``eps=1e-5``.
@@ -48,6 +48,8 @@ def quartet_core(q, k, v, q2=None, k2=None, mixture=None, quartet_scale=None, *,
     if add_mask is not None:
         scores = scores + add_mask
     p = torch.softmax(scores, dim=-1)
+    if drop_mask is not None:   # attn_drop(P) with an explicit mask of factors 0 | 1/(1-p)  (quartet_attn_patch.py:118-119)
+        p = p * drop_mask
     y = p @ v
     return (y, p) if return_probs else y
 

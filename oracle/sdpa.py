@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 
 def sdpa_core(q, k, v, *, causal: bool = False, zero_mask: Optional[torch.Tensor] = None,
-              bias: Optional[torch.Tensor] = None, return_probs: bool = False):
+              bias: Optional[torch.Tensor] = None, return_probs: bool = False, drop_mask: Optional[torch.Tensor] = None):
     """softmax(q k^T / sqrt(dk) [masked] [+ bias]) v.
 
     Order of operations follows whisper_mop.py:163-175: scale, causal fill with
@@ -40,6 +40,8 @@ def sdpa_core(q, k, v, *, causal: bool = False, zero_mask: Optional[torch.Tensor
     if bias is not None:
         att = att + bias
     p = F.softmax(att, dim=-1)
+    if drop_mask is not None:   # attn_drop(P) with an explicit mask of factors 0 | 1/(1-p)  (whisper_mop.py:173, components.py:63)
+        p = p * drop_mask
     y = p @ v
     return (y, p) if return_probs else y
 

@@ -130,3 +130,70 @@ def test_patched_reference_unified_msa_e(patched):
     x = torch.randn(2, 24, 32)
     y_ref, y = ref_model(x), ours(x.cuda())
     assert max_abs(y, y_ref) <= 1e-5
+
+
+# ---- variants C and D against fixtures recorded from the reference (tests/golden/make_golden_cd.py) -----------------------------
+def _check_golden_module(m, case, call, tol=1e-5, ptol=2e-5):
+    from conftest import load_golden  # noqa: F401
+    ins = {k: v.cuda().requires_grad_(True) for k, v in case["inputs"].items()}
+    y = call(m, ins)
+    assert max_abs(y, case["y"]) <= tol * max(1.0, case["y"].abs().max().item())
+    y.backward(case["dy"].cuda())
+    for k, t in ins.items():
+        assert max_abs(t.grad, case["dinputs"][k]) <= tol * max(1.0, case["dinputs"][k].abs().max().item()), k
+    for k, p in m.named_parameters():
+        ref = case["dparams"][k]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert max_abs(g, ref) <= ptol * max(1.0, ref.abs().max().item()), k
+
+
+@pytest.mark.parametrize("name", ["crossview_default", "crossview_mix_t_mask", "crossview_dk56"])
+def test_crossview_mixer_matches_reference_golden(name):
+    from conftest import load_golden
+    from mop_b200 import CrossViewMixerMSA
+    case = load_golden(name)
+    m = CrossViewMixerMSA(case["dim"], heads=case["heads"], **case["kwargs"])
+    m.load_state_dict(case["state_dict"], strict=True)
+    mask = case["mask"]
+    _check_golden_module(m.cuda(), case, lambda mod, t: mod(t["x"], None if mask is None else mask.cuda()))
+
+
+@pytest.mark.parametrize("name", ["multihop_default", "multihop_gates_h4", "multihop_h2_chain"])
+def test_multihop_matches_reference_golden(name):
+    from conftest import load_golden
+    from mop_b200 import MultiHopMSA
+    case = load_golden(name)
+    m = MultiHopMSA(case["dim"], heads=case["heads"], **case["kwargs"])
+    m.load_state_dict(case["state_dict"], strict=True)
+    _check_golden_module(m.cuda(), case, lambda mod, t: mod(t["x"]))
+
+
+def test_unified_msa_modes_c_d_build_and_run():
+    from mop_b200 import UnifiedMSA
+    x = torch.randn(2, 16, 32, device="cuda")
+    for mode in ("C", "D"):
+        m = UnifiedMSA(mode, 32, heads=2).cuda()
+        assert m(x).shape == x.shape
+
+
+def test_multihop_bf16_storage_vs_oracle():
+    """Variant D on bf16 activations (fp32-math kernel, bf16 storage) against the fp64 oracle on the same rounded inputs."""
+    from mop_b200 import edgewise_attention
+    from oracle.variants_cd import multihop_core
+    from gpu_util import bf16_round
+    g = torch.Generator().manual_seed(9)
+    B, N, H, dk = 2, 64, 2, 32
+    qkv = bf16_round(torch.randn(B, N, 2, 3, H, dk, generator=g, dtype=torch.float64))
+    dy = bf16_round(torch.randn(B, N, H, dk, generator=g, dtype=torch.float64))
+    logit = torch.tensor(-1.0, dtype=torch.float64)
+    gates = dict(and_=0.8, or_=0.3, not_=0.2, chain=0.6)
+    qr = qkv.clone().requires_grad_(True); lr = logit.clone().requires_grad_(True)
+    t = lambda v, w: qr[:, :, v, w].permute(0, 2, 1, 3)
+    y_ref = multihop_core(t(0, 0), t(0, 1), t(0, 2), t(1, 0), t(1, 1), t(1, 2), lr, gates=gates, beta_not=0.5, hops=3).permute(0, 2, 1, 3)
+    gq, gl = torch.autograd.grad(y_ref, (qr, lr), dy)
+    qg = qkv.to("cuda", torch.bfloat16).requires_grad_(True); lg = logit.float().cuda().requires_grad_(True)
+    y = edgewise_attention(qg, None, None, None, lg, {}, n_views=2, beta_not=0.5, gate_mode="const",
+                           const_gates=(0.8, 0.3, 0.2, 0.6), hops=3)
+    y.backward(dy.to("cuda", torch.bfloat16))
+    assert rel_to_max(y, y_ref) <= 2e-2 and rel_to_max(qg.grad, gq) <= 2e-2
+    assert abs(lg.grad.item() - gl.item()) <= 2e-2 * abs(gl.item()) + 1e-3

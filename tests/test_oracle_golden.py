@@ -14,6 +14,7 @@ from conftest import GOLDEN, load_golden
 from oracle.edgewise import EdgewiseConfig, edgewise_msa, gate_bias_preset
 from oracle.quartet import quartet_module
 from oracle.sdpa import msa_module, whisper_cross_module, whisper_self_module
+from oracle.variants_cd import crossview_module, multihop_module
 
 TOL = 1e-11
 CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pt")) if "gate_presets" not in p)
@@ -36,6 +37,11 @@ def _run(case, ins, sd):
         am = case["add_mask"]
         return quartet_module(ins["x"], sd, case["n_head"], case["use_quartet"], case["eps"],
                               None if am is None else am.double())
+    if kind == "crossview":
+        m = case["mask"]
+        return crossview_module(ins["x"], sd, case["heads"], attn_mask=None if m is None else m.double(), **case["kwargs"])
+    if kind == "multihop":
+        return multihop_module(ins["x"], sd, case["heads"], **case["kwargs"])
     raise AssertionError(kind)
 
 
