@@ -37,11 +37,12 @@ import torch.nn.functional as F  # noqa: E402
 MODEL = dict(dim=224, depth=8, heads=4, n_classes=100, mlp_ratio=3.0, n_views=5, share_qkv=True, use_k3=True,
              gate_mode="lowrank", gate_rank=4, gate_init="mix5", drop_path=0.1)
 BATCH, IMG, PATCH, NTOK = 256, 32, 4, 64
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ewtc::edgewise_bwd2_kernel, B*H = 1024
-# problems) from the committed `ncu --set full` capture; algorithmic read bytes (Q, K, V, dy) are 29.4 MB, i.e. no re-reads
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ew64::edgewise_bwd3_kernel, B*H = 1024
+# problems) from the committed `ncu --set full` capture (a citation, not measured in this run): algorithmic read bytes are
+# 29.4 MB (Q, K, V, dy) + 17.8 MB (the forward's row statistics / feature means / gate factors) = 47.2 MB, i.e. no re-reads
 # (the 22 MB of dqkv written stay in L2 until after the launch).
-DOMINANT_KERNEL_DRAM_BYTES = 29555712 + 138496
-DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01e_ew64_bwd_ncu_full_raw.csv (ncu --set full, one launch)"
+DOMINANT_KERNEL_DRAM_BYTES = 47307520 + 1048832
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r02b_ew64_bwd3_ncu_full_raw.csv (ncu --set full, one launch; cited constant)"
 WORKLOAD = "ViTEdgewise E+ (dim224 depth8 heads4 V5 share_qkv use_k3 lowrank:mix5 r4), CIFAR-shaped 32x32, batch 256/GPU, fwd+bwd+AdamW"
 
 
@@ -269,14 +270,19 @@ def run_ours(args):
     # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -------------
     sampler = ClockSampler(local)
     MF.kernel_events.clear()
+    launches_per_step = None
     if graph is not None:
         # per-kernel CUDA events cannot live inside a replayed graph: time the attention kernels in 3 eager steps
-        # of the same model (same launches, same stream) right before the timed region
+        # of the same model (same launches, same stream) right before the timed region; the same steps count this
+        # repo's kernel launches per step (every ABI call of this model enqueues exactly one kernel)
         MF.kernel_timing = True
+        c0 = dict(MF.abi_calls)
         for _ in range(3):
+            flush.zero_()
             eager_step(static_x, static_y)
         torch.cuda.synchronize()
         MF.kernel_timing = False
+        launches_per_step = sum(MF.abi_calls[k] - c0.get(k, 0) for k in MF.abi_calls) // 3
     else:
         MF.kernel_timing = True
     calls0 = dict(MF.abi_calls)
@@ -300,9 +306,9 @@ def run_ours(args):
     MF.kernel_timing = False
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
     kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in MF.kernel_events.items()}
-    launches = sum(MF.abi_calls[k] - calls0[k] for k in calls0)
-    if graph is not None:   # replayed launches: 2 per attention layer (fwd + bwd) per step
-        launches = 2 * MODEL["depth"] * args.steps
+    launches = sum(MF.abi_calls[k] - calls0.get(k, 0) for k in MF.abi_calls)
+    if graph is not None:   # replayed: the launches of one step (counted above, eagerly) times the timed steps
+        launches = launches_per_step * args.steps
     impl_used = dict(MF.last_impl)
 
     # ---- end to end: host buffers in, loss out, wall clock ------------------------------------
@@ -335,6 +341,9 @@ def run_ours(args):
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_throughput(steps=4, warmup=1, sample_batch=64)
+        extras = {}
+        if world == 1 and not args.no_extras:
+            extras = extra_measurements(dev, flush, pk)
         line = {
             "metric": "vit_mop_train_images_per_sec", "value": world * BATCH / (step_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
@@ -356,9 +365,85 @@ def run_ours(args):
                          "attention_share_of_step": attn_ms / step_ms if step_ms else None},
             "cpu_baseline": cb,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if ddp:
         dist.destroy_process_group()
+
+
+def extra_measurements(dev, flush, pk):
+    """Secondary measurements of the same run (N = 1 only; all outside the timed region of the headline):
+    * `attention`: BASELINE.json's "MoP attention TFLOP/s" for every named shape - attention core through
+      the public functional API, CUDA events, L2 flushed, algorithmic FLOPs (bwd = 2 x fwd), fraction of the measured burst
+      bf16 peak (kernels timed in isolation);
+    * `variant_dense_k3`: the E+ model with `gate_mode="dense", use_k3=True` (SURVEY M2: the low-rank head ignores use_k3), eager;
+    * `gpu_reference_eager`: the UNMODIFIED reference modules (baseline/_ref) run eagerly on this GPU - the informative GPU baseline."""
+    import mop_b200
+    out = {}
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    try:
+        import attn_microbench as mb
+        it = 6
+        rows = [mb.edgewise_case("M1/M2 Edgewise E core (B=256,H=4,N=64,dk=56,V=5)", 256, 4, 64, 56, 5, 4, None, it, flush),
+                mb.edgewise_case("M3 Edgewise ViT-B/16 core (B=256,H=12,N=196,dk=64,V=5)", 256, 12, 196, 64, 5, 4, "tcgen05", 3, flush),
+                mb.quartet_case("M4 Quartet GPT-1024 (B=16,H=12)", 16, 12, 1024, 64, "tcgen05", it, flush),
+                mb.quartet_case("M4 Quartet GPT-4096 (B=4,H=12)", 4, 12, 4096, 64, "tcgen05", it, flush),
+                mb.sdpa_case("M1 MSA model A (B=256,H=4,N=64,dk=56)", 256, 4, 64, 56, False, "tcgen05", it, flush),
+                mb.sdpa_case("M5 Whisper encoder self-attention (B=8,H=16,N=1500)", 8, 16, 1500, 64, False, "tcgen05", it, flush)]
+        for r in rows:
+            r["frac_of_peak_fwd"] = r["fwd_tflops"] / pk["bf16_burst"]
+            r["frac_of_peak_fwd_bwd"] = r["fwd_bwd_tflops"] / pk["bf16_burst"]
+            for k in ("dtype", "B", "H", "N", "dk", "V", "r", "causal", "op"):
+                r.pop(k, None)
+        out["attention"] = {"peak_tflops": pk["bf16_burst"], "peak": "measured burst bf16 (kernels timed alone)", "l2": "flushed",
+                            "flops": "algorithmic, dense contractions only, bwd = 2 x fwd", "shapes": rows}
+    except Exception as e:   # never lose the headline line to a secondary measurement
+        out["attention"] = {"error": repr(e)[:200]}
+
+    def time_steps(model, autocast, steps, warm):
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
+        x = torch.randn(BATCH, 3, IMG, IMG, device=dev)
+        y = torch.randint(0, MODEL["n_classes"], (BATCH,), device=dev)
+        ts = []
+        for i in range(warm + steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                loss = F.cross_entropy(model(x), y)
+            loss.backward()
+            opt.step()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+    try:
+        kw = dict(MODEL, gate_mode="dense")
+        torch.manual_seed(0)
+        m = mop_b200.ViTEdgewise(num_tokens=NTOK, patch=PATCH, compat_experiments_init=False, **kw).to(dev).train()
+        ms = time_steps(m, True, 3, 2)
+        out["variant_dense_k3"] = {"model": "E+ with gate_mode=dense, use_k3=True (4,116,840 parameters)", "ms_per_step": ms,
+                                   "images_per_sec": BATCH / (ms * 1e-3), "step_launch": "eager",
+                                   "attention_impl": "fp32-math kernels on bf16 storage (the dense 3x3 gate head has no tensor-core path)"}
+        del m
+    except Exception as e:
+        out["variant_dense_k3"] = {"error": repr(e)[:200]}
+    try:
+        from baseline.ref_models import reference_vit_edgewise
+        res = {}
+        for name, ac in (("bf16_autocast", True), ("fp32_tf32", False)):
+            torch.manual_seed(0)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            m = reference_vit_edgewise(num_tokens=NTOK, patch=PATCH, **MODEL).to(dev).train()
+            ms = time_steps(m, ac, 3, 2)
+            res[name] = {"ms_per_step": ms, "images_per_sec": BATCH / (ms * 1e-3)}
+            del m
+        out["gpu_reference_eager"] = dict(res, note="unmodified reference modules (baseline/_ref) run eagerly on this GPU, same model / batch")
+    except Exception as e:
+        out["gpu_reference_eager"] = {"unavailable": repr(e)[:200]}
+    return out
 
 
 def main():
@@ -368,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the attention-shape table, the dense+k3 variant and the reference-eager-on-GPU arm")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,7 +64,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     qtc::prep_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws);
     qtc::acc_to_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(ws, w.gacc, w.gram);
   }
-  const bool hm = p->add_mask != nullptr;
+  const bool hm = p->add_mask != nullptr, drop = p->dropout_p > 0.f;   // compiled with / without the mask and the dropout code
   // TMA tensor maps: activations [B,T,H,dk] (contiguous) and the centred keys in the workspace ([nm*B*H, T, 1, 64])
   const int64_t sT = (int64_t)p->H * p->dk, sB = (int64_t)p->T * sT;
   CUtensorMap tmQ, tmQ2, tmKc, tmV;
@@ -73,11 +73,14 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   if ((rc = make_tile_map_sw(&tmKc, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
   if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
   if (!bwd) {
-    if ((rc = allow_smem(hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>, smem_f))) return rc;
-    (hm ? qtc::fwd_kernel<true> : qtc::fwd_kernel<false>)<<<BH * w.nqb, 192, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
+    auto kf = hm ? (drop ? qtc::fwd_kernel<true, true> : qtc::fwd_kernel<true, false>) : (drop ? qtc::fwd_kernel<false, true> : qtc::fwd_kernel<false, false>);
+    if ((rc = allow_smem(kf, smem_f))) return rc;
+    kf<<<BH * w.nqb, 192, smem_f, st>>>(*p, w, ws, tmQ, tmQ2, tmKc, tmV);
   } else {
-    if ((rc = allow_smem(hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>, smem_q))) return rc;
-    if ((rc = allow_smem(hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>, smem_k))) return rc;
+    auto kq = hm ? (drop ? qtc::bwd_dq_kernel<true, true> : qtc::bwd_dq_kernel<true, false>) : (drop ? qtc::bwd_dq_kernel<false, true> : qtc::bwd_dq_kernel<false, false>);
+    auto kk = hm ? (drop ? qtc::bwd_dkdv_kernel<true, true> : qtc::bwd_dkdv_kernel<true, false>) : (drop ? qtc::bwd_dkdv_kernel<false, true> : qtc::bwd_dkdv_kernel<false, false>);
+    if ((rc = allow_smem(kq, smem_q))) return rc;
+    if ((rc = allow_smem(kk, smem_k))) return rc;
     CUtensorMap tmdO, tmQs, tmQ2s, tmdOs, tmKcL, tmVL;   // dO (128-row box); 64-row boxes of q, q2, dO; 128-row boxes of kc, v
     if ((rc = make_tile_map_sw(&tmdO, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmQs, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
@@ -85,7 +88,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     if ((rc = make_tile_map_sw(&tmdOs, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
     if ((rc = make_tile_map_sw(&tmKcL, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-    (hm ? qtc::bwd_dq_kernel<true> : qtc::bwd_dq_kernel<false>)<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
+    kq<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
     const int nct = (p->T + 63) / 64, cpg = 4, groups = (nct + cpg - 1) / cpg;
     if (BH * w.nm >= 2 * sm_count() || groups == 1) {
       qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws, 1, nct);
@@ -94,7 +97,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
       qtc::gmat_kernel<<<BH * w.nm * groups, 256, 0, st>>>(*p, w, ws, groups, cpg);
       qtc::acc_to_tiles_kernel<<<BH * w.nm, 256, 0, st>>>(ws, w.macc, w.mmat);
     }
-    (hm ? qtc::bwd_dkdv_kernel<true> : qtc::bwd_dkdv_kernel<false>)<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws, tmQs, tmQ2s, tmdOs, tmKcL, tmVL);
+    kk<<<BH * w.nqb, 256, smem_k, st>>>(*p, w, ws, tmQs, tmQ2s, tmdOs, tmKcL, tmVL);
     qtc::finish_kernel<<<BH * w.nm * ((p->T + 63) / 64), 256, 0, st>>>(*p, w, ws);
   }
   MOP_CHECK_CUDA(cudaGetLastError());

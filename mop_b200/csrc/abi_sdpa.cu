@@ -41,12 +41,14 @@ int mop_sdpa_fwd(MopSdpaParams* p, void* stream) {
   if (tc_ok && p->impl != MOP_IMPL_SIMT) {
     const size_t smem_tc = sizeof(sdpa2::SmemF) + 128;
     const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
-    if ((rc = allow_smem(extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>, smem_tc))) return rc;
+    const bool drop = p->dropout_p > 0.f;   // kernels are compiled with and without the optional tensors / the dropout code
+    auto kf = extra ? (drop ? sdpa2::fwd_kernel<true, true> : sdpa2::fwd_kernel<true, false>) : (drop ? sdpa2::fwd_kernel<false, true> : sdpa2::fwd_kernel<false, false>);
+    if ((rc = allow_smem(kf, smem_tc))) return rc;
     CUtensorMap tmQ, tmK, tmV;
     if ((rc = make_tile_map_sw(&tmQ, p->q, p->B, p->Nq, p->H, p->dk, p->q_sb, p->q_sn, p->q_sh, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmK, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 64))) return rc;
     if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 64))) return rc;
-    (extra ? sdpa2::fwd_kernel<true> : sdpa2::fwd_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 192, smem_tc, st>>>(*p, tmQ, tmK, tmV);
+    kf<<<p->B * p->H * ((p->Nq + 127) / 128), 192, smem_tc, st>>>(*p, tmQ, tmK, tmV);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
@@ -78,8 +80,11 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
     cudaStream_t st2 = (cudaStream_t)stream;
     const size_t smem_q = sizeof(sdpa2::SmemQ) + 128, smem_k = sizeof(sdpa2::SmemK) + 128;
     const bool extra = p->bias != nullptr || p->zero_mask != nullptr;
-    if ((rc = allow_smem(extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>, smem_q))) return rc;
-    if ((rc = allow_smem(extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>, smem_k))) return rc;
+    const bool drop = p->dropout_p > 0.f;
+    auto kq = extra ? (drop ? sdpa2::bwd_dq_kernel<true, true> : sdpa2::bwd_dq_kernel<true, false>) : (drop ? sdpa2::bwd_dq_kernel<false, true> : sdpa2::bwd_dq_kernel<false, false>);
+    auto kk = extra ? (drop ? sdpa2::bwd_dkdv_kernel<true, true> : sdpa2::bwd_dkdv_kernel<true, false>) : (drop ? sdpa2::bwd_dkdv_kernel<false, true> : sdpa2::bwd_dkdv_kernel<false, false>);
+    if ((rc = allow_smem(kq, smem_q))) return rc;
+    if ((rc = allow_smem(kk, smem_k))) return rc;
     // TMA tensor maps: 128-row boxes for the stationary tiles, 64-row boxes for the streamed ones
     const int64_t sY = (int64_t)p->H * p->dk, sYb = (int64_t)p->Nq * sY;
     CUtensorMap tmQ, tmdO, tmK, tmV, tmQs, tmdOs, tmKL, tmVL;
@@ -91,8 +96,8 @@ int mop_sdpa_bwd(MopSdpaParams* p, void* stream) {
     if ((rc = make_tile_map_sw(&tmdOs, p->dy, p->B, p->Nq, p->H, p->dk, sYb, sY, p->dk, 64))) return rc;
     if ((rc = make_tile_map_sw(&tmKL, p->k, p->B, p->Nk, p->H, p->dk, p->k_sb, p->k_sn, p->k_sh, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->Nk, p->H, p->dk, p->v_sb, p->v_sn, p->v_sh, 128))) return rc;
-    (extra ? sdpa2::bwd_dq_kernel<true> : sdpa2::bwd_dq_kernel<false>)<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta, tmQ, tmdO, tmK, tmV);
-    (extra ? sdpa2::bwd_dkdv_kernel<true> : sdpa2::bwd_dkdv_kernel<false>)<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta, tmQs, tmdOs, tmKL, tmVL);
+    kq<<<p->B * p->H * ((p->Nq + 127) / 128), 256, smem_q, st2>>>(*p, delta, tmQ, tmdO, tmK, tmV);
+    kk<<<p->B * p->H * ((p->Nk + 127) / 128), 256, smem_k, st2>>>(*p, delta, tmQs, tmdOs, tmKL, tmVL);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

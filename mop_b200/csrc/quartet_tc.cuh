@@ -412,7 +412,7 @@ struct __align__(128) SmemF {
 #define MOP_QLAZY 8.f
 #endif
 constexpr float kLazy = MOP_QLAZY;   // the running maximum is raised only when a tile exceeds it by 2^kLazy
-template <bool HAS_MASK>
+template <bool HAS_MASK, bool DROP = false>
 static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                      const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmKc,
                                                      const __grid_constant__ CUtensorMap tmV) {
@@ -654,7 +654,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
         }
         ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
         ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
-        if (drop.on) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
+        if constexpr (DROP) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             if (!dropout_keep(rkey, (uint32_t)(k0 + 8 * c + e), drop.thresh)) pv[e] = 0.f;
@@ -670,7 +670,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopQuartetParams p, 
     if (tid == 0) TS_DUMP("softmax", ntiles, 6);
     mbar_wait(&sm.bar_pv, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
-    const float il = (drop.on ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    const float il = (DROP ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + at(p, b, row_ok ? gi : 0, h);
     float* y32 = p.y_f32 ? p.y_f32 + at(p, b, row_ok ? gi : 0, h) : nullptr;
 #pragma unroll
@@ -709,7 +709,7 @@ struct __align__(128) SmemQ {
   float gx[2][2][128];   // [warpgroup][map][row]: row-coefficient partial sums
   float red[16];
   uint64_t bar;      // MMA completion (Gram epilogue)
-  uint64_t bar_in;   // S1, S2, dP of a tile complete (three issuing threads)
+  uint64_t bar_in[2];   // S1, S2, dP of a tile complete (three issuing threads); one barrier per input buffer (tile parity)
   uint64_t bar_out;  // dQ1, dQ2 of a tile complete (two issuing threads)
   uint64_t ld[3];    // TMA completion of the ring stages
   uint64_t ldq;      // TMA completion of the query-side tiles
@@ -741,7 +741,7 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
 // Software pipeline: S1 / S2 / dP of tile t+1 are issued (three lanes) as soon as tile t's have completed, into the other input
 // buffer, so they run during tile t's element math; dQ += W K of tile t (two lanes) runs during tile t+1's element math (W has one
 // buffer per tile parity); one lane refills the three-stage key / value ring once dQ(t-1) is done.
-template <bool HAS_MASK>
+template <bool HAS_MASK, bool DROP = false>
 static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
                                                         const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
@@ -758,7 +758,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   const size_t BH = (size_t)p.B * p.H, stride = (size_t)p.H * dk;
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) {
-    mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in, 3); mbar_init(&sm.bar_out, 2);
+    mbar_init(&sm.bar, 1); mbar_init(&sm.bar_in[0], 3); mbar_init(&sm.bar_in[1], 3); mbar_init(&sm.bar_out, 2);
     mbar_init(&sm.ld[0], 1); mbar_init(&sm.ld[1], 1); mbar_init(&sm.ld[2], 1); mbar_init(&sm.ldq, 1);
     fence_mbar_init();
   }
@@ -832,14 +832,18 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
     } else {
       for (int ks = 0; ks < dks; ++ks) mma_ss(xc + 128, desc_k_sw(smem_u32(sm.dO), 16 * ks), desc_k_sw(smem_u32(sm.V[s]), 16 * ks), id, ks > 0 ? 1u : 0u);
     }
-    mma_commit(&sm.bar_in);
+    mma_commit(&sm.bar_in[tile & 1]);
   };
   const bool in_lane = tid == 0 || tid == 32 || tid == 64;
   if (in_lane) issue_in(0);
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * 64, par = it & 1;
     const uint32_t tx = tl + 192u * (uint32_t)par;   // this tile's input buffer
-    mbar_wait(&sm.bar_in, ph_in); ph_in ^= 1; tc_fence_after();
+    // Tile it+1's products are issued below, BEFORE the CTA barrier of this tile, so a barrier shared by all tiles could complete
+    // two phases while a late warp (slow prologue loads) had not yet waited for the first - the parity wait then blocks for
+    // ever (seen as a rare hang of whole sub-partitions).  One barrier per tile parity: the phase a warp waits for can be
+    // followed by at most one more before the CTA barrier of tile it+1, which needs that warp.
+    mbar_wait(&sm.bar_in[par], (uint32_t)(it >> 1) & 1u); tc_fence_after();
     if (in_lane && it + 1 < ntiles) issue_in(it + 1);   // the other input buffer was consumed before the barrier of tile it-1
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -849,7 +853,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
       if (mx.quart) tmem_ld_32x32b_x16(tx + 64 + col, v2);
       tmem_ld_32x32b_x16(tx + 128 + col, dp);
       tmem_ld_wait();
-      if (drop.on) {   // D = P (.) (M (.) dP - delta), M = dropout factor of the forward
+      if constexpr (DROP) {   // D = P (.) (M (.) dP - delta), M = dropout factor of the forward
 #pragma unroll
         for (int e = 0; e < 16; ++e) dp[e] *= dropout_factor(drop, rkey, (uint32_t)(k0 + col + e));
       }
@@ -1079,7 +1083,7 @@ struct __align__(128) SmemK {
 // The three accumulators leave room for one input buffer only, so the input products of tile t+1 are issued at the barrier of tile
 // t (ahead of the output products in the tensor pipe's queue); the output products of tile t run during tile t+1 (P^T / W^T have
 // one buffer per tile parity) and a lane refills the three-stage query ring once the outputs of tile t-1 are done.
-template <bool HAS_MASK>
+template <bool HAS_MASK, bool DROP = false>
 static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
                                                           const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
@@ -1122,7 +1126,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
       cp_async4(&sm.vec[buf][1][tid], stats + (size_t)i * 3 + 1);
       cp_async4(&sm.vec[buf][2][tid], stats + (size_t)i * 3 + 2);
       cp_async4(&sm.vec[buf][3][tid], delta + i);
-      if (drop.on) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
+      if constexpr (DROP) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
     }
     cp_async_commit();
   };
@@ -1178,7 +1182,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
       tmem_ld_32x32b_x16(tl + 128 + colb, dp);
       tmem_ld_wait();
       uint32_t km = 0xFFFFu;   // keep bits of this thread's 16 (query) columns
-      if (drop.on) {
+      if constexpr (DROP) {
         km = 0u;
 #pragma unroll
         for (int e = 0; e < 16; ++e) km |= (dropout_keep(sm.rk[buf][colb + e], (uint32_t)gj, drop.thresh) ? 1u : 0u) << e;
@@ -1223,7 +1227,7 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
         w2[e] = o.dn2 * i2;
       }
       const int ch = colb >> 3;
-      if (drop.on) {   // dV = (M (.) P)^T dO
+      if constexpr (DROP) {   // dV = (M (.) P)^T dO
 #pragma unroll
         for (int e = 0; e < 16; ++e) pt[e] = ((km >> e) & 1u) ? pt[e] * drop.inv_keep : 0.f;
       }

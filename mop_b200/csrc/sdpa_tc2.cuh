@@ -68,7 +68,7 @@ struct __align__(128) SmemF {
 // everything (~220 instructions per tile) was the bottleneck of the first pipelined version.  The running maximum is only
 // raised when a tile exceeds it by more than 2^8 (exponentials stay <= 256; fp32 sums and bf16 products keep their relative
 // precision), which removes nearly all rescales of O.
-template <bool EXTRA>
+template <bool EXTRA, bool DROP = false>
 static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                      const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -236,7 +236,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, con
         }
         ps0 = add2(ps0, add2(make_float2(pv[0], pv[1]), make_float2(pv[2], pv[3])));
         ps1 = add2(ps1, add2(make_float2(pv[4], pv[5]), make_float2(pv[6], pv[7])));
-        if (drop.on) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
+        if constexpr (DROP) {   // the row sum above is that of the un-dropped probabilities; 1/(1-p) is folded into the final 1/l
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             if (!dropout_keep(rkey, (uint32_t)(k0 + 8 * c + e), drop.thresh)) pv[e] = 0.f;
@@ -252,7 +252,7 @@ static __global__ void __launch_bounds__(192, 2) fwd_kernel(MopSdpaParams p, con
     if (tid == 0) TS_DUMP("softmax", ntiles, 6);
     if (ntiles > 1) mbar_wait(&sm.bar_pv[ntiles & 1], (uint32_t)((ntiles - 2) >> 1) & 1u);
     if (ntiles > 0) { mbar_wait(&sm.bar_pv[(ntiles - 1) & 1], (uint32_t)((ntiles - 1) >> 1) & 1u); tc_fence_after(); }
-    const float il = (drop.on ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
+    const float il = (DROP ? drop.inv_keep : 1.f) / l_run;   // fully masked row: 0/0 = NaN like the reference softmax
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((int64_t)b * Nq + (row_ok ? gi : 0)) * p.H + h) * dk;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -314,7 +314,7 @@ struct __align__(128) SmemQ {
 };
 
 // grid: B*H*ceil(Nq/128), 256 threads; TMEM 256 columns (S | dP | dQ): two CTAs per SM
-template <bool EXTRA>
+template <bool EXTRA, bool DROP = false>
 static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, float* delta, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
                                                         const __grid_constant__ CUtensorMap tmV) {
@@ -394,7 +394,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, 
       tmem_ld_32x32b_x16(tl + col, v1);
       tmem_ld_32x32b_x16(tl + 64 + col, dp);
       tmem_ld_wait();
-      if (drop.on) {   // dS = P (.) (M (.) dP - delta), M = dropout factor of the forward
+      if constexpr (DROP) {   // dS = P (.) (M (.) dP - delta), M = dropout factor of the forward
 #pragma unroll
         for (int e = 0; e < 16; ++e) dp[e] *= dropout_factor(drop, rkey, (uint32_t)(k0 + col + e));
       }
@@ -467,7 +467,7 @@ struct __align__(128) SmemK {
 
 // grid: B*H*ceil(Nk/128), 256 threads (thread per key row; two warpgroups split the 64 query columns); TMEM 256 columns
 // (S^T | dP^T | dV | dK): two CTAs per SM
-template <bool EXTRA>
+template <bool EXTRA, bool DROP = false>
 static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p, const float* delta, const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmK,
                                                           const __grid_constant__ CUtensorMap tmV) {
@@ -501,7 +501,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
       const int i = min(q0 + tid, Nq - 1);
       cp_async4(&sm.vec[buf][0][tid], lsep + i);
       cp_async4(&sm.vec[buf][1][tid], dltp + i);
-      if (drop.on) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
+      if constexpr (DROP) sm.rk[buf][tid] = dropout_row_key(drop, (uint32_t)bh, (uint32_t)i);
     }
     cp_async_commit();
   };
@@ -538,7 +538,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
       tmem_ld_32x32b_x16(tl + 64 + colb, dp);
       tmem_ld_wait();
       uint32_t km = 0xFFFFu;   // keep bits of this thread's 16 (query) columns
-      if (drop.on) {
+      if constexpr (DROP) {
         km = 0u;
 #pragma unroll
         for (int e = 0; e < 16; ++e) km |= (dropout_keep(sm.rk[buf][colb + e], (uint32_t)gj, drop.thresh) ? 1u : 0u) << e;
@@ -568,7 +568,7 @@ static __global__ void __launch_bounds__(256, 2) bwd_dkdv_kernel(MopSdpaParams p
           elem_x<EXTRA>(p, b, h, gi, gj, v1[e], dp[e], sm.vec[buf][0][col], sm.vec[buf][1][col], gi >= Nq || !key_ok, pt[e], wt[e]);
         }
       }
-      if (drop.on) {   // dV = (M (.) P)^T dO
+      if constexpr (DROP) {   // dV = (M (.) P)^T dO
 #pragma unroll
         for (int e = 0; e < 16; ++e) pt[e] = ((km >> e) & 1u) ? pt[e] * drop.inv_keep : 0.f;
       }

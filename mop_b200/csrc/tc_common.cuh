@@ -27,7 +27,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // release.cta: t
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap after ~2 s of SM clock instead.
+// Bounded wait: a lost arrive must never hang the GPU (gpurun strike) - trap after ~10 s of WALL time instead (%globaltimer;
+// an SM-cycle bound of 2 s fired spuriously when the context shared the GPU with another process right after box start).
 __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -39,11 +40,18 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 static __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
+  const long long c0 = clock64();
   while (!mbar_try(a, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mop_b200: mbarrier wait timed out (block %d thread %d, barrier at shared offset %u, parity %u)\n", blockIdx.x, threadIdx.x, a, parity);
+    if (global_ns() - t0 > 10000000000ULL) {
+      printf("mop_b200: mbarrier wait timed out after %llu ms / %lld SM cycles (block %d thread %d, barrier at shared offset %u, parity %u)\n",
+             (global_ns() - t0) / 1000000ULL, clock64() - c0, blockIdx.x, threadIdx.x, a, parity);
       __trap();
     }
   }
