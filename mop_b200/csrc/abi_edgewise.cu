@@ -3,7 +3,6 @@
 #include "abi_host.h"
 #include "edgewise_simt.cuh"
 #include "edgewise_tc.cuh"
-#include "edgewise_tc_bwd2.cuh"
 #include "edgewise_tc_large.cuh"
 #include "edgewise_tc_large_bwd.cuh"
 
@@ -118,26 +117,15 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
   }
-  if (tc_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem_f = sizeof(ewtc::Smem<false>) + 1024, smem_b2 = sizeof(ewtc::SmemBwd2) + 1024;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    MOP_CHECK_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewtc::edgewise_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b2));
-      configured_dev = dev;
+  if (tc_ok && p->impl != MOP_IMPL_SIMT) {   // N = 64: edgewise_n64_fwd.cuh / edgewise_n64_bwd.cuh (abi_edgewise64.cu)
+    if (bwd) {
+      MOP_REQUIRE(edgewise_n64_bwd_supported(p), MOP_EINVAL,
+                  "the N = 64 tcgen05 backward needs `aux` (mop_edgewise_aux_floats() floats written by mop_edgewise_fwd of the same call)");
+      rc = edgewise_n64_bwd_launch(p, st);
+    } else {
+      rc = edgewise_n64_fwd_launch(p, st);
     }
-    const int G = p->B * p->H, sms = sm_count();
-    const int grid = bwd ? (G < sms ? G : sms) : (G < 2 * sms ? G : 2 * sms);   // forward: two CTAs per SM
-    if (bwd && edgewise_n64_bwd_supported(p)) {   // the forward handed its row statistics / feature means / gate factors on (aux)
-      if ((rc = edgewise_n64_bwd_launch(p, st))) return rc;
-      p->impl_used = MOP_IMPL_TCGEN05;
-      return MOP_OK;
-    }
-    if (bwd) ewtc::edgewise_bwd2_kernel<<<grid, 256, smem_b2, st>>>(*p);
-    else ewtc::edgewise_kernel<false><<<grid, 128, smem_f, st>>>(*p);
-    MOP_CHECK_CUDA(cudaGetLastError());
+    if (rc != MOP_OK) return rc;
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;
   }

@@ -1,6 +1,7 @@
 // libmop_b200.so - launcher of the third-generation N = 64 Edgewise backward (own translation unit: compiles in parallel)
 #include "abi_host.h"
 #include "edgewise_n64_bwd.cuh"
+#include "edgewise_n64_fwd.cuh"
 
 namespace mop {
 
@@ -24,6 +25,25 @@ int edgewise_n64_bwd_launch(MopEdgewiseParams* p, cudaStream_t st) {
   const int G = p->B * p->H, sms = sm_count();
   const int grid = G < sms ? G : sms;
   ew64::edgewise_bwd3_kernel<<<grid, ew64::kThreads, smem, st>>>(*p, tmQ, tmK, tmV, tmDY);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+int edgewise_n64_fwd_launch(MopEdgewiseParams* p, cudaStream_t st) {
+  const size_t smem = sizeof(ew64::SmemF) + 1024;
+  int rc;
+  if ((rc = allow_smem(ew64::edgewise_fwd3_kernel, smem))) return rc;
+  MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->qkv) & 15) == 0, MOP_EINVAL, "qkv must be 16-byte aligned");
+  const int H = p->H, dk = p->dk, N = p->N;
+  const int64_t hd = (int64_t)H * dk;
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p->qkv);
+  CUtensorMap tmQ, tmK, tmV;
+  if ((rc = make_tile_map_sw(&tmQ, qkv, p->B, N, H, dk, (int64_t)N * 3 * hd, 3 * hd, dk, 64))) return rc;
+  if ((rc = make_tile_map_sw(&tmK, qkv + hd, p->B, N, H, dk, (int64_t)N * 3 * hd, 3 * hd, dk, 64))) return rc;
+  if ((rc = make_tile_map_sw(&tmV, qkv + 2 * hd, p->B, N, H, dk, (int64_t)N * 3 * hd, 3 * hd, dk, 64))) return rc;
+  const int G = p->B * p->H, sms = sm_count();
+  const int grid = G < 2 * sms ? G : 2 * sms;   // two CTAs per SM
+  ew64::edgewise_fwd3_kernel<<<grid, ew64::kFwdThreads, smem, st>>>(*p, tmQ, tmK, tmV);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;
 }
