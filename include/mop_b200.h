@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 6
+#define MOP_ABI_VERSION 7
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -116,6 +116,12 @@ typedef struct MopEdgewiseParams {
      reverse chain; dhead_part is not written */
   float const_gates[4];
   int32_t hops;         /* chain length >= 2 (CONST mode); ignored otherwise */
+  /* S lens bank (attention_variants.py:427-442, :523-533): lens_n depthwise 3x3 convolutions of the V score maps with dilation
+     (= zero padding) lens_dil[l]; channel l*V + v = conv_l(S_v) is appended to the gate-head features (C = 2V + 2 + V lens_n) */
+  int32_t lens_n;       /* 0: off; <= 4 */
+  int32_t lens_dil[4];
+  const float* lens_w;  /* [lens_n, V, 3, 3] fp32 (the lens_bank.{l}.weight tensors stacked) */
+  float* dlens_part;    /* backward: [B*H, lens_n * V * 9] partial grads */
 } MopEdgewiseParams;
 
 size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);

@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 6
+MOP_ABI_VERSION = 7
 MOP_F32, MOP_BF16 = 0, 1
 MOP_GATE_DENSE, MOP_GATE_LOWRANK, MOP_GATE_CONST = 0, 1, 2
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
@@ -36,6 +36,7 @@ class EdgewiseParams(C.Structure):
         ("dy", vp), ("dqkv", vp), ("dscale_part", vp), ("dhead_part", vp), ("dlogit_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),
         ("const_gates", f32 * 4), ("hops", i32),
+        ("lens_n", i32), ("lens_dil", i32 * 4), ("lens_w", vp), ("dlens_part", vp),
     ]
 
 

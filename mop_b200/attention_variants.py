@@ -14,7 +14,7 @@ whole attention core to libmop_b200 instead of materialising N x N maps:
 Unsupported corners raise instead of silently diverging:
   * ``attn_mask`` on EdgewiseMSA: the reference itself returns NaN for any mask
     (-inf enters the gate features), so there is nothing to match.
-  * ``attn_drop > 0`` in training mode, ``use_lens_bank`` (S lens bank).
+  * ``attn_drop > 0`` in training mode on EdgewiseMSA.
 """
 from __future__ import annotations
 
@@ -298,8 +298,6 @@ class EdgewiseMSA(nn.Module):
             raise RuntimeError(
                 "EdgewiseMSA: attn_mask is not supported - the reference forward returns NaN for any mask "
                 "(masked scores enter the gate features as -inf); pass attn_mask=None")
-        if self.use_lens_bank:
-            raise NotImplementedError("use_lens_bank (S lens bank channels) is not provided by the fused kernel yet")
         _no_attn_dropout(self)
         B, N, D = x.shape
         H, dk, V = self.h, self.dk, self.n_views
@@ -315,9 +313,16 @@ class EdgewiseMSA(nn.Module):
         else:
             qkv = torch.stack([lin(x) for lin in self.qkv_list], dim=2).view(B, N, V, 3, H, dk)
         head = self.edge_head
+        lens_w, lens_d = None, ()
+        if self.use_lens_bank:   # S lens bank: depthwise 3x3 convolutions of the score maps as extra gate-head channels
+            if self.lens_kernel_size != 3:
+                raise NotImplementedError("S lens bank: only lens_kernel_size=3 keeps the map size (reference padding = dilation)")
+            lens_w = torch.stack([conv.weight[:, 0] for conv in self.lens_bank], dim=0)   # [L, V, 3, 3]
+            lens_d = self.lens_dilations
         y = MF.edgewise_attention(
             qkv, *scales, self.chain_value_logit, head.tensors(), n_views=V, beta_not=self.beta_not,
-            gate_mode=head.gate_mode, gate_rank=head.gate_rank, use_k3=head.use_k3, impl=self.impl)
+            gate_mode=head.gate_mode, gate_rank=head.gate_rank, use_k3=head.use_k3, impl=self.impl,
+            lens_w=lens_w, lens_dilations=lens_d)
         return self.proj_drop(self.proj(y.reshape(B, N, D)))
 
 

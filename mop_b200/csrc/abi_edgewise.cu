@@ -31,6 +31,12 @@ static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
     MOP_REQUIRE(p->conv1_w && p->conv1_b && p->conv2_w && p->conv2_b, MOP_EINVAL, "dense head tensors missing");
     MOP_REQUIRE(!p->use_k3 || (p->mid3_w && p->mid3_b), MOP_EINVAL, "use_k3 set but mid3 tensors missing");
   }
+  MOP_REQUIRE(p->lens_n >= 0 && p->lens_n <= ew::kMaxLens, MOP_EUNSUPPORTED, "lens_n=%d outside [0,%d]", p->lens_n, ew::kMaxLens);
+  if (p->lens_n > 0) {
+    MOP_REQUIRE(p->lens_w != nullptr && p->gate_mode != MOP_GATE_CONST, MOP_EINVAL, "S lens bank needs lens_w and a gate head");
+    for (int l = 0; l < p->lens_n; ++l) MOP_REQUIRE(p->lens_dil[l] >= 1, MOP_EINVAL, "lens dilation must be >= 1");
+    MOP_REQUIRE(!bwd || p->dlens_part, MOP_EINVAL, "dlens_part missing");
+  }
   if (bwd) {
     MOP_REQUIRE(p->dy && p->dqkv && p->dlogit_part && (p->dhead_part || p->gate_mode == MOP_GATE_CONST), MOP_EINVAL, "backward buffers missing");
     MOP_REQUIRE((p->q_scale == nullptr) || p->dscale_part, MOP_EINVAL, "dscale_part missing");
@@ -49,7 +55,7 @@ static ew::Layout edgewise_layout(const MopEdgewiseParams* p, int bwd) {
   ew::Layout L;
   const bool dense = p->gate_mode == MOP_GATE_DENSE, cg = p->gate_mode == MOP_GATE_CONST;
   L.build(p->N, p->dk, p->V, p->Vp, (dense || cg) ? 1 : p->gate_rank, dense ? p->hidden : 1, dense ? 1 : 0,
-          dense && p->use_k3 ? 1 : 0, bwd, cg ? p->hops : 0, cg ? 1 : 0);
+          dense && p->use_k3 ? 1 : 0, bwd, cg ? p->hops : 0, cg ? 1 : 0, p->lens_n);
   return L;
 }
 
@@ -63,7 +69,7 @@ size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
   if (!p) return 0;
   if (p->gate_mode == MOP_GATE_CONST) return 0;
   const bool dense = p->gate_mode == MOP_GATE_DENSE;
-  return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3);
+  return ew::head_param_count(p->gate_mode, p->V, dense ? 1 : p->gate_rank, p->hidden, dense && p->use_k3, p->lens_n);
 }
 
 int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p) {

@@ -19,12 +19,16 @@ namespace mop {
 namespace ew {
 
 constexpr int kMaxViews = 8;
+constexpr int kMaxLens = 4;                                           // dilations of the S lens bank
+constexpr int kMaxFeat = 2 * kMaxViews + 2 + kMaxViews * kMaxLens;    // feature channels of the gate head
 constexpr int kMaxRank = 8;
 constexpr int kMaxHidden = 16;
 
 // Per-CTA scratch layout, in floats.  Shared by host (sizing) and device.
 struct Layout {
   int N, dk, V, Vp, C, r, hid, dense, k3, bwd;
+  int nl;      // S lens bank (attention_variants.py:427-442, :523-533): number of dilations; V * nl extra feature channels
+  int mL;      // first lens feature map
   int hops;    // length of the chain product: V for the Edgewise modes, `hops` for the fixed-gate multi-hop mode (views 0,1,1,..)
   int cgate;   // fixed scalar gates (MultiHopMSA): no gate head, no reverse chain
   size_t N2, Nd;
@@ -37,10 +41,10 @@ struct Layout {
   size_t total;
 
   __host__ __device__ void build(int N_, int dk_, int V_, int Vp_, int r_, int hid_, int dense_, int k3_, int bwd_, int hops_ = 0,
-                                 int cgate_ = 0) {
+                                 int cgate_ = 0, int nl_ = 0) {
     N = N_; dk = dk_; V = V_; Vp = Vp_; r = r_; hid = hid_; dense = dense_; k3 = k3_; bwd = bwd_;
-    hops = hops_ > 0 ? hops_ : V_; cgate = cgate_;
-    C = 2 * V + 2;
+    hops = hops_ > 0 ? hops_ : V_; cgate = cgate_; nl = cgate_ ? 0 : nl_;
+    C = 2 * V + 2 + V * nl;
     N2 = (size_t)N * N; Nd = (size_t)N * dk;
     int m = 0;
     mS = m; m += V;
@@ -49,6 +53,7 @@ struct Layout {
     mR = m; m += cgate ? 0 : V - 1;
     mM = m; m += 1;
     mG = m; m += 4;
+    mL = m; m += V * nl;
     mZ1 = mH2 = mDH2 = -1;
     if (dense) { mZ1 = m; m += hid; if (k3) { mH2 = m; m += hid; } }
     mD = mdA = mX0 = mX1 = mdG = -1;
@@ -87,8 +92,8 @@ struct Layout {
   }
 };
 
-__host__ __device__ inline size_t head_param_count(int gate_mode, int V, int r, int hid, int k3) {
-  int C = 2 * V + 2;
+__host__ __device__ inline size_t head_param_count(int gate_mode, int V, int r, int hid, int k3, int nl = 0) {
+  int C = 2 * V + 2 + V * nl;
   if (gate_mode == MOP_GATE_LOWRANK) return (size_t)2 * (4 * r * C + 4 * r);
   return (size_t)hid * C + hid + (k3 ? (size_t)hid * hid * 9 + hid : 0) + 4 * hid + 4;
 }
@@ -154,6 +159,34 @@ __device__ void stage_inputs(const Ctx& c) {
   __syncthreads();
 }
 
+// S lens bank (reference :523-533): depthwise 3x3 convolutions of the score maps with dilation d_l and zero padding d_l,
+// channel l * V + v = conv_l(S_v).  Stored as maps: the dense head reads them per pixel, the low-rank head their means.
+__device__ void lens_forward(const Ctx& c) {
+  const auto& p = c.p; const auto& L = c.L;
+  const int N = L.N, V = L.V;
+  for (int ch = 0; ch < V * L.nl; ++ch) {
+    const int l = ch / V, v = ch % V, d = p.lens_dil[l];
+    const float* wt = p.lens_w + (size_t)ch * 9;
+    const float* S = c.S(v);
+    float* out = c.map(L.mL + ch);
+    for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) {
+      const int i = idx / N, j = idx % N;
+      float acc = 0.f;
+      for (int u = 0; u < 3; ++u) {
+        const int ii = i + (u - 1) * d;
+        if (ii < 0 || ii >= N) continue;
+        for (int x = 0; x < 3; ++x) {
+          const int jj = j + (x - 1) * d;
+          if (jj < 0 || jj >= N) continue;
+          acc = fmaf(wt[u * 3 + x], S[(size_t)ii * N + jj], acc);
+        }
+      }
+      out[idx] = acc;
+    }
+  }
+  __syncthreads();
+}
+
 // Dense head: z1 = W1 feat + b1 for every pixel (stored), h2 (stored iff k3), gates -> G maps.
 __device__ void dense_head_forward(const Ctx& c) {
   const auto& p = c.p; const auto& L = c.L;
@@ -162,10 +195,11 @@ __device__ void dense_head_forward(const Ctx& c) {
   const float* Fm = c.F(); const float* Rm = c.Rf();
   for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) {
     int i = idx / N, j = idx % N;
-    float feat[2 * kMaxViews + 2];
+    float feat[kMaxFeat];
     for (int v = 0; v < V; ++v) { feat[v] = c.S(v)[idx]; feat[V + v] = c.S(v)[(size_t)j * N + i]; }
     feat[2 * V] = logf(Fm[idx] + eps);
     feat[2 * V + 1] = logf(Rm[idx] + eps);
+    for (int ch = 0; ch < V * L.nl; ++ch) feat[2 * V + 2 + ch] = c.map(L.mL + ch)[idx];
     float h[kMaxHidden];
     for (int o = 0; o < hid; ++o) {
       float z = p.conv1_b[o];
@@ -222,6 +256,8 @@ __device__ void lowrank_head_forward(const Ctx& c) {
   }
   simt::row_col_means<true>(c.F(), N, p.eps, rho + (size_t)(2 * V) * N, kap + (size_t)(2 * V) * N);
   simt::row_col_means<true>(c.Rf(), N, p.eps, rho + (size_t)(2 * V + 1) * N, kap + (size_t)(2 * V + 1) * N);
+  for (int ch = 0; ch < V * L.nl; ++ch)
+    simt::row_col_means<false>(c.map(L.mL + ch), N, 0.f, rho + (size_t)(2 * V + 2 + ch) * N, kap + (size_t)(2 * V + 2 + ch) * N);
   float* a = c.ws + L.o_a; float* bb = c.ws + L.o_b;
   for (int idx = threadIdx.x; idx < 4 * r * N; idx += simt::kThreads) {
     int q = idx / N, i = idx % N;
@@ -263,6 +299,7 @@ __device__ void forward_maps(Ctx& c) {
     __syncthreads();
   } else {
     for (int k = V - 2; k >= 0; --k) simt::gemm(c.R(k), N, c.R(k + 1), N, 1, c.A(k), N, 1, N, N, N, nullptr, nullptr, 1.f, false, c.gs);
+    if (L.nl) lens_forward(c);
     if (L.dense) dense_head_forward(c); else lowrank_head_forward(c);
   }
   // mix (attention_variants.py:537-547) then row softmax
@@ -492,9 +529,12 @@ __device__ void dense_head_backward(const Ctx& c, float* dhead) {
         const float* f = c.S(ch - V);
         for (int i = 0; i < N; ++i)
           for (int j = 0; j < N; ++j) s = fmaf(dz[(size_t)i * N + j], f[(size_t)j * N + i], s);
-      } else {
+      } else if (ch < 2 * V + 2) {
         const float* f = (ch == 2 * V) ? Fm : Rm;
         for (size_t q = 0; q < L.N2; ++q) s = fmaf(dz[q], logf(f[q] + eps), s);
+      } else {
+        const float* f = c.map(L.mL + ch - (2 * V + 2));
+        for (size_t q = 0; q < L.N2; ++q) s = fmaf(dz[q], f[q], s);
       }
       dW1[idx] = s;
     } else {
@@ -528,7 +568,7 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
   const float s = rsqrtf((float)dk);
   const float bn = p.beta_not / (float)max(1, V - 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = simt::kThreads / 32;
-  const size_t nhead = head_param_count(p.gate_mode, V, L.r, L.hid, L.k3);
+  const size_t nhead = head_param_count(p.gate_mode, V, L.r, L.hid, L.k3, L.nl);
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     Ctx c{p, L, ws_base + (size_t)blockIdx.x * L.total, gs, red, g / H, g % H, g, 0.f};
     forward_maps<T>(c);
@@ -618,6 +658,25 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
       for (size_t idx = threadIdx.x; idx < L.N2; idx += simt::kThreads) dAl[idx] += X[idx];
       __syncthreads();
     }
+    // S lens bank: weight gradients dW[l,v,u,x] = sum_p dfeat_ch[p] S_v[p + (u-1,x-1) d_l]
+    if (L.nl) {
+      float* dl = p.dlens_part + (size_t)g * V * L.nl * 9;
+      for (int idx = threadIdx.x; idx < V * L.nl * 9; idx += simt::kThreads) {
+        const int x = idx % 3, u = (idx / 3) % 3, ch = idx / 9, l = ch / V, v = ch % V, d = p.lens_dil[l];
+        const float* S = c.S(v);
+        float acc = 0.f;
+        for (int i = 0; i < N; ++i) {
+          const int ii = i + (u - 1) * d;
+          if (ii < 0 || ii >= N) continue;
+          for (int j = 0; j < N; ++j) {
+            const int jj = j + (x - 1) * d;
+            if (jj < 0 || jj >= N) continue;
+            acc = fmaf(dfeat_at(c, 2 * V + 2 + ch, i, j), S[(size_t)ii * N + jj], acc);
+          }
+        }
+        dl[idx] = acc;
+      }
+    }
     // dS_k (in place over dA_k): softmax backward + direct mix terms + feature terms
     for (int i = warp; i < N; i += nw) {
       float rs[kMaxViews];
@@ -642,6 +701,19 @@ static __global__ void __launch_bounds__(simt::kThreads, 2) bwd_kernel(MopEdgewi
           float direct = (k == 0) ? d * (1.f + g_or * (pi - 1.f)) : d * (g_and + g_or * pi - g_not * bn);
           float* da = c.map(L.mdA + k);
           float v = c.A(k)[idx] * (da[idx] - rs[k]) + direct + dfeat_at(c, k, i, j) + dfeat_at(c, V + k, j, i);
+          for (int l = 0; l < L.nl; ++l) {   // through the lens convolutions: S_k[i,j] feeds pixel (i,j) - (u-1,x-1) d_l of channel l*V+k
+            const int d = p.lens_dil[l], ch = 2 * V + 2 + l * V + k;
+            const float* wt = p.lens_w + (size_t)(l * V + k) * 9;
+            for (int u = 0; u < 3; ++u) {
+              const int ii = i - (u - 1) * d;
+              if (ii < 0 || ii >= N) continue;
+              for (int x = 0; x < 3; ++x) {
+                const int jj = j - (x - 1) * d;
+                if (jj < 0 || jj >= N) continue;
+                v = fmaf(wt[u * 3 + x], dfeat_at(c, ch, ii, jj), v);
+              }
+            }
+          }
           da[idx] = v;
         }
       }

@@ -218,7 +218,7 @@ __device__ __forceinline__ float cta_sum(float v, float* scratch4) {
 
 inline bool supported(const MopEdgewiseParams* p) {
   return p->dtype == MOP_BF16 && p->N == 64 && p->dk <= 64 && p->dk % 8 == 0 && p->V >= 2 && p->V <= kMaxV && p->Vp == 1 &&
-         p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr;
+         p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr && p->lens_n == 0;
 }
 
 }  // namespace ewtc

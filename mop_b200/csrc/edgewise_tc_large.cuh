@@ -595,7 +595,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
 
 inline bool supported(const MopEdgewiseParams* p) {
   return p->dtype == MOP_BF16 && p->N >= 1 && p->N <= kMaxTokens && p->dk <= 64 && p->dk % 8 == 0 && p->V >= 2 && p->V <= kMaxV &&
-         p->Vp == 1 && p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr;
+         p->Vp == 1 && p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr && p->lens_n == 0;
 }
 
 // one persistent CTA per SM (sizing without a device: B200)

@@ -106,6 +106,13 @@ def _fill_edgewise(p, qkv, scales, logit, head, cfg):
     if scales is not None:
         p.q_scale, p.k_scale, p.v_scale = (_ptr(s) for s in scales)
     p.chain_value_logit = _ptr(logit)
+    lens = cfg.get("lens_dilations", ())
+    if lens:   # S lens bank: the stacked [L,V,3,3] weights travel as the last "head" tensor
+        p.lens_n = len(lens)
+        for i, d in enumerate(lens):
+            p.lens_dil[i] = int(d)
+        p.lens_w = _ptr(head[-1])
+        head = head[:-1]
     if cfg["gate_mode"] == "lowrank":
         p.row_w, p.row_b, p.col_w, p.col_b = (_ptr(h) for h in head)
     elif cfg["gate_mode"] == "dense":
@@ -194,6 +201,10 @@ class _Edgewise(torch.autograd.Function):
             dscale_part = torch.empty(G, 3, V, dk, dtype=torch.float32, device=dev) if scales is not None else None
             p.dy, p.dqkv = _ptr(dy_c), _ptr(dqkv)
             p.dhead_part, p.dlogit_part, p.dscale_part = _ptr(dhead_part), _ptr(dlogit_part), _ptr(dscale_part)
+            dlens_part = None
+            if cfg.get("lens_dilations", ()):
+                dlens_part = torch.empty(G, head32[-1].numel(), dtype=torch.float32, device=dev)
+                p.dlens_part = _ptr(dlens_part)
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
@@ -212,17 +223,21 @@ class _Edgewise(torch.autograd.Function):
         dlogit = dlogit_part.sum().reshape(()).to(dts[3])
         flat = dhead_part.sum(0) if dhead_part is not None else None
         dheads, off = [], 0
-        for shp, dt in zip(ctx.head_shapes, dts[4:]):
+        n_gate = len(ctx.head_shapes) - (1 if dlens_part is not None else 0)
+        for shp, dt in zip(ctx.head_shapes[:n_gate], dts[4:]):
             n = math.prod(shp)
             dheads.append(flat[off:off + n].reshape(shp).to(dt))
             off += n
+        if dlens_part is not None:
+            dheads.append(dlens_part.sum(0).reshape(ctx.head_shapes[-1]).to(dts[-1]))
         return (None, dqkv, dq_s, dk_s, dv_s, dlogit, *dheads)
 
 
 def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value_logit: torch.Tensor,
                        head: Dict[str, torch.Tensor], *, n_views: int, beta_not: float, gate_mode: str,
                        gate_rank: int = 4, use_k3: bool = False, impl: Optional[str] = None,
-                       const_gates=None, hops: Optional[int] = None) -> torch.Tensor:
+                       const_gates=None, hops: Optional[int] = None, lens_w: Optional[torch.Tensor] = None,
+                       lens_dilations=()) -> torch.Tensor:
     """Edgewise Mixture-of-Products attention core (reference attention_variants.py:500-562).
 
     qkv   ``[B, N, Vp, 3, H, dk]``: output of the shared qkv Linear (Vp=1, with
@@ -249,7 +264,14 @@ def edgewise_attention(qkv: torch.Tensor, q_scale, k_scale, v_scale, chain_value
     hidden = head["conv1.weight"].shape[0] if gate_mode == "dense" else 16
     cfg = dict(n_views=int(n_views), beta_not=float(beta_not), gate_mode=gate_mode, gate_rank=int(gate_rank),
                use_k3=dense_k3, hidden=int(hidden), impl=impl)
-    return _Edgewise.apply(cfg, qkv, q_scale, k_scale, v_scale, chain_value_logit, *[head[k] for k in keys])
+    tensors = [head[k] for k in keys]
+    if lens_w is not None and len(lens_dilations):
+        # S lens bank (reference :427-442, :523-533): lens_w [L, V, 3, 3] = the depthwise 3x3 weights per dilation, stacked
+        if lens_w.shape != (len(lens_dilations), int(n_views), 3, 3):
+            raise ValueError(f"lens_w must be [L={len(lens_dilations)}, V={n_views}, 3, 3], got {tuple(lens_w.shape)}")
+        cfg["lens_dilations"] = tuple(int(d) for d in lens_dilations)
+        tensors.append(lens_w)
+    return _Edgewise.apply(cfg, qkv, q_scale, k_scale, v_scale, chain_value_logit, *tensors)
 
 
 # ----------------------------------------------------------------------------

@@ -98,8 +98,13 @@ def edgewise_cases():
         ("ew_lensqk_lowrank", 16, 2, 12, dict(n_views=3, share_qkv=True, gate_mode="lowrank", gate_rank=2, use_lens_bank_qk=True, lens_qk_dilations=(1, 2, 3))),
         ("ew_lensqk_causal_dense", 16, 2, 12, dict(n_views=2, share_qkv=True, gate_mode="dense", use_k3=True, use_lens_bank_qk=True, lens_qk_causal=True)),
         ("ew_lensS_dense", 16, 2, 10, dict(n_views=3, share_qkv=True, gate_mode="dense", use_k3=True, use_lens_bank=True)),
+        ("ew_lensS_lowrank_qk", 16, 2, 10, dict(n_views=4, share_qkv=True, gate_mode="lowrank", gate_rank=2, use_lens_bank=True,
+                                                lens_dilations=(1, 2), use_lens_bank_qk=True, lens_qk_dilations=(2, 3), lens_qk_causal=True)),
     ]
+    only = os.environ.get("MOP_GOLDEN_ONLY")   # regenerate a single (new) case without touching the committed ones
     for i, (name, dim, H, N, kw) in enumerate(cases):
+        if only and name != only:
+            continue
         torch.manual_seed(100 + i)
         mod = EdgewiseMSA(dim, heads=H, **kw)
         redraw(mod, 200 + i)
@@ -157,6 +162,8 @@ def gate_presets():
 
 if __name__ == "__main__":
     edgewise_cases()
+    if os.environ.get("MOP_GOLDEN_ONLY"):
+        sys.exit(0)
     sdpa_cases()
     quartet_cases()
     gate_presets()

@@ -20,7 +20,8 @@ PARAM_TOL = 2e-5   # relative to ||g||_inf (reference fp32 self-noise reaches 5e
 BF16_TOL = 2e-2
 
 EW_GOLDEN = ["ew_lowrank_share_v5", "ew_lowrank_sep_v3", "ew_lowrank_share_v2_n64", "ew_dense_share_v2",
-             "ew_dense_k3_share_v5", "ew_dense_k3_sep_v3", "ew_lensqk_lowrank", "ew_lensqk_causal_dense"]
+             "ew_dense_k3_share_v5", "ew_dense_k3_sep_v3", "ew_lensqk_lowrank", "ew_lensqk_causal_dense", "ew_lensS_dense",
+             "ew_lensS_lowrank_qk"]
 
 
 def _module_from_golden(case, device, dtype=torch.float32):
@@ -366,3 +367,17 @@ def test_unified_msa_mode_e_matches_edgewise_module():
     for mode in ("A", "B"):
         b = UnifiedMSA(mode, 48, heads=3).cuda()
         assert b(x).shape == x.shape
+
+
+@pytest.mark.parametrize("use_lens_bank,use_lens_bank_qk,lens_dilations,lens_qk_dilations,n_views", [
+    (True, False, (1, 2), (1, 2), 3), (False, True, (1,), (1, 2, 3), 3), (True, True, (1, 2), (2, 3), 4), (False, False, (1,), (1,), 3)])
+def test_reference_lens_bank_test_through_the_dropin(use_lens_bank, use_lens_bank_qk, lens_dilations, lens_qk_dilations, n_views):
+    """The reference's own tests/test_edgewise_lens_bank.py:7-40 (same constructor arguments, same assertion), on the fused path."""
+    from mop_b200 import EdgewiseMSA
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 64, device="cuda")
+    msa = EdgewiseMSA(dim=64, heads=4, n_views=n_views, share_qkv=True, gate_mode="lowrank", gate_rank=2, gate_init="neutral", use_k3=True,
+                      use_lens_bank=use_lens_bank, lens_kernel_size=3, lens_dilations=lens_dilations, use_lens_bank_qk=use_lens_bank_qk,
+                      lens_qk_kernel_size=3, lens_qk_dilations=lens_qk_dilations, lens_qk_causal=True).cuda()
+    y = msa(x)
+    assert y.shape == (2, 8, 64) and torch.isfinite(y).all()
