@@ -238,6 +238,19 @@ int mop_ln_partial_rows(int rows);
 int mop_ln_fwd(MopLnParams* p, void* cuda_stream);
 int mop_ln_bwd(MopLnParams* p, void* cuda_stream);
 
+/* ------------------------------------------------------------------------- */
+/* Whisper-MoP 2D gate                                           */
+/* ------------------------------------------------------------------------- */
+/* MoP2D.forward mop/models/whisper_mop.py:91-124 is linear and bias-free: ViewsConv2D (1x1) -> Kernels2D (k x k, zero padding
+ * k/2) -> FuseExcInh2D (1x1) -> mean over mel bins -> 1 + a_pos g_pos - a_neg g_neg.  The caller folds the weights into ONE
+ * k x k filter He (a_pos H_pos - a_neg H_neg); the library computes, without forming any [B, V+K, T, F] map,
+ *   R[b,t,w]   = sum of the mel bins that filter column w sees at row t      (fwd out, bwd in; [B, T, ks])
+ *   gate[b,t]  = 1 + (1/F) sum_{u,w} He[u,w] R[b, t+u-k/2, w]                 ([B, T])
+ * backward: dHe_part[i] (nparts = mop_mop2d_partial_rows() rows of ks*ks, summed by the caller); mel is data (no gradient). */
+int mop_mop2d_partial_rows(void);
+int mop_mop2d_fwd(const float* mel, const float* He, float* R, float* gate, int B, int T, int F, int ks, void* cuda_stream);
+int mop_mop2d_bwd(const float* R, const float* dgate, float* dHe_part, int nparts, int B, int T, int F, int ks, void* cuda_stream);
+
 /* The dropout factor every attention kernel applies to P[b,h,i,j] for (p, seed, offset): out[bh, i, j] = 0 or 1 / (1 - p)
  * (fp32, [BH, Nq, Nk]).  Test infrastructure: lets the CPU oracle be evaluated under the kernels' own mask. */
 int mop_dropout_mask(float* out, int BH, int Nq, int Nk, float p, uint64_t seed, uint64_t offset, void* cuda_stream);

@@ -9,10 +9,10 @@ from .components import MLP, MSA, Block, DropPath, PatchEmbed
 from .functional import edgewise_attention, quartet_attention, sdpa
 from .quartet_attn_patch import CausalSelfAttention, TransformerConfig
 from .vit_edgewise import BlockEdgewise, ViTEdgewise
-from .whisper_mop import MultiheadCrossAttention, MultiheadSelfAttention
+from .whisper_mop import MoP2D, MultiheadCrossAttention, MultiheadSelfAttention
 
 __all__ = [
     "BaselineMSA", "CrossViewMixerMSA", "MultiHopMSA", "EdgewiseGateHead", "EdgewiseMSA", "UnifiedMSA", "MSA", "MLP", "Block", "DropPath", "PatchEmbed",
-    "BlockEdgewise", "ViTEdgewise", "MultiheadSelfAttention", "MultiheadCrossAttention",
+    "BlockEdgewise", "ViTEdgewise", "MultiheadSelfAttention", "MultiheadCrossAttention", "MoP2D",
     "CausalSelfAttention", "TransformerConfig", "edgewise_attention", "quartet_attention", "sdpa",
 ]

@@ -110,6 +110,11 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_mop2d_partial_rows.restype = C.c_int
+        lib.mop_mop2d_fwd.restype = C.c_int
+        lib.mop_mop2d_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.mop_mop2d_bwd.restype = C.c_int
+        lib.mop_mop2d_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.mop_dropout_mask.restype = C.c_int
         lib.mop_dropout_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.mop_ln_partial_rows.restype = C.c_int

@@ -27,6 +27,7 @@ _CANONICAL = {
     "CrossViewMixerMSA": av.CrossViewMixerMSA, "MultiHopMSA": av.MultiHopMSA,
     "MSA": comp.MSA, "CausalSelfAttention": qp.CausalSelfAttention,
     "MultiheadSelfAttention": wm.MultiheadSelfAttention, "MultiheadCrossAttention": wm.MultiheadCrossAttention,
+    "MoP2D": wm.MoP2D,
 }
 _EXPERIMENT_MODULES = tuple(pre + n for pre in ("", "experiments.") for n in (
     "cifar100_edgewise_gates", "cifar10_edgewise_gates", "cifar100_crossview_mixer", "cifar10_crossview_mixer",

@@ -630,3 +630,59 @@ def add_layer_norm(x: torch.Tensor, r: Optional[torch.Tensor], scale: Optional[t
     rows_per_sample = x.shape[-2] if x.dim() >= 2 else 1
     x_new, y = _AddLayerNorm.apply(x, r, scale, gamma, beta, float(eps), rows_per_sample, out_dtype)
     return (x if r is None else x_new), y
+
+
+# ----------------------------------------------------------------------------
+# Whisper-MoP 2D gate
+# ----------------------------------------------------------------------------
+class _MoP2DGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mel, He):
+        lib = _lib.load()
+        _need_cuda(mel, "mel")
+        if mel.requires_grad:
+            raise NotImplementedError("MoP2D gate: gradient w.r.t. the mel spectrogram is not provided (it is input data)")
+        B, T, Fb = mel.shape
+        ks = He.shape[-1]
+        mel32 = mel.detach().float().contiguous()
+        he32 = He.detach().float().contiguous()
+        R = torch.empty(B, T, ks, dtype=torch.float32, device=mel.device)
+        gate = torch.empty(B, T, dtype=torch.float32, device=mel.device)
+        with torch.cuda.device(mel.device):
+            _lib.check(lib.mop_mop2d_fwd(_ptr(mel32), _ptr(he32), _ptr(R), _ptr(gate), B, T, Fb, ks, _stream()), "mop_mop2d_fwd")
+        abi_calls["mop2d_fwd"] = abi_calls.get("mop2d_fwd", 0) + 1
+        ctx.save_for_backward(R)
+        ctx.meta = (B, T, Fb, ks, He.dtype)
+        return gate
+
+    @staticmethod
+    def backward(ctx, dgate):
+        lib = _lib.load()
+        (R,) = ctx.saved_tensors
+        B, T, Fb, ks, dt = ctx.meta
+        dg = dgate.detach().float().contiguous()
+        with torch.cuda.device(R.device):
+            nparts = lib.mop_mop2d_partial_rows()
+            parts = torch.empty(nparts, ks * ks, dtype=torch.float32, device=R.device)
+            _lib.check(lib.mop_mop2d_bwd(_ptr(R), _ptr(dg), _ptr(parts), nparts, B, T, Fb, ks, _stream()), "mop_mop2d_bwd")
+        abi_calls["mop2d_bwd"] = abi_calls.get("mop2d_bwd", 0) + 1
+        return None, parts.sum(0).reshape(ks, ks).to(dt)
+
+
+def mop2d_gate(mel: torch.Tensor, views_w: torch.Tensor, kernels_w: torch.Tensor, fuse_w: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+    """Per-time-step gate of ``MoP2D`` (reference whisper_mop.py:91-124) without the [B, V+K, T, F] intermediates.
+
+    mel ``[B, T, F]`` (the ``mel2d[:, 0]`` map); ``views_w [V,1,1,1]``, ``kernels_w [K,V,k,k]``, ``fuse_w [2,V+K,1,1]``,
+    ``alpha [2]`` are the module's parameters.  The module is linear, so the weights fold into one k x k filter
+    (differentiable PyTorch, a few hundred flops); the kernel applies it fused with the mean over the mel bins.
+    Returns ``gate [B, T]`` (fp32)."""
+    V = views_w.shape[0]
+    ks = kernels_w.shape[-1]
+    wv = views_w.reshape(V).float()
+    fw = fuse_w.reshape(2, -1).float()
+    H = torch.einsum("ck,kvuw,v->cuw", fw[:, V:], kernels_w.float(), wv)       # through Kernels2D
+    centre = torch.zeros_like(H)
+    centre[:, ks // 2, ks // 2] = fw[:, :V] @ wv                                 # the views themselves (1x1 path)
+    H = H + centre
+    He = alpha[0].float() * H[0] - alpha[1].float() * H[1]
+    return _MoP2DGate.apply(mel, He)

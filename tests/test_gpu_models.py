@@ -197,3 +197,28 @@ def test_multihop_bf16_storage_vs_oracle():
     y.backward(dy.to("cuda", torch.bfloat16))
     assert rel_to_max(y, y_ref) <= 2e-2 and rel_to_max(qg.grad, gq) <= 2e-2
     assert abs(lg.grad.item() - gl.item()) <= 2e-2 * abs(gl.item()) + 1e-3
+
+
+@pytest.mark.parametrize("B,T,Fb,V,K,ks", [(2, 40, 16, 3, 2, 3), (3, 150, 80, 5, 3, 5), (1, 7, 9, 2, 1, 7)])
+def test_mop2d_gate_vs_reference_module(B, T, Fb, V, K, ks, patched):
+    """Fused MoP2D gate against the unmodified reference module (whisper_mop.py:91-124) in fp64: gate and every parameter gradient."""
+    mods, dropin = patched
+    import mop_b200
+    torch.manual_seed(B * 100 + ks)
+    ref = mods["wm"].MoP2D(V, K, ks).double()
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(torch.randn_like(p) * 0.5)
+    ours = mop_b200.MoP2D(V, K, ks)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
+    ours = ours.cuda()
+    mel2d = torch.randn(B, 1, T, Fb)
+    dg = torch.randn(B, T, 1)
+    g_ref, _, _ = ref(mel2d.double())
+    g_ref.backward(dg.double())
+    g, Vm, Km = ours(mel2d.cuda())
+    assert Vm is None and Km is None
+    g.backward(dg.cuda())
+    assert max_abs(g, g_ref) <= 1e-5 * max(1.0, g_ref.abs().max().item())
+    for (k, p), (_, q) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert max_abs(q.grad, p.grad) <= 2e-5 * max(1.0, p.grad.abs().max().item()), k
