@@ -37,6 +37,24 @@ import torch.nn.functional as F  # noqa: E402
 MODEL = dict(dim=224, depth=8, heads=4, n_classes=100, mlp_ratio=3.0, n_views=5, share_qkv=True, use_k3=True,
              gate_mode="lowrank", gate_rank=4, gate_init="mix5", drop_path=0.1)
 BATCH, IMG, PATCH, NTOK = 256, 32, 4, 64
+CONFIG = "vit_e_cifar"
+# BASELINE.json configs[2]: ViT-B/16-MoP, 224x224 (196 tokens), 86,624,652 parameters, batch 256 per GPU
+VIT_B16 = dict(dim=768, depth=12, heads=12, n_classes=1000, mlp_ratio=4.0, n_views=5, share_qkv=True, use_k3=True,
+               gate_mode="lowrank", gate_rank=4, gate_init="mix5", drop_path=0.4)
+
+
+def select_config(name: str, batch: int = 0):
+    """`vit_e_cifar` (default, BASELINE.json configs[1], the headline) or `vit_b16` (configs[2], the 8-GPU model)."""
+    global MODEL, BATCH, IMG, PATCH, NTOK, WORKLOAD, CONFIG
+    CONFIG = name
+    if name == "vit_b16":
+        MODEL, IMG, PATCH, NTOK = VIT_B16, 224, 16, 196
+        BATCH = batch or 256
+        WORKLOAD = (f"ViTEdgewise ViT-B/16-MoP (dim768 depth12 heads12 V5 share_qkv use_k3 lowrank:mix5 r4, 86.6 M parameters), "
+                    f"ImageNet-shaped 224x224 (196 tokens), batch {BATCH}/GPU, fwd+bwd+AdamW")
+    elif batch:
+        BATCH = batch
+        WORKLOAD = WORKLOAD.replace("batch 256/GPU", f"batch {BATCH}/GPU")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ew64::edgewise_bwd3_kernel, B*H = 1024
 # problems) from the committed `ncu --set full` capture (a citation, not measured in this run): algorithmic read bytes are
 # 29.4 MB (Q, K, V, dy) + 17.8 MB (the forward's row statistics / feature means / gate factors) = 47.2 MB, i.e. no re-reads
@@ -163,9 +181,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, mean_s = cpu_throughput(args.steps, args.warmup, BATCH)
+    # ViT-B/16 at batch 256 takes minutes per step on host cores: a bounded sample of the same workload (8 images per step)
+    sample = BATCH if CONFIG == "vit_e_cifar" else 8
+    cb, mean_s = cpu_throughput(args.steps, args.warmup, sample)
     line = {"impl": "reference", "metric": "vit_mop_train_images_per_sec", "value": cb["value"], "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3 * BATCH / sample,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH,
                        "note": "reference eager path on the host cores only (kind: see cpu_baseline); no GPU work"},
@@ -197,11 +217,11 @@ def run_ours(args):
     model.train()
     # N > 1: every p.grad is a view into one flat buffer and the step does ONE all-reduce (mean) after backward, so that
     # the whole step, collective included, is captured in a CUDA graph (mop_b200/ddp.py).  --no-graph: torch DDP, eager.
-    use_graph = not args.no_graph
+    # ViT-B/16 (a 300 ms step, 346 MB of gradients): eager launches, gradient buckets all-reduced WHILE the backward runs
+    use_graph = not args.no_graph and CONFIG == "vit_e_cifar"
     from mop_b200.ddp import FlatGradAllReduce
-    flat = FlatGradAllReduce(model) if (ddp and use_graph) else None
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=64,
-                                                    gradient_as_bucket_view=True) if (ddp and not use_graph) else model
+    flat = FlatGradAllReduce(model, bucket_mb=0.0 if use_graph else args.bucket_mb) if ddp else None
+    net = model
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True, capturable=use_graph)
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
     x_host = torch.randn(BATCH, 3, IMG, IMG, generator=gen).pin_memory()
@@ -340,7 +360,7 @@ def run_ours(args):
         attn_ms = MODEL["depth"] * (kern_ms.get("edgewise_fwd", 0) + kern_ms.get("edgewise_bwd", 0))
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_throughput(steps=4, warmup=1, sample_batch=64)
+            cb, _ = cpu_throughput(steps=4, warmup=1, sample_batch=64) if CONFIG == "vit_e_cifar" else cpu_throughput(steps=1, warmup=0, sample_batch=4)
         extras = {}
         if world == 1 and not args.no_extras:
             extras = extra_measurements(dev, flush, pk)
@@ -348,7 +368,9 @@ def run_ours(args):
             "metric": "vit_mop_train_images_per_sec", "value": world * BATCH / (step_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "name": CONFIG, "global_batch": world * BATCH, "parallelism": f"dp{world}",
+                       "grad_allreduce": (None if not ddp else "one flat 16 MB all-reduce between two CUDA graphs" if graph is not None else
+                                          f"{len(flat.buckets)} buckets of ~{args.bucket_mb:g} MB launched from grad hooks during the backward"),
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
                        "attention_impl": impl_used, "loss": loss_val,
                        "step_launch": "cuda_graph_replay" if graph is not None else "eager"},
@@ -357,7 +379,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16"], "traffic": DOMINANT_KERNEL_DRAM_BYTES, "traffic_source": DOMINANT_KERNEL_DRAM_SOURCE,
+                         "frac": achieved / pk["bf16"],
+                         "traffic": DOMINANT_KERNEL_DRAM_BYTES if CONFIG == "vit_e_cifar" else None,
+                         "traffic_source": DOMINANT_KERNEL_DRAM_SOURCE if CONFIG == "vit_e_cifar" else None,
                          "peak_source": pk["source"],
                          "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
                          "fwd_ms": kern_ms.get("edgewise_fwd"), "bwd_ms": kern_ms.get("edgewise_bwd"),
@@ -455,7 +479,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the attention-shape table, the dense+k3 variant and the reference-eager-on-GPU arm")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--config", default="vit_e_cifar", choices=["vit_e_cifar", "vit_b16"],
+                    help="vit_e_cifar: BASELINE.json configs[1] (headline); vit_b16: configs[2], ViT-B/16-MoP at 224x224")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 256)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient bucket size of the overlapped all-reduce (eager multi-GPU steps)")
     args = ap.parse_args()
+    select_config(args.config, args.batch)
+    if args.config != "vit_e_cifar":
+        args.no_extras = True
     if args.impl == "reference":
         run_reference(args)
     else:

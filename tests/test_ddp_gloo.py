@@ -49,13 +49,15 @@ def test_sharded_gradients_match_full_batch(tmp_path):
     assert got["slow"] == 2.0
 
 
-def _worker_flat(rank, world, port, out):
+def _worker_flat(rank, world, port, out, bucket_mb=0.0):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from mop_b200 import ddp
     ddp.init("gloo")
     torch.manual_seed(rank)   # different initial weights per rank: the constructor broadcasts rank 0's
     model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
-    flat = ddp.FlatGradAllReduce(model)
+    flat = ddp.FlatGradAllReduce(model, bucket_mb=bucket_mb)
+    if bucket_mb > 0:
+        assert len(flat.buckets) >= 2 and flat.buckets[0][1] == flat.flat.numel() and flat.buckets[-1][0] == 0
     g = torch.Generator().manual_seed(1)
     X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
     lo, hi = ddp.shard_bounds(10, rank, world)
@@ -80,6 +82,21 @@ def test_flat_gradient_allreduce_matches_full_batch(tmp_path):
     model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
     for a, p in zip(got["w"], model.parameters()):
         assert torch.equal(a, p.detach())
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()
+    for a, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(a, p.grad, atol=1e-6)
+
+
+def test_bucketed_overlapped_allreduce_matches_full_batch(tmp_path):
+    """FlatGradAllReduce(bucket_mb > 0): buckets in reverse parameter order, all-reduces launched from post-accumulate-grad hooks
+    during the backward (the ViT-B/16 path: 346 MB of gradients) == full-batch gradients, on both steps."""
+    out = str(tmp_path / "fb.pt")
+    mp.spawn(_worker_flat, args=(2, _free_port(), out, 0.0002), nprocs=2, join=True)   # ~50-element buckets: two buckets
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
     g = torch.Generator().manual_seed(1)
     X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
     torch.nn.functional.cross_entropy(model(X), Y).backward()
