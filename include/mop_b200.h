@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 7
+#define MOP_ABI_VERSION 8
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -104,10 +104,12 @@ typedef struct MopEdgewiseParams {
   /* backward only */
   const void* dy;       /* [B,N,H,dk] `dtype` */
   void* dqkv;           /* [B,N,Vp,3,H,dk] `dtype`, fully overwritten */
-  float* dscale_part;   /* [B*H,3,V,dk] per-(b,h) partial grads of q/k/v_scale (sum over b on the host side); NULL if scales are NULL */
-  float* dhead_part;    /* [B*H, mop_edgewise_head_param_count()] partial grads of the gate head, packed in the order
+  float* dscale_part;   /* [R,3,V,dk], R = mop_edgewise_partial_rows(): partial grads of q/k/v_scale; row i belongs to head i % H
+                           (R = B*H: one row per (b,h) problem; the N = 64 tcgen05 backward sums over the problems of a CTA and
+                           writes one row per CTA).  The caller sums rows with equal i % H.  NULL if scales are NULL */
+  float* dhead_part;    /* [R, mop_edgewise_head_param_count()] partial grads of the gate head, packed in the order
                            lowrank: row_w,row_b,col_w,col_b ; dense: conv1_w,conv1_b,(mid3_w,mid3_b),conv2_w,conv2_b */
-  float* dlogit_part;   /* [B*H] */
+  float* dlogit_part;   /* [B*H] (always one value per problem) */
   /* scratch */
   void* workspace;
   size_t workspace_bytes;
@@ -128,6 +130,8 @@ size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p);
 /* 1 if mop_edgewise_fwd with these params would run the kernel whose backward wants `row_stats` and `y_base`: allocate
  * them, pass them to the forward and hand them back to the backward; 0 otherwise (both may be NULL) */
 int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p);
+/* rows R of dscale_part / dhead_part that mop_edgewise_bwd writes for these params (B*H, or the persistent grid) */
+int mop_edgewise_partial_rows(const MopEdgewiseParams* p);
 /* number of floats of `aux` the forward would write / the backward needs for these params (0: none) */
 size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p);
 /* bytes of workspace needed by mop_edgewise_fwd (backward=0) / mop_edgewise_bwd (backward=1) */

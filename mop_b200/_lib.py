@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 7
+MOP_ABI_VERSION = 8
 MOP_F32, MOP_BF16 = 0, 1
 MOP_GATE_DENSE, MOP_GATE_LOWRANK, MOP_GATE_CONST = 0, 1, 2
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
@@ -125,6 +125,8 @@ def load():
             fn.argtypes = [C.POINTER(LnParams), C.c_void_p]
         lib.mop_edgewise_needs_row_stats.restype = C.c_int
         lib.mop_edgewise_needs_row_stats.argtypes = [C.POINTER(EdgewiseParams)]
+        lib.mop_edgewise_partial_rows.restype = C.c_int
+        lib.mop_edgewise_partial_rows.argtypes = [C.POINTER(EdgewiseParams)]
         lib.mop_edgewise_aux_floats.restype = C.c_size_t
         lib.mop_edgewise_aux_floats.argtypes = [C.POINTER(EdgewiseParams)]
         lib.mop_edgewise_head_param_count.restype = C.c_size_t

@@ -77,6 +77,13 @@ int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p) {
   return (p->impl != MOP_IMPL_SIMT && !ewtc::supported(p) && ewl::supported(p)) ? 1 : 0;
 }
 
+int mop_edgewise_partial_rows(const MopEdgewiseParams* p) {
+  if (check_edgewise(p, false) != MOP_OK) return 0;
+  // the N = 64 tcgen05 backward sums its partials over the problems of a CTA (rows ordered [cta], head = cta % H)
+  if (p->impl != MOP_IMPL_SIMT && ewtc::supported(p)) return edgewise_n64_bwd_partial_rows(p);
+  return p->B * p->H;
+}
+
 size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p) {
   if (check_edgewise(p, false) != MOP_OK) return 0;
   return (p->impl != MOP_IMPL_SIMT && ewtc::supported(p)) ? (size_t)p->B * p->H * ewtc::kAuxFloats : 0;

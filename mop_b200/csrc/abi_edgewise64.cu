@@ -6,6 +6,10 @@
 namespace mop {
 
 bool edgewise_n64_bwd_supported(const MopEdgewiseParams* p) { return ew64::supported_bwd(p); }
+int edgewise_n64_bwd_partial_rows(const MopEdgewiseParams* p) {
+  int sms = sm_count();
+  return ew64::bwd_grid(p, sms > 0 ? sms : 148);
+}
 
 int edgewise_n64_bwd_launch(MopEdgewiseParams* p, cudaStream_t st) {
   const size_t smem = sizeof(ew64::Smem) + 1024;
@@ -22,8 +26,7 @@ int edgewise_n64_bwd_launch(MopEdgewiseParams* p, cudaStream_t st) {
   if ((rc = make_tile_map_sw(&tmK, qkv + hd, p->B, N, H, dk, (int64_t)N * 3 * hd, 3 * hd, dk, 64))) return rc;
   if ((rc = make_tile_map_sw(&tmV, qkv + 2 * hd, p->B, N, H, dk, (int64_t)N * 3 * hd, 3 * hd, dk, 64))) return rc;
   if ((rc = make_tile_map_sw(&tmDY, p->dy, p->B, N, H, dk, (int64_t)N * hd, hd, dk, 64))) return rc;
-  const int G = p->B * p->H, sms = sm_count();
-  const int grid = G < sms ? G : sms;
+  const int grid = ew64::bwd_grid(p, sm_count());
   ew64::edgewise_bwd3_kernel<<<grid, ew64::kThreads, smem, st>>>(*p, tmQ, tmK, tmV, tmDY);
   MOP_CHECK_CUDA(cudaGetLastError());
   return MOP_OK;

@@ -26,6 +26,7 @@ template <typename K> static int allow_smem(K kernel, size_t bytes) {
 
 // third-generation N = 64 Edgewise backward (abi_edgewise64.cu)
 bool edgewise_n64_bwd_supported(const MopEdgewiseParams* p);
+int edgewise_n64_bwd_partial_rows(const MopEdgewiseParams* p);
 int edgewise_n64_bwd_launch(MopEdgewiseParams* p, cudaStream_t st);
 int edgewise_n64_fwd_launch(MopEdgewiseParams* p, cudaStream_t st);
 }  // namespace mop

@@ -196,14 +196,15 @@ class _Edgewise(torch.autograd.Function):
             p.aux = _ptr(aux)
             nhead = lib.mop_edgewise_head_param_count(C.byref(p))
             G = B * H
-            dhead_part = torch.empty(G, nhead, dtype=torch.float32, device=dev) if nhead else None
+            R = lib.mop_edgewise_partial_rows(C.byref(p))   # rows of the partial-gradient buffers: B*H or one per CTA
+            dhead_part = torch.empty(R, nhead, dtype=torch.float32, device=dev) if nhead else None
             dlogit_part = torch.empty(G, dtype=torch.float32, device=dev)
-            dscale_part = torch.empty(G, 3, V, dk, dtype=torch.float32, device=dev) if scales is not None else None
+            dscale_part = torch.empty(R, 3, V, dk, dtype=torch.float32, device=dev) if scales is not None else None
             p.dy, p.dqkv = _ptr(dy_c), _ptr(dqkv)
             p.dhead_part, p.dlogit_part, p.dscale_part = _ptr(dhead_part), _ptr(dlogit_part), _ptr(dscale_part)
             dlens_part = None
             if cfg.get("lens_dilations", ()):
-                dlens_part = torch.empty(G, head32[-1].numel(), dtype=torch.float32, device=dev)
+                dlens_part = torch.empty(G, head32[-1].numel(), dtype=torch.float32, device=dev)   # fp32-mode kernel: one row per problem
                 p.dlens_part = _ptr(dlens_part)
             nbytes = lib.mop_edgewise_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
@@ -214,7 +215,7 @@ class _Edgewise(torch.autograd.Function):
         abi_calls["edgewise_bwd"] += 1
         dts = ctx.in_dtypes
         if scales is not None:
-            ds = dscale_part.view(B, H, 3, V, dk).sum(0).permute(1, 2, 0, 3)  # [3,V,H,dk]
+            ds = dscale_part.view(R // H, H, 3, V, dk).sum(0).permute(1, 2, 0, 3)  # [3,V,H,dk]  (row i belongs to head i % H)
             dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:
             dq_s = dk_s = dv_s = None
