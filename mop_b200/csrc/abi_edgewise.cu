@@ -14,7 +14,8 @@ static int check_edgewise(const MopEdgewiseParams* p, bool bwd) {
               "MopEdgewiseParams size mismatch: caller %d, library %d", p->struct_bytes, (int)sizeof(MopEdgewiseParams));
   MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "bad dtype %d", p->dtype);
   MOP_REQUIRE(p->B > 0 && p->H > 0 && p->N > 0 && p->dk > 0, MOP_EINVAL, "bad shape B=%d H=%d N=%d dk=%d", p->B, p->H, p->N, p->dk);
-  MOP_REQUIRE(p->V >= 2 && p->V <= ew::kMaxViews, MOP_EUNSUPPORTED, "n_views=%d outside [2,%d]", p->V, ew::kMaxViews);
+  // V = 1 happens with a single-dilation Q/K lens bank (attention_variants.py:472-498): chain = A_1, all mix terms vanish
+  MOP_REQUIRE(p->V >= 1 && p->V <= ew::kMaxViews, MOP_EUNSUPPORTED, "n_views=%d outside [1,%d]", p->V, ew::kMaxViews);
   MOP_REQUIRE(p->Vp == 1 || p->Vp == p->V, MOP_EINVAL, "Vp must be 1 or V");
   MOP_REQUIRE(p->gate_mode == MOP_GATE_DENSE || p->gate_mode == MOP_GATE_LOWRANK || p->gate_mode == MOP_GATE_CONST, MOP_EINVAL,
               "bad gate_mode %d", p->gate_mode);

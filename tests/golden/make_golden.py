@@ -98,6 +98,8 @@ def edgewise_cases():
         ("ew_lensqk_lowrank", 16, 2, 12, dict(n_views=3, share_qkv=True, gate_mode="lowrank", gate_rank=2, use_lens_bank_qk=True, lens_qk_dilations=(1, 2, 3))),
         ("ew_lensqk_causal_dense", 16, 2, 12, dict(n_views=2, share_qkv=True, gate_mode="dense", use_k3=True, use_lens_bank_qk=True, lens_qk_causal=True)),
         ("ew_lensS_dense", 16, 2, 10, dict(n_views=3, share_qkv=True, gate_mode="dense", use_k3=True, use_lens_bank=True)),
+        ("ew_lensqk_single_v1", 16, 2, 9, dict(n_views=3, share_qkv=True, gate_mode="lowrank", gate_rank=2, use_lens_bank_qk=True,
+                                               lens_qk_dilations=(2,))),
         ("ew_lensS_lowrank_qk", 16, 2, 10, dict(n_views=4, share_qkv=True, gate_mode="lowrank", gate_rank=2, use_lens_bank=True,
                                                 lens_dilations=(1, 2), use_lens_bank_qk=True, lens_qk_dilations=(2, 3), lens_qk_causal=True)),
     ]

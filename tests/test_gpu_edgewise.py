@@ -21,7 +21,7 @@ BF16_TOL = 2e-2
 
 EW_GOLDEN = ["ew_lowrank_share_v5", "ew_lowrank_sep_v3", "ew_lowrank_share_v2_n64", "ew_dense_share_v2",
              "ew_dense_k3_share_v5", "ew_dense_k3_sep_v3", "ew_lensqk_lowrank", "ew_lensqk_causal_dense", "ew_lensS_dense",
-             "ew_lensS_lowrank_qk"]
+             "ew_lensS_lowrank_qk", "ew_lensqk_single_v1"]
 
 
 def _module_from_golden(case, device, dtype=torch.float32):
