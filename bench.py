@@ -363,7 +363,14 @@ def run_ours(args):
             cb, _ = cpu_throughput(steps=4, warmup=1, sample_batch=64) if CONFIG == "vit_e_cifar" else cpu_throughput(steps=1, warmup=0, sample_batch=4)
         extras = {}
         if world == 1 and not args.no_extras:
-            extras = extra_measurements(dev, flush, pk)
+            # secondary measurements run in a CHILD process after the headline numbers are final: a fault there cannot touch them
+            del flush
+            torch.cuda.empty_cache()
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only"], capture_output=True, text=True, timeout=420)
+                extras = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            except Exception as e:
+                extras = {"extras_error": repr(e)[:300]}
         line = {
             "metric": "vit_mop_train_images_per_sec", "value": world * BATCH / (step_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
@@ -483,7 +490,13 @@ def main():
                     help="vit_e_cifar: BASELINE.json configs[1] (headline); vit_b16: configs[2], ViT-B/16-MoP at 224x224")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 256)")
     ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient bucket size of the overlapped all-reduce (eager multi-GPU steps)")
+    ap.add_argument("--extras-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.extras_only:
+        torch.cuda.set_device(0)
+        dev = torch.device("cuda", 0)
+        print(json.dumps(extra_measurements(dev, torch.empty(256 << 20, dtype=torch.uint8, device=dev), peaks())), flush=True)
+        return
     select_config(args.config, args.batch)
     if args.config != "vit_e_cifar":
         args.no_extras = True

@@ -34,7 +34,7 @@ struct Layout {
   size_t N2, Nd;
   int n_maps;
   // map indices
-  int mS, mA, mP, mR, mM, mG, mD, mdA, mX0, mX1, mdG, mZ1, mH2, mDH2;
+  int mS, mA, mP, mR, mM, mG, mD, mdA, mX0, mX1, mdG, mZ1, mH2, mDH2, mX2;
   // vector offsets
   size_t o_maps, o_qb, o_kb, o_vb, o_yacc, o_rho, o_kap, o_a, o_b, o_cvec, o_vs1, o_vsL;
   size_t o_dyf, o_dv1, o_dvl, o_tt, o_dqa, o_dka, o_da, o_db, o_drho, o_dkap, o_z;
@@ -54,8 +54,8 @@ struct Layout {
     mM = m; m += 1;
     mG = m; m += 4;
     mL = m; m += V * nl;
-    mZ1 = mH2 = mDH2 = -1;
-    if (dense) { mZ1 = m; m += hid; if (k3) { mH2 = m; m += hid; } }
+    mZ1 = mH2 = mDH2 = mX2 = -1;
+    if (dense) { mZ1 = m; m += hid; if (k3) { mH2 = m; m += hid; mX2 = m; m += hid; } }   // X2 = gelu(gelu(z1)): the input of the 3x3 stage
     mD = mdA = mX0 = mX1 = mdG = -1;
     if (bwd) {
       mD = m; m += 1;
@@ -206,6 +206,7 @@ __device__ void dense_head_forward(const Ctx& c) {
       for (int ch = 0; ch < C; ++ch) z = fmaf(p.conv1_w[o * C + ch], feat[ch], z);
       c.map(L.mZ1 + o)[idx] = z;
       h[o] = gelu_tanh_(z);
+      if (L.k3) c.map(L.mX2 + o)[idx] = gelu_tanh_(h[o]);   // evaluated once per pixel (the 3x3 stage reads it at 9 neighbours)
     }
     if (!L.k3) {
       for (int t = 0; t < 4; ++t) {
@@ -230,7 +231,7 @@ __device__ void dense_head_forward(const Ctx& c) {
         if (jj < 0 || jj >= N) continue;
         size_t q = (size_t)ii * N + jj;
         for (int ch = 0; ch < hid; ++ch) {
-          float x = gelu_tanh_(gelu_tanh_(c.map(L.mZ1 + ch)[q]));
+          const float x = c.map(L.mX2 + ch)[q];
           for (int o = 0; o < hid; ++o) h2[o] = fmaf(p.mid3_w[((o * hid + ch) * 3 + u) * 3 + v], x, h2[o]);
         }
       }
@@ -454,27 +455,46 @@ __device__ void dense_head_backward(const Ctx& c, float* dhead) {
       }
     }
     __syncthreads();
-    // dW3[o,ch,u,v] = sum_p dh2[o,p] * gelu(gelu(z1[ch, p + (u-1,v-1)]));  db3[o] = sum_p dh2[o,p]
-    for (int idx = threadIdx.x; idx < nW3 + hid; idx += simt::kThreads) {
-      float s = 0.f;
-      if (idx < nW3) {
-        int v = idx % 3, u = (idx / 3) % 3, ch = (idx / 9) % hid, o = idx / (9 * hid);
-        const float* dh = c.map(L.mDH2 + o);
-        const float* z1 = c.map(L.mZ1 + ch);
-        for (int i = 0; i < N; ++i) {
-          int ii = i + u - 1;
-          if (ii < 0 || ii >= N) continue;
-          for (int j = 0; j < N; ++j) {
-            int jj = j + v - 1;
-            if (jj < 0 || jj >= N) continue;
-            s = fmaf(dh[(size_t)i * N + j], gelu_tanh_(gelu_tanh_(z1[(size_t)ii * N + jj])), s);
+    // dW3[o,ch,u,v] = sum_p dh2[o,p] * X2[ch, p + (u-1,v-1)];  db3[o] = sum_p dh2[o,p].  One warp per (o, ch) pair, lanes
+    // stride over the pixels, nine accumulators (the first version recomputed gelu(gelu(z1)) per output and pixel: 330 k
+    // instructions per output element)
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = simt::kThreads / 32;
+      for (int pair = warp; pair < hid * hid + hid; pair += nw) {
+        if (pair < hid * hid) {
+          const int o = pair / hid, ch = pair % hid;
+          const float* dh = c.map(L.mDH2 + o);
+          const float* x2 = c.map(L.mX2 + ch);
+          float acc[9];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+          for (int q = lane; q < N * N; q += 32) {
+            const int i = q / N, j = q % N;
+            const float d = dh[q];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int ii = i + u - 1;
+              if (ii < 0 || ii >= N) continue;
+#pragma unroll
+              for (int v = 0; v < 3; ++v) {
+                const int jj = j + v - 1;
+                if (jj < 0 || jj >= N) continue;
+                acc[u * 3 + v] = fmaf(d, x2[(size_t)ii * N + jj], acc[u * 3 + v]);
+              }
+            }
           }
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float sv = warp_sum(acc[t]);
+            if (lane == 0) dW3[(size_t)pair * 9 + t] = sv;
+          }
+        } else {
+          const float* dh = c.map(L.mDH2 + (pair - hid * hid));
+          float sv = 0.f;
+          for (int q = lane; q < N * N; q += 32) sv += dh[q];
+          sv = warp_sum(sv);
+          if (lane == 0) db3[pair - hid * hid] = sv;
         }
-        dW3[idx] = s;
-      } else {
-        const float* dh = c.map(L.mDH2 + (idx - nW3));
-        for (size_t q = 0; q < L.N2; ++q) s += dh[q];
-        db3[idx - nW3] = s;
       }
     }
     __syncthreads();
