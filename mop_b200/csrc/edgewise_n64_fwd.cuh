@@ -305,10 +305,13 @@ edgewise_fwd3_kernel(MopEdgewiseParams p, const __grid_constant__ CUtensorMap tm
         float a = 0.f;
         if (k < r) {
           a = bias[q];
-          const float* wr = W + q * C;
+          const float* wr = W + q * C;   // C = 2V + 2 is even: rows are 8-byte aligned, warp-uniform (broadcast) 8-byte loads
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c)
-            if (c < C) a = fmaf(wr[c], ft[c], a);
+          for (int c = 0; c < kMaxC; c += 2)
+            if (c < C) {
+              const float2 w2 = *reinterpret_cast<const float2*>(wr + c);
+              a = fmaf(w2.x, ft[c], fmaf(w2.y, ft[c + 1], a));
+            }
         }
         acc[j] = a;
       }

@@ -35,7 +35,11 @@ for l in sass[start + 1:]:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# a report may hold several kernels: keep the launches whose (demangled) name contains the function name of `kernel`
+fname = re.sub(r"^_ZN?\d*", "", a.kernel)
+fname = re.search(r"[A-Za-z_][A-Za-z0-9_]*kernel[A-Za-z0-9_]*", a.kernel)
+flt = ["--kernel-name", "regex:" + fname.group(0)] if fname else []
+out = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", *flt], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 ins = [r for r in rows[2:] if len(r) >= len(hdr)]
