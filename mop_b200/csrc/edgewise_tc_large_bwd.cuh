@@ -17,11 +17,10 @@
 //      part of dS_k and D g_chain / (F + eps); the row-factor gradients da are fp32 register sums;
 //   3  column-factor gradients db = sum_t dG_t^T a (MMA), gate-head parameter partials, feature-mean gradients;
 //   4  value gradients dV = (A^T dY) vs_1 + (F^T dY) w vs_V, v_scale partials, chain_value_logit partial;
-//   5  chain seeds and sweeps.  For the F chain (k = V-1..1):  X' = X A_k^T,  dA_k = P_{k-1}^T X,
-//      C = A_k (dA_k - rowsum(dA_k A_k)); same for the R chain (k = 0..V-2) with the suffix products;
-//   6  every contribution C to dS_k (chain links, direct part + rank-1 feature terms) goes straight through
-//      T = C K, U = C^T Q and is accumulated into fp32 dQ / dK rows (softmax backward is linear, so the
-//      contributions never have to be summed as maps).
+//   5  chain seeds and sweeps.  The F chain (k = V-1..1):  X' = X A_k^T,  dA_k = P_{k-1}^T X, recorded as bf16 rows in the
+//      scratch; the R chain (k = 0..V-2, suffix products) forms its own dA_k, adds the recorded one, and finishes the view:
+//      dS_k = A_k (dA_k - rowsum(dA_k A_k)) + direct part + rank-1 feature terms;
+//   6  each dS_k goes straight through T = dS_k K, U = dS_k^T Q into fp32 dQ / dK rows (one pair of contractions per view).
 #pragma once
 #include "edgewise_tc_large.cuh"
 
@@ -46,7 +45,8 @@ constexpr int kSlotDS = 18;     // direct part of dS_k, 5 maps
 constexpr int kSlotHf = 23;     // D g_chain / (F + eps)
 constexpr int kSlotXN = 24;     // next running product of a sweep (X tile image, kBufX bytes)
 constexpr int kSlotAcc = 25;    // fp32 dQ rows [208][64] (slot 25) and dK rows (slot 26)
-constexpr int kBwdSlots = 27;
+constexpr int kSlotDAF = 27;    // dA_k of the F chain (bf16), 5 maps: added to the R chain's dA_k before the softmax backward
+constexpr int kBwdSlots = 32;
 
 struct __align__(128) SmemBwd {
   unsigned char X[kBufX];
@@ -889,45 +889,64 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       acc_started = true;
       sync_cta();   // the A buffer may be refilled
     };
-    // C[m,:] = Ak[m,:] * (x[m,:] - sum_j x[m,j] Ak[m,j]) for this thread's row m.  A_k sits in the A buffer (bulk loaded)
-    // and is overwritten in place by C (bf16); x comes from the accumulator (from_tmem) or from the X tile.
-    // Rows >= N of A_k are zero, so C keeps them zero.
-    auto softmax_bwd_row = [&](bool from_tmem) {
-      if (!warp_on) return;   // (warp-uniform: the TMEM loads below are warp-collective)
+    // dS_k rows, complete: x = dA_k of the R chain (accumulator, or the X tile for the final link) + dA_k of the F chain
+    // (scratch, bf16);  C[m,:] = Ak[m,:] * (x[m,:] - sum_j x[m,j] Ak[m,j]) + direct part of dS_k (scratch, bf16) + rank-1
+    // feature terms, for this thread's row m.  A_k sits in the A buffer and is overwritten in place by C (bf16).  The summed x
+    // is parked in the accumulator columns between the two passes.  Rows >= N stay zero.
+    auto softmax_bwd_row = [&](bool from_tmem, int k) {
+      if (!warp_on) return;   // (warp-uniform: the TMEM accesses below are warp-collective)
       const bool has_row = row < kRA;
+      float rt = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxV; ++i)
+        if (i == k) rt = rterm[i];
       float dot = 0.f;
+      uint4 nx[2];
+      nx[0] = has_row ? ldcg16(map_chunk(kSlotDAF + k, 0)) : make_uint4(0, 0, 0, 0);
+      nx[1] = has_row ? ldcg16(map_chunk(kSlotDAF + k, 1)) : make_uint4(0, 0, 0, 0);
       for (int c = 0; c < KS; ++c) {
-        float v[16], a8[8];
+        float v[16], a8[8], f8[8];
         if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
+        const uint4 cur[2] = {nx[0], nx[1]};
+        if (c + 1 < KS && has_row) { nx[0] = ldcg16(map_chunk(kSlotDAF + k, 2 * c + 2)); nx[1] = ldcg16(map_chunk(kSlotDAF + k, 2 * c + 3)); }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
+          unpack8(cur[hh], f8);
           unpack8(has_row ? *reinterpret_cast<const uint4*>(sm.A + (2 * c + hh) * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0), a8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dot = fmaf(v[8 * hh + e], a8[e], dot);
+          for (int e = 0; e < 8; ++e) { v[8 * hh + e] += f8[e]; dot = fmaf(v[8 * hh + e], a8[e], dot); }
         }
+        tmem_st_32x32b_x16(tl + 16 * c, v);
       }
+      tmem_st_wait();
+      nx[0] = has_row ? ldcg16(map_chunk(kSlotDS + k, 0)) : make_uint4(0, 0, 0, 0);
+      nx[1] = has_row ? ldcg16(map_chunk(kSlotDS + k, 1)) : make_uint4(0, 0, 0, 0);
       for (int c = 0; c < KS; ++c) {
-        float v[16], a8[8];
-        if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
+        float v[16], a8[8], d8[8];
+        tmem_ld_32x32b_x16(tl + 16 * c, v);
+        tmem_ld_wait();
+        const uint4 cur[2] = {nx[0], nx[1]};
+        if (c + 1 < KS && has_row) { nx[0] = ldcg16(map_chunk(kSlotDS + k, 2 * c + 2)); nx[1] = ldcg16(map_chunk(kSlotDS + k, 2 * c + 3)); }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           unsigned char* ap = sm.A + (2 * c + hh) * (kRA * 16) + row * 16;
-          if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
           unpack8(has_row ? *reinterpret_cast<const uint4*>(ap) : make_uint4(0, 0, 0, 0), a8);
+          unpack8(cur[hh], d8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) a8[e] = row_ok ? a8[e] * (v[8 * hh + e] - dot) : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            const int j = 16 * c + 8 * hh + e;
+            a8[e] = (row_ok && j < N) ? fmaf(a8[e], v[8 * hh + e] - dot, d8[e] + rt + cprime_s[k * kNmax + j]) : 0.f;
+          }
           if (has_row) *reinterpret_cast<uint4*>(ap) = pack8(a8);
         }
       }
     };
-    // one sweep: X holds the seed.  order[s] = view visited at step s (V-1 steps), pslot(s) = scratch slot of the
-    // partial product multiplying X from the left (transposed); last_view = view of the final link (dA += X).
-    // One sweep.  On entry X holds the seed (written by its row owners) and the load of the first view's A_k into the A
-    // buffer is in flight; on exit the load of `next_slot` is in flight.  Loads are issued as early as their target buffer
-    // is free so that they overlap the epilogues: P during the X' stash, X' during the softmax backward + contribution,
-    // the next A_k during the contribution's epilogue.
-    auto sweep = [&](bool fchain, int next_slot) {
+    // One sweep.  On entry X holds the seed (written by its row owners) and the first view's A_k is in (or on its way into)
+    // the A buffer.  Step s visits view k with the partial product `pslot` multiplying X from the left (transposed); the
+    // final link is dA += X.  Loads are issued as early as their target buffer is free so that they overlap the epilogues:
+    // P during the X' stash, X' and the next A_k during the dA epilogue / the softmax backward + contribution.
+    auto sweep = [&](bool fchain) {
       for (int s = 0; s < V - 1; ++s) {
         const int k = fchain ? V - 1 - s : s;
         const int knext = fchain ? k - 1 : k + 1;   // view of the next step (or of the final link)
@@ -962,27 +981,58 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
           if (t == 0) { mma_at_x(); commit(); }     // dA_k part = P^T X
           mma_wait();
         }
-        sync_cta();      // A buffer (P) and X are free: A_k comes back (turned into C in place), X' replaces X
-        load_start(sm.A, slot(kSlotA + k), map_bytes);
-        load_start(sm.X, slot(kSlotXN), xmap_bytes);
-        cp_async_wait<1>();   // A_k only
-        fence_async_smem();
-        __syncthreads();
-        softmax_bwd_row(true);
-        contribute(k, kSlotA + knext);
+        sync_cta();      // A buffer (P) and X are free
+        if (fchain) {
+          // the F chain only records its dA_k (bf16 rows in the scratch): the R chain adds it to its own dA_k, so that every
+          // view goes through ONE softmax backward and ONE pair of dQ / dK contractions.  The next view's A and X' load meanwhile.
+          load_start(sm.A, slot(kSlotA + knext), map_bytes);
+          load_start(sm.X, slot(kSlotXN), xmap_bytes);
+          if (warp_on) {
+            for (int c = 0; c < KS; ++c) {
+              float v[16];
+              tmem_ld_32x32b_x16(tl + 16 * c, v);
+              tmem_ld_wait();
+              if (row < kRA) {
+                uint4 lo, hi;
+                pack16(v, 1.f, lo, hi);
+                if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(map_chunk(kSlotDAF + k, 2 * c)) = lo;
+                *reinterpret_cast<uint4*>(map_chunk(kSlotDAF + k, 2 * c + 1)) = hi;
+              }
+            }
+          }
+        } else {
+          // A_k comes back (turned into dS_k in place), X' replaces X
+          load_start(sm.A, slot(kSlotA + k), map_bytes);
+          load_start(sm.X, slot(kSlotXN), xmap_bytes);
+          cp_async_wait<1>();   // A_k only
+          fence_async_smem();
+          __syncthreads();
+          softmax_bwd_row(true, k);
+          contribute(k, kSlotA + knext);
+        }
       }
       // final link: dA += X
-      const int kl = fchain ? 0 : V - 1;
       cp_async_wait<0>();
       fence_async_smem();
-      __syncthreads();   // A_kl and the last X' landed
-      softmax_bwd_row(false);
-      contribute(kl, next_slot);
+      __syncthreads();   // the last X' landed (and the A map whose load the last step started)
+      if (fchain) {
+        // dA_0 of the F chain is the running product itself: this thread's row of X goes to the scratch.  The A buffer
+        // already holds A_0, the first view of the R sweep.
+        if (row < kRA) {
+          for (int c = 0; c < 2 * KS; ++c)
+            *reinterpret_cast<uint4*>(map_chunk(kSlotDAF + 0, c)) =
+                row_ok ? *reinterpret_cast<const uint4*>(sm.X + c * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0);
+        }
+      } else {
+        softmax_bwd_row(false, V - 1);
+        contribute(V - 1, -1);
+      }
     };
     MOP_TS(T7);
     sync_cta();
     load_start(sm.A, slot(kSlotA + V - 1), map_bytes);   // first view of the F sweep
-    sweep(true, kSlotA + 0);                              // ... and of the R sweep
+    sweep(true);
     // seed of the R sweep: X = (drho_R[i] + dkap_R[j]) / (R + eps)
     if (row < kRX) {
       uint4 rnext[2];
@@ -1001,31 +1051,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       }
     }
     MOP_TS(T8pre);
-    sweep(false, kSlotDS + 0);
+    sweep(false);
     MOP_TS(T9);
-    // direct parts + rank-1 feature terms
-    for (int k = 0; k < V; ++k) {
-      load_wait();   // the direct part of dS_k (its load was started by the previous contribution)
-      if (row_ok) {
-        float rt = 0.f;
-#pragma unroll
-        for (int i = 0; i < kMaxV; ++i)
-          if (i == k) rt = rterm[i];
-        for (int c = 0; c < 2 * KS; ++c) {
-          float v8[8];
-          unsigned char* ptr = sm.A + c * (kRA * 16) + row * 16;
-          unpack8(*reinterpret_cast<const uint4*>(ptr), v8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = 8 * c + e;
-            v8[e] = j < N ? v8[e] + rt + cprime_s[k * kNmax + j] : 0.f;
-          }
-          *reinterpret_cast<uint4*>(ptr) = pack8(v8);
-        }
-      }
-      contribute(k, k + 1 < V ? kSlotDS + k + 1 : -1);
-    }
-    MOP_TS(T10);
     // =================================================================================================
     // outputs: dQ, dK rows; q/k scale partials
     // =================================================================================================
