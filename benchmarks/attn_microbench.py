@@ -28,18 +28,40 @@ def peak():
         return 1590.0, "fallback"
 
 
-def timeit(fn, iters, flush):
+def timeit(fn, iters, flush, graph=True):
+    """Median device time of fn().  The launches of one call are captured in a CUDA graph and the replays are timed (the
+    training step replays graphs too): for the small shapes an eager call is bound by the ~10 host-side launches, not by
+    the kernels.  Falls back to eager launches if the capture fails."""
     for _ in range(10):
         fn()
     torch.cuda.synchronize()
+    run = fn
+    if graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            run = g.replay
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+        except Exception:
+            torch.cuda.synchronize()
+            run = fn
     evs = []
     for _ in range(iters):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
+        a.record(); run(); b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
     ts = sorted(x.elapsed_time(y) for x, y in evs)
+    timeit.last_launch = "cuda graph replay" if run is not fn else "eager"
     return ts[len(ts) // 2]
 
 
@@ -57,7 +79,8 @@ def sdpa_case(name, B, H, N, dk, causal, impl, iters, flush, dtype=torch.bfloat1
         t_f = timeit(fwd, iters, flush)
     t_fb = timeit(fb, iters, flush)
     return dict(shape=name, op="sdpa", impl=MF.last_impl["sdpa_fwd"], B=B, H=H, N=N, dk=dk, causal=causal, dtype=str(dtype),
-                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9)
+                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9,
+                launch=timeit.last_launch)
 
 
 def edgewise_case(name, B, H, N, dk, V, r, impl, iters, flush, dtype=torch.bfloat16):
@@ -79,7 +102,8 @@ def edgewise_case(name, B, H, N, dk, V, r, impl, iters, flush, dtype=torch.bfloa
         t_f = timeit(call, iters, flush)
     t_fb = timeit(fb, iters, flush)
     return dict(shape=name, op="edgewise", impl=MF.last_impl["edgewise_fwd"], B=B, H=H, N=N, dk=dk, V=V, r=r, dtype=str(dtype),
-                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9)
+                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9,
+                launch=timeit.last_launch)
 
 
 def quartet_case(name, B, H, T, dk, impl, iters, flush, dtype=torch.bfloat16):
@@ -96,7 +120,8 @@ def quartet_case(name, B, H, T, dk, impl, iters, flush, dtype=torch.bfloat16):
         t_f = timeit(call, iters, flush)
     t_fb = timeit(fb, iters, flush)
     return dict(shape=name, op="quartet", impl=MF.last_impl["quartet_fwd"], B=B, H=H, N=T, dk=dk, dtype=str(dtype),
-                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9)
+                fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=fl / t_f / 1e9, fwd_bwd_tflops=3 * fl / t_fb / 1e9,
+                launch=timeit.last_launch)
 
 
 def main():

@@ -25,7 +25,8 @@
 #include "edgewise_tc_large.cuh"
 
 #ifdef MOP_PHASE_TIMING
-#define MOP_TS(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0) printf("ts %s %lld\n", #name, clock64()); } while (0)
+// stamps are kept in local memory and printed after the first problem (a printf per stamp costs ~60k cycles)
+#define MOP_TS(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0 && ts_n < 32) { ts_v[ts_n] = clock64(); ts_name[ts_n++] = #name; } } while (0)
 #else
 #define MOP_TS(name) do { } while (0)
 #endif
@@ -44,7 +45,7 @@ constexpr int kSlotDG = 14;     // gate pre-activation gradients, 4 maps
 constexpr int kSlotDS = 18;     // direct part of dS_k, 5 maps
 constexpr int kSlotHf = 23;     // D g_chain / (F + eps)
 constexpr int kSlotXN = 24;     // next running product of a sweep (X tile image, kBufX bytes)
-constexpr int kSlotAcc = 25;    // fp32 dQ rows [208][64] (slot 25) and dK rows (slot 26)
+constexpr int kSlotAcc = 25;    // fp32 dQ rows, [16][208] float4 (slot 25) and dK rows (slot 26)
 constexpr int kSlotDAF = 27;    // dA_k of the F chain (bf16), 5 maps: added to the R chain's dA_k before the softmax backward
 constexpr int kBwdSlots = 32;
 
@@ -169,6 +170,11 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
   __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(p.dqkv);
   const size_t hd = (size_t)H * dk;
   const int G = p.B * H;
+#ifdef MOP_PHASE_TIMING
+  long long ts_v[32];
+  const char* ts_name[32];
+  int ts_n = 0;
+#endif
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
     auto in_row = [&](int n) { return qkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };
@@ -821,13 +827,15 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       }
     }
     bool acc_started = false;   // dQ / dK rows in the scratch hold valid partial sums
-    float* dq_acc = reinterpret_cast<float*>(slot(kSlotAcc)) + (size_t)row * 64;
-    float* dk_acc = reinterpret_cast<float*>(slot(kSlotAcc + 1)) + (size_t)row * 64;
+    // fp32 dQ / dK rows, stored [16 groups of 4 features][208 rows] so that the one-thread-per-row accesses coalesce
+    float4* dq_acc = reinterpret_cast<float4*>(slot(kSlotAcc)) + row;
+    float4* dk_acc = reinterpret_cast<float4*>(slot(kSlotAcc + 1)) + row;
     // C (bf16, all rows, in the A buffer) is one additive part of dS_k:  T = C K -> dQ, scale sums ; U = C^T Q -> dK
     // next_slot >= 0: once both warpgroups' MMAs have read C, that scratch map starts to load into the A buffer, so that its
     // latency hides behind the epilogue (the caller waits for it with load_wait before the next use of the A buffer).
     auto contribute = [&](int k, int next_slot) {
       publish_cta();   // C rows written by their owners
+      if (k == 1) MOP_TS(c_pub);
       if (blk_on) {
         if (t == 0) {
           mma_a_tile(0, sK, kRA);
@@ -836,23 +844,25 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         }
         mma_wait();
       }
+      if (k == 1) MOP_TS(c_mma);
       if (next_slot >= 0) {
         sync_cta();
         load_start(sm.A, slot(next_slot), map_bytes);
       }
+      if (k == 1) MOP_TS(c_sync);
       if (blk_on) {
         if (warp_on) {
           // T part: dQ rows (fp32 partial sums live in the scratch; all loads are issued before the first use)
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
-            float* acc = part ? dk_acc : dq_acc;
+            float4* acc = part ? dk_acc : dq_acc;
             float4 av[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (acc_started && row_ok) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (4 * i < dk) av[i] = __ldcg(reinterpret_cast<const float4*>(acc + 4 * i));
+                if (4 * i < dk) av[i] = __ldcg(acc + i * kNmax);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -881,8 +891,9 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
             if (row_ok) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (4 * i < dk) *reinterpret_cast<float4*>(acc + 4 * i) = av[i];
+                if (4 * i < dk) acc[i * kNmax] = av[i];
             }
+            if (k == 1) MOP_TS(c_part);
           }
         }
       }
@@ -901,45 +912,63 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       for (int i = 0; i < kMaxV; ++i)
         if (i == k) rt = rterm[i];
       float dot = 0.f;
-      uint4 nx[2];
-      nx[0] = has_row ? ldcg16(map_chunk(kSlotDAF + k, 0)) : make_uint4(0, 0, 0, 0);
-      nx[1] = has_row ? ldcg16(map_chunk(kSlotDAF + k, 1)) : make_uint4(0, 0, 0, 0);
-      for (int c = 0; c < KS; ++c) {
-        float v[16], a8[8], f8[8];
-        if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
-        const uint4 cur[2] = {nx[0], nx[1]};
-        if (c + 1 < KS && has_row) { nx[0] = ldcg16(map_chunk(kSlotDAF + k, 2 * c + 2)); nx[1] = ldcg16(map_chunk(kSlotDAF + k, 2 * c + 3)); }
+      // the scratch rows come from L2 (~1k cycles away with two warps per scheduler): four 16-column chunks are in flight
+      uint4 cur[8], nxt[8];
+      auto fetch4 = [&](uint4* dst, int s, int c0) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
-          unpack8(cur[hh], f8);
-          unpack8(has_row ? *reinterpret_cast<const uint4*>(sm.A + (2 * c + hh) * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0), a8);
+        for (int i = 0; i < 8; ++i)
+          dst[i] = (has_row && c0 + (i >> 1) < KS) ? ldcg16(map_chunk(s, 2 * c0 + i)) : make_uint4(0, 0, 0, 0);
+      };
+      fetch4(cur, kSlotDAF + k, 0);
+      for (int c0 = 0; c0 < KS; c0 += 4) {
+        fetch4(nxt, kSlotDAF + k, c0 + 4);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { v[8 * hh + e] += f8[e]; dot = fmaf(v[8 * hh + e], a8[e], dot); }
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c0 + ci;
+          if (c < KS) {
+            float v[16], a8[8], f8[8];
+            if (from_tmem) { tmem_ld_32x32b_x16(tl + 16 * c, v); tmem_ld_wait(); }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              if (!from_tmem) unpack8(row < kRX ? *reinterpret_cast<const uint4*>(sm.X + (2 * c + hh) * (kRX * 16) + row * 16) : make_uint4(0, 0, 0, 0), v + 8 * hh);
+              unpack8(cur[2 * ci + hh], f8);
+              unpack8(has_row ? *reinterpret_cast<const uint4*>(sm.A + (2 * c + hh) * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0), a8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { v[8 * hh + e] += f8[e]; dot = fmaf(v[8 * hh + e], a8[e], dot); }
+            }
+            tmem_st_32x32b_x16(tl + 16 * c, v);
+          }
         }
-        tmem_st_32x32b_x16(tl + 16 * c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       }
       tmem_st_wait();
-      nx[0] = has_row ? ldcg16(map_chunk(kSlotDS + k, 0)) : make_uint4(0, 0, 0, 0);
-      nx[1] = has_row ? ldcg16(map_chunk(kSlotDS + k, 1)) : make_uint4(0, 0, 0, 0);
-      for (int c = 0; c < KS; ++c) {
-        float v[16], a8[8], d8[8];
-        tmem_ld_32x32b_x16(tl + 16 * c, v);
-        tmem_ld_wait();
-        const uint4 cur[2] = {nx[0], nx[1]};
-        if (c + 1 < KS && has_row) { nx[0] = ldcg16(map_chunk(kSlotDS + k, 2 * c + 2)); nx[1] = ldcg16(map_chunk(kSlotDS + k, 2 * c + 3)); }
+      fetch4(cur, kSlotDS + k, 0);
+      for (int c0 = 0; c0 < KS; c0 += 4) {
+        fetch4(nxt, kSlotDS + k, c0 + 4);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          unsigned char* ap = sm.A + (2 * c + hh) * (kRA * 16) + row * 16;
-          unpack8(has_row ? *reinterpret_cast<const uint4*>(ap) : make_uint4(0, 0, 0, 0), a8);
-          unpack8(cur[hh], d8);
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = c0 + ci;
+          if (c < KS) {
+            float v[16], a8[8], d8[8];
+            tmem_ld_32x32b_x16(tl + 16 * c, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = 16 * c + 8 * hh + e;
-            a8[e] = (row_ok && j < N) ? fmaf(a8[e], v[8 * hh + e] - dot, d8[e] + rt + cprime_s[k * kNmax + j]) : 0.f;
+            for (int hh = 0; hh < 2; ++hh) {
+              unsigned char* ap = sm.A + (2 * c + hh) * (kRA * 16) + row * 16;
+              unpack8(has_row ? *reinterpret_cast<const uint4*>(ap) : make_uint4(0, 0, 0, 0), a8);
+              unpack8(cur[2 * ci + hh], d8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = 16 * c + 8 * hh + e;
+                a8[e] = (row_ok && j < N) ? fmaf(a8[e], v[8 * hh + e] - dot, d8[e] + rt + cprime_s[k * kNmax + j]) : 0.f;
+              }
+              if (has_row) *reinterpret_cast<uint4*>(ap) = pack8(a8);
+            }
           }
-          if (has_row) *reinterpret_cast<uint4*>(ap) = pack8(a8);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       }
     };
     // One sweep.  On entry X holds the seed (written by its row owners) and the first view's A_k is in (or on its way into)
@@ -953,13 +982,16 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         int pslot;
         if (fchain) pslot = (k - 1 == 0) ? kSlotA + 0 : kSlotPfx + (k - 1) - 1;                 // P_{k-1}
         else pslot = (k + 1 == V - 1) ? kSlotA + V - 1 : kSlotSfx + (k + 1) - 1;               // A_{V-1}..A_{k+1}
+        if (s == 1) MOP_TS(s_begin);
         cp_async_wait<0>();
         publish_cta();   // A_k and X (seed or reloaded image) landed / visible
+        if (s == 1) MOP_TS(s_landed);
         if (blk_on) {
           if (t == 0) { mma_x_at(); commit(); }     // X' = X A_k^T
           mma_wait();
         }
         sync_cta();      // both warpgroups' MMAs have read A_k
+        if (s == 1) MOP_TS(s_mma1);
         load_start(sm.A, slot(pslot), map_bytes);
         if (warp_on) {
           for (int c = 0; c < KS; ++c) {
@@ -975,13 +1007,16 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
             }
           }
         }
+        if (s == 1) MOP_TS(s_stash);
         cp_async_wait<0>();
         publish_cta();   // P landed; the X' image is complete in the scratch
+        if (s == 1) MOP_TS(s_pland);
         if (blk_on) {
           if (t == 0) { mma_at_x(); commit(); }     // dA_k part = P^T X
           mma_wait();
         }
         sync_cta();      // A buffer (P) and X are free
+        if (s == 1) MOP_TS(s_mma2);
         if (fchain) {
           // the F chain only records its dA_k (bf16 rows in the scratch): the R chain adds it to its own dA_k, so that every
           // view goes through ONE softmax backward and ONE pair of dQ / dK contractions.  The next view's A and X' load meanwhile.
@@ -1008,8 +1043,11 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
           cp_async_wait<1>();   // A_k only
           fence_async_smem();
           __syncthreads();
+          if (s == 1) MOP_TS(s_aland);
           softmax_bwd_row(true, k);
+          if (s == 1) MOP_TS(s_smbwd);
           contribute(k, kSlotA + knext);
+          if (s == 1) MOP_TS(s_contrib);
         }
       }
       // final link: dA += X
@@ -1053,6 +1091,10 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
     MOP_TS(T8pre);
     sweep(false);
     MOP_TS(T9);
+#ifdef MOP_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0)
+      for (int i = 0; i < ts_n; ++i) printf("ts %s %lld\n", ts_name[i], ts_v[i]);
+#endif
     // =================================================================================================
     // outputs: dQ, dK rows; q/k scale partials
     // =================================================================================================
@@ -1060,8 +1102,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (c * 8 < dk) {
-          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(dq_acc + 8 * c)), a1 = __ldcg(reinterpret_cast<const float4*>(dq_acc + 8 * c + 4));
-          const float4 b0 = __ldcg(reinterpret_cast<const float4*>(dk_acc + 8 * c)), b1 = __ldcg(reinterpret_cast<const float4*>(dk_acc + 8 * c + 4));
+          const float4 a0 = __ldcg(dq_acc + (2 * c) * kNmax), a1 = __ldcg(dq_acc + (2 * c + 1) * kNmax);
+          const float4 b0 = __ldcg(dk_acc + (2 * c) * kNmax), b1 = __ldcg(dk_acc + (2 * c + 1) * kNmax);
           const float qa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, ka[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           *reinterpret_cast<uint4*>(out_row(row) + 8 * c) = pack8(qa);
           *reinterpret_cast<uint4*>(out_row(row) + hd + 8 * c) = pack8(ka);
