@@ -76,33 +76,6 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.f + f
 
 __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
-// column sums over the 32 rows of a warp: v[e] is this lane's value of column e (16 columns).  After the
-// butterfly lane L (L even) holds the sum of column bitrev-ish index col(L); returns it, *col receives the index.
-__device__ __forceinline__ float warp_colsum16(const float* v, int lane, int* col) {
-  float a8[8], a4[4], a2[2];
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
-    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = h8 ? a8[i] : a8[i + 4], keep = h8 ? a8[i + 4] : a8[i];
-    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = h4 ? a4[i] : a4[i + 2], keep = h4 ? a4[i + 2] : a4[i];
-    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float send = h2 ? a2[0] : a2[1], keep = h2 ? a2[1] : a2[0];
-  float s = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  *col = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
-  return s;
-}
-
 // 16 fp32 -> 2 x (8 bf16), optionally scaled
 // (callers zero v[] for padded rows themselves: 0 * NaN would not be zero)
 __device__ __forceinline__ void pack16(const float* v, float sc, uint4& lo, uint4& hi) {

@@ -110,9 +110,20 @@ __device__ inline void write_hilo_tiles(const float* G, unsigned char* dst) {
     *reinterpret_cast<uint4*>(dst + kT64 + ch * 1024 + r * 16) = pack8(lo);
   }
 }
-// 8 KB tile image global -> shared (plain copy)
-__device__ __forceinline__ void copy_tile64(unsigned char* dst, const unsigned char* src) {
-  for (int idx = threadIdx.x; idx < kT64 / 16; idx += blockDim.x) *reinterpret_cast<uint4*>(dst + idx * 16) = *reinterpret_cast<const uint4*>(src + idx * 16);
+// n (<= 4) 8 KB tile images global -> shared, 256 threads: every load is issued before the first store, so the CTA pays one
+// L2 round trip (a copy loop per tile paid eight: these tiles are read once per CTA, at the end of a short kernel)
+__device__ __forceinline__ void copy_tiles64(unsigned char* const* dst, const unsigned char* const* src, int n) {
+  uint4 v[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (i < n) v[i][j] = __ldg(reinterpret_cast<const uint4*>(src[i] + (threadIdx.x + 256 * j) * 16));
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (i < n) *reinterpret_cast<uint4*>(dst[i] + (threadIdx.x + 256 * j) * 16) = v[i][j];
 }
 // Z[128 x 64] at TMEM column dcol = X (Mhi + Mlo): X a [128 x 64] K-major tile, M symmetric (tile images in shared memory)
 __device__ __forceinline__ void mma_x_sym(uint32_t d_tmem, uint32_t xtile, uint32_t mhi, uint32_t mlo) {
@@ -788,25 +799,52 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   const float i1 = 1.f / (s1v + mx.eps), i2 = mx.quart ? 1.f / (s2v + mx.eps) : 0.f;
   const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
-  float dlt = 0.f;
-  if (row_ok) {
-    const __nv_bfloat16* yr = reinterpret_cast<const __nv_bfloat16*>(p.y) + at(p, b, gi, h);
-    const __nv_bfloat16* dr = reinterpret_cast<const __nv_bfloat16*>(p.dy) + at(p, b, gi, h);
-    const float* y32 = p.y_f32 ? p.y_f32 + at(p, b, gi, h) : nullptr;
-    for (int d0 = 0; d0 < dk; d0 += 8) {
-      float a[8], c[8];
-      if (y32) {
-        const float4 u0 = *reinterpret_cast<const float4*>(y32 + d0), u1 = *reinterpret_cast<const float4*>(y32 + d0 + 4);
-        a[0] = u0.x; a[1] = u0.y; a[2] = u0.z; a[3] = u0.w; a[4] = u1.x; a[5] = u1.y; a[6] = u1.z; a[7] = u1.w;
-      } else {
-        unpack8(*reinterpret_cast<const uint4*>(yr + d0), a);
-      }
-      unpack8(*reinterpret_cast<const uint4*>(dr + d0), c);
+  // delta = dO . y per query row: eight lanes share a row (32 B of fp32 y and 16 B of dO per lane and pass: four rows = 1 KB
+  // per warp instruction, all of a warp's 16 rows in flight) - one thread per 256-byte row costs 32 sectors per load.
+  {
+    const int wrp = tid >> 5, sub = lane >> 3, l8 = lane & 7;
+    float part[4];
+    float4 ya[4], yb[4];
+    uint4 da[4], yh[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dlt = fmaf(a[e], c[e], dlt);
+    for (int ps = 0; ps < 4; ++ps) {
+      const int r = q0 + 16 * wrp + 4 * ps + sub;
+      const bool ok = r < T && 8 * l8 < dk;
+      const size_t o = at(p, b, ok ? r : 0, h) + 8 * l8;
+      da[ps] = ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + o)) : make_uint4(0, 0, 0, 0);
+      if (p.y_f32) {
+        ya[ps] = ok ? __ldg(reinterpret_cast<const float4*>(p.y_f32 + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        yb[ps] = ok ? __ldg(reinterpret_cast<const float4*>(p.y_f32 + o + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        yh[ps] = ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.y) + o)) : make_uint4(0, 0, 0, 0);
+      }
     }
-    if (wg == 0) (reinterpret_cast<float*>(ws + w.delta) + (size_t)bh * T)[gi] = dlt;   // for bwd_dkdv
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      float a[8], c[8];
+      if (p.y_f32) {
+        a[0] = ya[ps].x; a[1] = ya[ps].y; a[2] = ya[ps].z; a[3] = ya[ps].w; a[4] = yb[ps].x; a[5] = yb[ps].y; a[6] = yb[ps].z; a[7] = yb[ps].w;
+      } else {
+        unpack8(yh[ps], a);
+      }
+      unpack8(da[ps], c);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(a[e], c[e], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      part[ps] = d;
+    }
+    if (l8 == 0) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) sm.gx[0][0][16 * wrp + 4 * ps + sub] = part[ps];
+    }
   }
+  __syncthreads();
+  const float dlt = row_ok ? sm.gx[0][0][t] : 0.f;
+  if (row_ok && wg == 0) (reinterpret_cast<float*>(ws + w.delta) + (size_t)bh * T)[gi] = dlt;   // for bwd_dkdv
+  __syncthreads();   // gx is written again by the epilogue only, but keep the read and any later write apart
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0, ph_in = 0, ph_out = 0;
   float g1 = 0.f, g2 = 0.f, sc0 = 0.f, sc1 = 0.f;
@@ -932,11 +970,11 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   sm.gx[wg][0][t] = g1;
   sm.gx[wg][1][t] = g2;
   // G q by MMA: the Gram tiles (hi, lo per map) go to the dead key / value / W buffers; Z1 -> columns [0,64), Z2 -> [64,128)
-  copy_tile64(sm.K1[0], ws + w.gram + (size_t)bh * 2 * kT64);
-  copy_tile64(sm.K2[0], ws + w.gram + (size_t)bh * 2 * kT64 + kT64);
-  if (mx.quart) {
-    copy_tile64(sm.V[0], ws + w.gram + (BH + bh) * 2 * kT64);
-    copy_tile64(sm.W1[0], ws + w.gram + (BH + bh) * 2 * kT64 + kT64);
+  {
+    unsigned char* const dst[4] = {sm.K1[0], sm.K2[0], sm.V[0], sm.W1[0]};
+    const unsigned char* const src[4] = {ws + w.gram + (size_t)bh * 2 * kT64, ws + w.gram + (size_t)bh * 2 * kT64 + kT64,
+                                         ws + w.gram + (BH + bh) * 2 * kT64, ws + w.gram + (BH + bh) * 2 * kT64 + kT64};
+    copy_tiles64(dst, src, mx.quart ? 4 : 2);
   }
   publish();
   if (tid == 0) {
@@ -1281,11 +1319,11 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
   }
   // M kc by MMA: the M tiles (hi, lo per map) go to the dead query / dO buffers; Z1 -> columns [0,64), Z2 -> [64,128)
   __syncthreads();
-  copy_tile64(sm.Q[0], ws + w.mmat + (size_t)bh * 2 * kT64);
-  copy_tile64(sm.Q[1], ws + w.mmat + (size_t)bh * 2 * kT64 + kT64);
-  if (mx.quart) {
-    copy_tile64(sm.dO[0], ws + w.mmat + (BH + bh) * 2 * kT64);
-    copy_tile64(sm.dO[1], ws + w.mmat + (BH + bh) * 2 * kT64 + kT64);
+  {
+    unsigned char* const dst[4] = {sm.Q[0], sm.Q[1], sm.dO[0], sm.dO[1]};
+    const unsigned char* const src[4] = {ws + w.mmat + (size_t)bh * 2 * kT64, ws + w.mmat + (size_t)bh * 2 * kT64 + kT64,
+                                         ws + w.mmat + (BH + bh) * 2 * kT64, ws + w.mmat + (BH + bh) * 2 * kT64 + kT64};
+    copy_tiles64(dst, src, mx.quart ? 4 : 2);
   }
   publish();
   if (tid == 0) {
@@ -1311,17 +1349,11 @@ static __global__ void __launch_bounds__(256, 1) bwd_dkdv_kernel(MopQuartetParam
           *reinterpret_cast<float4*>(out + col + 4 * e4) = make_float4(acc[4 * e4], acc[4 * e4 + 1], acc[4 * e4 + 2], acc[4 * e4 + 3]);
       }
       // column sums of this warp's 32 key rows -> global (finish_kernel subtracts the mean over all T keys)
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float v = acc[e];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[e] = v;
-      }
-      if ((tid & 31) == 0) {
+      {
+        int cix;
+        const float cs = warp_colsum16(acc, tid & 31, &cix);   // 16-step butterfly: even lanes hold one column sum each
         float* sum = reinterpret_cast<float*>(ws + w.dksum) + ((size_t)map * BH + bh) * 64 + col;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) atomicAdd(sum + e, acc[e]);
+        if ((tid & 1) == 0) atomicAdd(sum + cix, cs);
       }
     }
   }

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("rep"); ap.add_argument("kernel")
 ap.add_argument("--so", default=os.path.join(os.path.dirname(__file__), "..", "mop_b200", "libmop_b200.so"))
 ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--name", default=None, help="regex for ncu's --kernel-name filter (default: the function name inside `kernel`)")
 a = ap.parse_args()
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(a.so)], cwd=tmp, capture_output=True)
@@ -38,7 +39,7 @@ for l in sass[start + 1:]:
 # a report may hold several kernels: keep the launches whose (demangled) name contains the function name of `kernel`
 fname = re.sub(r"^_ZN?\d*", "", a.kernel)
 fname = re.search(r"[A-Za-z_][A-Za-z0-9_]*kernel[A-Za-z0-9_]*", a.kernel)
-flt = ["--kernel-name", "regex:" + fname.group(0)] if fname else []
+flt = ["--kernel-name", "regex:" + (a.name or fname.group(0))] if (a.name or fname) else []
 out = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", *flt], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
