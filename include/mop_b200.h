@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MOP_ABI_VERSION 8
+#define MOP_ABI_VERSION 9
 
 enum { MOP_OK = 0, MOP_EINVAL = -1, MOP_EABI = -2, MOP_EUNSUPPORTED = -3, MOP_ECUDA = -4, MOP_EWORKSPACE = -5 };
 enum { MOP_F32 = 0, MOP_BF16 = 1 };
@@ -199,6 +199,9 @@ typedef struct MopQuartetParams {
   /* attention dropout (quartet_attn_patch.py:24,118-119; TransformerConfig.dropout defaults to 0.1): see MopSdpaParams */
   float dropout_p;
   uint64_t dropout_seed, dropout_offset;
+  /* ABI v9, backward only, optional: the workspace the forward call of the same inputs ran with (left untouched since).  The
+     tcgen05 backward then reads the forward's key preparation (centred keys, Gram tile images) from it instead of redoing it. */
+  const void* fwd_workspace; size_t fwd_workspace_bytes;
 } MopQuartetParams;
 
 size_t mop_quartet_workspace_bytes(const MopQuartetParams* p, int backward);

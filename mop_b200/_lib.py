@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOP_B200_LIB") or os.path.join(_HERE, "libmop_b200.so")   # override: experiment builds only
 
-MOP_ABI_VERSION = 8
+MOP_ABI_VERSION = 9
 MOP_F32, MOP_BF16 = 0, 1
 MOP_GATE_DENSE, MOP_GATE_LOWRANK, MOP_GATE_CONST = 0, 1, 2
 MOP_IMPL_AUTO, MOP_IMPL_SIMT, MOP_IMPL_TCGEN05 = 0, 1, 2
@@ -69,6 +69,7 @@ class QuartetParams(C.Structure):
         ("dscalar_part", vp),
         ("workspace", vp), ("workspace_bytes", sz),
         ("dropout_p", f32), ("dropout_seed", C.c_uint64), ("dropout_offset", C.c_uint64),
+        ("fwd_workspace", vp), ("fwd_workspace_bytes", sz),
     ]
 
 

@@ -55,7 +55,13 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   const size_t smem_q = sizeof(qtc::SmemQ) + 128 > one_per_sm ? sizeof(qtc::SmemQ) + 128 : one_per_sm;
   const size_t smem_k = sizeof(qtc::SmemK) + 128 > one_per_sm ? sizeof(qtc::SmemK) + 128 : one_per_sm;
   int rc;
-  if (BH * w.nm >= 2 * sm_count()) {   // enough (b, h, map) problems to fill the GPU: one CTA each, one launch
+  // the key preparation of the forward call, if the caller kept that workspace (same layout prefix): nothing to redo
+  const bool reuse = bwd && p->fwd_workspace != nullptr && p->fwd_workspace_bytes >= qtc::layout(p, 0).total &&
+                     (reinterpret_cast<uintptr_t>(p->fwd_workspace) & 255) == 0;
+  unsigned char* pws = reuse ? reinterpret_cast<unsigned char*>(const_cast<void*>(p->fwd_workspace)) : ws;
+  if (reuse) {
+    MOP_CHECK_CUDA(cudaMemsetAsync(ws + w.dksum, 0, (size_t)w.nm * BH * 64 * 4, st));   // otherwise zeroed by the prep kernels
+  } else if (BH * w.nm >= 2 * sm_count()) {   // enough (b, h, map) problems to fill the GPU: one CTA each, one launch
     qtc::prep_fused_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws);
   } else {   // key-side preparation split over groups of kPrepRows keys (quartet_tc.cuh)
     const int groups = (p->T + qtc::kPrepRows - 1) / qtc::kPrepRows;
@@ -70,7 +76,7 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
   CUtensorMap tmQ, tmQ2, tmKc, tmV;
   if ((rc = make_tile_map_sw(&tmQ, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
   if ((rc = make_tile_map_sw(&tmQ2, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-  if ((rc = make_tile_map_sw(&tmKc, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
+  if ((rc = make_tile_map_sw(&tmKc, pws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 64))) return rc;
   if ((rc = make_tile_map_sw(&tmV, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
   if (!bwd) {
     auto kf = hm ? (drop ? qtc::fwd_kernel<true, true> : qtc::fwd_kernel<true, false>) : (drop ? qtc::fwd_kernel<false, true> : qtc::fwd_kernel<false, false>);
@@ -86,9 +92,9 @@ static int quartet_run_tc(MopQuartetParams* p, cudaStream_t st, bool bwd) {
     if ((rc = make_tile_map_sw(&tmQs, p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
     if ((rc = make_tile_map_sw(&tmQ2s, p->use_quartet ? p->q2 : p->q, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
     if ((rc = make_tile_map_sw(&tmdOs, p->dy, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 64))) return rc;
-    if ((rc = make_tile_map_sw(&tmKcL, ws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
+    if ((rc = make_tile_map_sw(&tmKcL, pws + w.kc, w.nm * BH, p->T, 1, 64, (int64_t)p->T * 64, 64, 64, 128))) return rc;
     if ((rc = make_tile_map_sw(&tmVL, p->v, p->B, p->T, p->H, p->dk, sB, sT, p->dk, 128))) return rc;
-    kq<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, tmQ, tmQ2, tmdO, tmKc, tmV);
+    kq<<<BH * w.nqb, 256, smem_q, st>>>(*p, w, ws, pws, tmQ, tmQ2, tmdO, tmKc, tmV);
     const int nct = (p->T + 63) / 64, cpg = 4, groups = (nct + cpg - 1) / cpg;
     if (BH * w.nm >= 2 * sm_count() || groups == 1) {
       qtc::gmat_kernel<<<BH * w.nm, 256, 0, st>>>(*p, w, ws, 1, nct);

@@ -753,7 +753,7 @@ __device__ __forceinline__ ElemOut elem_bwd(const Mix& mx, float r1, float r2, f
 // buffer, so they run during tile t's element math; dQ += W K of tile t (two lanes) runs during tile t+1's element math (W has one
 // buffer per tile parity); one lane refills the three-stage key / value ring once dQ(t-1) is done.
 template <bool HAS_MASK, bool DROP = false>
-static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const __grid_constant__ CUtensorMap tmQ,
+static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams p, Ws w, unsigned char* ws, const unsigned char* pws, const __grid_constant__ CUtensorMap tmQ,
                                                         const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmdO,
                                                         const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -972,8 +972,9 @@ static __global__ void __launch_bounds__(256, 1) bwd_dq_kernel(MopQuartetParams 
   // G q by MMA: the Gram tiles (hi, lo per map) go to the dead key / value / W buffers; Z1 -> columns [0,64), Z2 -> [64,128)
   {
     unsigned char* const dst[4] = {sm.K1[0], sm.K2[0], sm.V[0], sm.W1[0]};
-    const unsigned char* const src[4] = {ws + w.gram + (size_t)bh * 2 * kT64, ws + w.gram + (size_t)bh * 2 * kT64 + kT64,
-                                         ws + w.gram + (BH + bh) * 2 * kT64, ws + w.gram + (BH + bh) * 2 * kT64 + kT64};
+    // (pws: the workspace that holds the key preparation - this call's, or the forward call's)
+    const unsigned char* const src[4] = {pws + w.gram + (size_t)bh * 2 * kT64, pws + w.gram + (size_t)bh * 2 * kT64 + kT64,
+                                         pws + w.gram + (BH + bh) * 2 * kT64, pws + w.gram + (BH + bh) * 2 * kT64 + kT64};
     copy_tiles64(dst, src, mx.quart ? 4 : 2);
   }
   publish();

@@ -470,6 +470,10 @@ class _Quartet(torch.autograd.Function):
         ctx.has_y32 = y32 is not None
         if y32 is not None:
             saved.append(y32)
+        # the tensor-core backward reads the forward's key preparation (centred keys, Gram tiles) from the forward workspace
+        ctx.has_ws = p.impl_used == _lib.MOP_IMPL_TCGEN05 and any(ctx.needs_input_grad)
+        if ctx.has_ws:
+            saved.append(ws)
         ctx.save_for_backward(*saved)
         return y
 
@@ -477,6 +481,7 @@ class _Quartet(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.load()
         saved = list(ctx.saved_tensors)
+        fws = saved.pop() if ctx.has_ws else None
         y32 = saved.pop() if ctx.has_y32 else None
         q, k, v, y, stats = saved[:5]
         rest = saved[5:]
@@ -502,6 +507,8 @@ class _Quartet(torch.autograd.Function):
             nbytes = lib.mop_quartet_workspace_bytes(C.byref(p), 1)
             ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+            if fws is not None:
+                p.fwd_workspace, p.fwd_workspace_bytes = _ptr(fws), fws.numel()
             with _Timed("quartet_bwd"):
                 _lib.check(lib.mop_quartet_bwd(C.byref(p), _stream()), "mop_quartet_bwd")
         last_impl["quartet_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
