@@ -311,6 +311,7 @@ struct __align__(128) SmemQ {
   uint64_t ld[2];    // TMA completion of key / value buffer 0 / 1
   uint64_t ldq;      // TMA completion of the query-side tiles
   uint32_t tmem_slot;
+  float dlt[128];    // dO . y of the tile's query rows
 };
 
 // grid: B*H*ceil(Nq/128), 256 threads; TMEM 256 columns (S | dP | dQ): two CTAs per SM
@@ -351,17 +352,36 @@ static __global__ void __launch_bounds__(256, 2) bwd_dq_kernel(MopSdpaParams p, 
   const float lse = p.lse[((int64_t)b * p.H + h) * Nq + (row_ok ? gi : Nq - 1)];
   const Dropout drop = make_dropout(p.dropout_p, p.dropout_seed, p.dropout_offset);
   const uint32_t rkey = dropout_row_key(drop, (uint32_t)bh, (uint32_t)gi);
-  float dlt = 0.f;
-  if (row_ok) {
-    for (int d0 = 0; d0 < dk; d0 += 8) {
-      float a[8], c[8];
-      unpack8(*reinterpret_cast<const uint4*>(yp + (size_t)gi * ystride + d0), a);
-      unpack8(*reinterpret_cast<const uint4*>(dyp + (size_t)gi * ystride + d0), c);
+  // delta = dO . y per query row: eight lanes share a row (16 B of y and of dO per lane; four rows per warp instruction, all
+  // 16 rows of a warp in flight) - one thread per 128-byte row costs 32 sectors per load and leaves eight dependent round trips
+  {
+    const int lane = tid & 31, wrp = tid >> 5, sub = lane >> 3, l8 = lane & 7;
+    uint4 ya[4], da[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dlt = fmaf(a[e], c[e], dlt);
+    for (int ps = 0; ps < 4; ++ps) {
+      const int r = q0 + 16 * wrp + 4 * ps + sub;
+      const bool ok = r < Nq && 8 * l8 < dk;
+      const size_t o = (size_t)(ok ? r : 0) * ystride + 8 * l8;
+      ya[ps] = ok ? __ldg(reinterpret_cast<const uint4*>(yp + o)) : make_uint4(0, 0, 0, 0);
+      da[ps] = ok ? __ldg(reinterpret_cast<const uint4*>(dyp + o)) : make_uint4(0, 0, 0, 0);
     }
-    if (wg == 0) delta[((int64_t)b * p.H + h) * Nq + gi] = dlt;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      float a[8], c[8];
+      unpack8(ya[ps], a);
+      unpack8(da[ps], c);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(a[e], c[e], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (l8 == 0) sm.dlt[16 * wrp + 4 * ps + sub] = d;
+    }
   }
+  __syncthreads();
+  const float dlt = row_ok ? sm.dlt[t] : 0.f;
+  if (row_ok && wg == 0) delta[((int64_t)b * p.H + h) * Nq + gi] = dlt;
   const uint32_t tb = sm.tmem_slot, tl = tb + ((uint32_t)(32 * warp4) << 16);
   const float2 coef2 = make_float2(p.scale * kLog2e, p.scale * kLog2e), nlse2 = make_float2(-lse * kLog2e, -lse * kLog2e), ndlt2 = make_float2(-dlt, -dlt);
   uint32_t phase = 0, phase2 = 0;
