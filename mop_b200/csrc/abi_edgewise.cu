@@ -5,6 +5,7 @@
 #include "edgewise_tc.cuh"
 #include "edgewise_tc_large.cuh"
 #include "edgewise_tc_large_bwd.cuh"
+#include "edgewise_tc_large_fwd2.cuh"
 
 namespace mop {
 // ---------------------------------------------------------------------------
@@ -113,12 +114,12 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
               "impl %d not available for this shape (tcgen05 path: bf16, dk%%8==0, dk<=64, V<=5, share_qkv, lowrank r<=4; "
               "N=64 forward+backward, N<=200 forward)", p->impl);
   if (large_ok && p->impl != MOP_IMPL_SIMT) {
-    const size_t smem = sizeof(ewl::Smem) + 128, smem_b = sizeof(ewl::SmemBwd) + 128;
+    const size_t smem = sizeof(ewl::Smem2) + 128, smem_b = sizeof(ewl::SmemBwd) + 128;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MOP_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MOP_CHECK_CUDA(cudaFuncSetAttribute(ewl::edgewise_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
       configured_dev = dev;
     }
@@ -126,7 +127,7 @@ static int edgewise_launch(MopEdgewiseParams* p, void* stream, bool bwd) {
     MOP_REQUIRE(p->workspace && p->workspace_bytes >= need, MOP_EWORKSPACE, "workspace too small: have %zu, need %zu", p->workspace_bytes, need);
     MOP_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, MOP_EINVAL, "workspace must be 16-byte aligned");
     if (bwd) ewl::edgewise_bwd_kernel<<<ewl::grid_size(p), 256, smem_b, st>>>(*p);
-    else ewl::edgewise_fwd_kernel<<<ewl::grid_size(p), 256, smem, st>>>(*p);
+    else ewl::edgewise_fwd2_kernel<<<ewl::grid_size(p), 512, smem, st>>>(*p);
     MOP_CHECK_CUDA(cudaGetLastError());
     p->impl_used = MOP_IMPL_TCGEN05;
     return MOP_OK;

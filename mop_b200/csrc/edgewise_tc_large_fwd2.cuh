@@ -1,114 +1,60 @@
-// Edgewise (Mixture-of-Products) attention forward on tcgen05 / TMEM for token counts up to 200
-// (ViT-B/16: N = 196, dk = 64, V = 5): bf16 operands, fp32 accumulation and fp32 statistics.
+// Edgewise (Mixture-of-Products) attention forward on tcgen05 / TMEM for token counts up to 200 (ViT-B/16: N = 196,
+// dk = 64, V = 5), 512 threads: TWO THREADS PER ROW.
 //
-// One persistent CTA of 256 threads (two warpgroups) per SM owns one (batch, head) problem at a time:
-//   * every N x N map is cut into two M=128 row blocks; warpgroup w owns row block w and reads its fp32
-//     accumulator (TMEM columns [256w, 256w + 208)) with the 32x32b shape, i.e. ONE THREAD PER ROW: row
-//     softmax statistics are thread local, column statistics are a 16-step shuffle butterfly + shared atomics;
-//   * bf16 MMA operands live in shared memory in the chunk-major layout of tc_common.cuh:
-//       A  (86.5 KB)  the current per-view softmax A_k  (B operand of the chain products, K = its rows)
-//       X  (83.2 KB)  the running chain product (A operand; row block w is rewritten in place by warpgroup w)
-//       Q  (25.6 KB)  unscaled queries (A operand),  K (26.6 KB)  keys scaled by q_scale*k_scale/sqrt(dk) per view
-//     which is all of the 227 KB;
-//   * pass R (views V-1..0):  S_k = Q Ks_k^T -> softmax -> A_k ;  Y <- Y A_k        -> R = A_{V-1}..A_0
-//     pass F (views 1..V-1):  A_k comes back by bulk copy      ;  X <- X A_k        -> F = A_0..A_{V-1} (stays in X)
-//     Between the passes the bf16 A_k wait in a per-CTA scratch slot of the caller's workspace (V x 86.5 KB per
-//     CTA, 64 MB for 148 CTAs: L2 resident; moved by cp.async.bulk in both directions).  Only the row / column
-//     means of S_k, log(F+eps), log(R+eps) leave the passes (gate features);
-//   * final stage, flash style over 32-column panels: the V score panels are recomputed into TMEM, mixed with
-//     the rank-r gates in registers (AND sum, OR log-sum-exp, NOT, chain log F from X), online softmax,
-//     P V_1 accumulated in TMEM; y = (P V_1)/l + F (w V_V).
+// Same algorithm, buffers and passes as the first version described at the top of edgewise_tc_large.cuh (pass R, pass F, flash-style
+// final stage); what changes is who does the element work.  Every fp32 accumulator row (TMEM lane) is shared by the two
+// threads tid and tid ^ 256 - warps w and w + 8 see the same 32 TMEM lanes - and each takes half of the row's columns
+// (chunks of 16 in the passes, 16 of the 32 panel columns in the final stage).  Row statistics (max, sums, log sums) are
+// combined through a 2 KB exchange buffer (all the shared memory that is left) and 64-thread named barriers.  With one thread per row the SM
+// ran 7 busy warps (2 per scheduler) and every TMEM load, MUFU result and shared-memory round trip was exposed; 14 busy warps
+// hide most of it.
 //
 // Math: SURVEY.md appendix A (reference attention_variants.py:500-562, :319-331); executable specification
-// oracle/edgewise_manual.py.  The token-count-64 specialisation is edgewise_tc.cuh.
+// oracle/edgewise_manual.py.
 #pragma once
-#include "edgewise_tc.cuh"
+#include "edgewise_tc_large.cuh"
+
+#ifdef MOP_PHASE_TIMING
+#define MOP_TSF(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0 && ts_n < 40) { ts_v[ts_n] = clock64(); ts_name[ts_n++] = #name; } } while (0)
+#else
+#define MOP_TSF(name) do { } while (0)
+#endif
 
 namespace mop {
 namespace ewl {
 
-using namespace tc;
-using ewtc::fast_exp2;
-using ewtc::fast_log2;
-using ewtc::fast_rcp;
-using ewtc::kLn2;
-using ewtc::kLog2e;
-using ewtc::kMaxQ;
-using ewtc::kMaxV;
-using ewtc::scale_chunk;
-
-constexpr int kNmax = 208;                    // 13 MMA k-steps (padded token count)
-constexpr int kMaxTokens = 200;               // rows held by the X / Q tiles
-constexpr int kRA = 208;                      // rows of the A / K / V tiles (K-dimension operands: every row finite)
-constexpr int kRX = 200;                      // rows of the X / Q tiles (M-dimension operands: over-read is harmless)
-constexpr int kMapChunks = kNmax / 8;         // 26 column chunks of 8
-constexpr int kBufX = kRX * 16 * kMapChunks;  // 83200
-constexpr int kBufA = kRA * 16 * kMapChunks;  // 86528
-constexpr int kQt = kRX * 16 * 8;             // 25600
-constexpr int kKt = kRA * 16 * 8;             // 26624
-constexpr int kPanel = 32;                    // final-stage panel width (columns)
-constexpr int kKsP = kPanel * 16 * 8;         // one scaled key panel: 4096
-
-struct __align__(128) Smem {
+struct __align__(128) Smem2 {
   unsigned char X[kBufX];
   unsigned char A[kBufA];
   unsigned char Q[kQt];
   unsigned char K[kKt];
-  float colsum[kMaxV + 2][kNmax];  // column sums of S_k (k < V), log F (V), log R (V+1)
-  float cvec[kMaxV][64];           // q_scale*k_scale/sqrt(dk) per view
-  float vs1[64], vsL[64];          // v_scale[0], sigmoid(chain_value_logit) * v_scale[V-1]
-  uint64_t bar[2];                 // MMA completion, one per warpgroup
+  float colsum[2][kNmax];          // column sums of log(F + eps) (0) and log(R + eps) (1)
+  float cvec[kMaxV][64];
+  float vs1[64], vsL[64];
+  float qsum[64], ksraw[64];       // column sums of the query / raw key rows (row and column means of S_k are rank-1: see row_col_means)
+  float xch[512];                  // row-statistic exchange between the two threads of a row
+  uint64_t bar[2];
   uint32_t tmem_slot;
 };
-// final-stage aliases inside A (dead once the chain passes are done)
-constexpr int kOffBfac = 0;                              // float [208][16]: column gate factors
-constexpr int kOffVt = kNmax * 16 * 4;                   // 13312: value tile (V_1, later w V_V)
-constexpr int kOffKsP = kOffVt + kKt;                    // 39936: [2 warpgroups][kMaxV][kKsP]
-static_assert(kOffKsP + 2 * kMaxV * kKsP <= kBufA, "final-stage aliases overflow the A buffer");
-// P panels ([2][128 rows x 32 cols] bf16) alias the K tile
-constexpr int kPt = 128 * 16 * (kPanel / 8);             // 8192
-static_assert(2 * kPt <= kKt, "P panels overflow the K tile");
+static_assert(sizeof(Smem2) + 128 <= 232448, "forward shared memory over the 227 KB limit");
 
-// sigmoid from ex2 + rcp (relative error ~1e-7).  tanh.approx (2^-11) is not enough here: the column-factor gradients of the
-// gate head are residuals of row sums of D g(1-g) that cancel to ~1 % of their terms, and forward and backward must use the
-// same gate values for the rows of D to sum to zero.
-__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.f + fast_exp2(-kLog2e * x)); }
-
-__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
-
-__device__ __forceinline__ void unpack8(uint4 u, float* f) {
-  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 u;
-  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
-  return u;
-}
-// 16 fp32 -> 2 x (8 bf16), optionally scaled
-// (callers zero v[] for padded rows themselves: 0 * NaN would not be zero)
-__device__ __forceinline__ void pack16(const float* v, float sc, uint4& lo, uint4& hi) {
-  lo.x = pack_bf16(v[0] * sc, v[1] * sc); lo.y = pack_bf16(v[2] * sc, v[3] * sc);
-  lo.z = pack_bf16(v[4] * sc, v[5] * sc); lo.w = pack_bf16(v[6] * sc, v[7] * sc);
-  hi.x = pack_bf16(v[8] * sc, v[9] * sc); hi.y = pack_bf16(v[10] * sc, v[11] * sc);
-  hi.z = pack_bf16(v[12] * sc, v[13] * sc); hi.w = pack_bf16(v[14] * sc, v[15] * sc);
-}
-
-
-static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewiseParams p) {
+static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewiseParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;
+  Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
+  const int tid = threadIdx.x, half = tid >> 8, wg = (tid >> 7) & 1, t = tid & 127, warp4 = (tid >> 5) & 3, lane = tid & 31;
   const int N = p.N, V = p.V, r = p.gate_rank, C = 2 * V + 2, dk = p.dk, H = p.H;
-  const int KS = (N + 15) >> 4, NN = KS * 16;   // MMA k-steps over tokens; padded token count
-  const int cfull = N >> 4;                     // column chunks of 16 without padding
+  const int KS = (N + 15) >> 4, NN = KS * 16;
+  const int cfull = N >> 4;
   const int dks = (dk + 15) >> 4;
   const int row = 128 * wg + t;
   const bool row_ok = row < N;
-  const bool blk_on = 128 * wg < N;                   // this warpgroup owns rows
-  const bool warp_on = 128 * wg + 32 * warp4 < N;     // this warp owns at least one valid row
+  const bool blk_on = 128 * wg < N;
+  const bool warp_on = 128 * wg + 32 * warp4 < N;
+  const bool issuer = t == 0 && half == 0;              // the thread of this row block that issues its MMAs
+  const int KH = (KS + 1) >> 1;
+  const int cb = half ? KH : 0, ce = half ? KS : KH;    // this thread's 16-column chunks of a row
   const float invN = 1.f / (float)N;
-  const uint32_t map_bytes = (uint32_t)(2 * KS) * (kRA * 16);   // the chunks of A that hold data
+  const uint32_t map_bytes = (uint32_t)(2 * KS) * (kRA * 16);
   unsigned char* spill = reinterpret_cast<unsigned char*>(p.workspace) + (size_t)blockIdx.x * kMaxV * kBufA;
 
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
@@ -117,8 +63,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = sm.tmem_slot;
-  const uint32_t tD = tbase + 256u * (uint32_t)wg;                      // accumulator of this warpgroup (MMA address)
-  const uint32_t tl = tD + ((uint32_t)(32 * warp4) << 16);              // the same, this warp's lane window
+  const uint32_t tD = tbase + 256u * (uint32_t)wg;
+  const uint32_t tl = tD + ((uint32_t)(32 * warp4) << 16);
   uint32_t phase = 0;
   const float w = 1.f / (1.f + __expf(-p.chain_value_logit[0]));
   const float bn = p.beta_not / (float)max(1, V - 1);
@@ -127,18 +73,27 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
 
   auto mma_wait = [&]() { mbar_wait(&sm.bar[wg], phase); phase ^= 1; tc_fence_after(); };
   auto publish_cta = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
-  auto publish_wg = [&]() { fence_async_smem(); tc_fence_before(); wg_sync(wg); tc_fence_after(); };
-  // D = X[row block] A  (A: the map in the A buffer, K index = its rows)
+  // the 256 threads of one row block
+  auto publish_wg = [&]() { fence_async_smem(); tc_fence_before(); asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); tc_fence_after(); };
+  // the two warps that share 32 rows: the other thread's value of a row statistic (second barrier: the slot may be rewritten)
+  const int pair_bar = 3 + ((tid >> 5) & 7);
+  auto exchange = [&](float v) {
+    sm.xch[tid] = v;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float o = sm.xch[tid ^ 256];
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    return o;
+  };
   auto chain_mma = [&]() {
     const uint32_t id = idesc_bf16(128, NN, 0, 1);
     for (int ks = 0; ks < KS; ++ks)
       mma_ss(tD, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_mnmajor(sA, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
     mma_commit(&sm.bar[wg]);
   };
-  // accumulator -> bf16 row of X (STORE) and / or row + column sums of log(D + eps) (LOGS)
+  // accumulator -> bf16 row of X (STORE) and / or row + column sums of log(D + eps) (LOGS): this thread's chunks
   auto chain_epilogue = [&](bool store, bool logs, int slot, float& rowmean) {
     float ls = 0.f;
-    for (int c = 0; c < KS; ++c) {
+    for (int c = cb; c < ce; ++c) {
       float v[16];
       tmem_ld_32x32b_x16(tl + 16 * c, v);
       tmem_ld_wait();
@@ -160,19 +115,42 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
         if ((lane & 1) == 0) atomicAdd(&sm.colsum[slot][16 * c + col], cs);
       }
     }
-    if (logs) rowmean = ls * invN;
+    if (logs) rowmean = (ls + exchange(ls)) * invN;
   };
 
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
   const size_t hd = (size_t)H * dk;
   const int G = p.B * H;
+#ifdef MOP_PHASE_TIMING
+  long long ts_v[40];
+  const char* ts_name[40];
+  int ts_n = 0;
+#endif
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
     auto in_row = [&](int n) { return qkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };   // q; +hd: k; +2hd: v
+    MOP_TSF(F0);
+    // a [rows x 64] operand tile from the token rows of q (which = 0), k (1) or v (2), optionally scaled per feature:
+    // item = (row, 8-feature chunk), consecutive threads take the chunks of one row (128 contiguous bytes)
+    // (R <= 208: at most four items per thread, all loads issued before the first use)
+    auto load_tile = [&](unsigned char* dst, int R, int which, const float* scale) {
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int item = tid + 512 * i, n = item >> 3, ch = item & 7;
+        v[i] = make_uint4(0, 0, 0, 0);
+        if (n < N && ch * 8 < dk) v[i] = __ldg(reinterpret_cast<const uint4*>(in_row(n) + (size_t)which * hd + ch * 8));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int item = tid + 512 * i, n = item >> 3, ch = item & 7;
+        if (item < R * 8) *reinterpret_cast<uint4*>(dst + ch * (R * 16) + n * 16) = scale ? scale_chunk(v[i], scale + ch * 8) : v[i];
+      }
+    };
     // =================================================================================================
-    // stage 0: per-view scale vectors, unscaled Q tile, this thread's key row (registers), zeroed column sums
+    // stage 0: per-view scale vectors, unscaled Q tile, zeroed column sums
     // =================================================================================================
-    for (int idx = tid; idx < V * 64; idx += 256) {
+    for (int idx = tid; idx < V * 64; idx += 512) {
       const int i = idx >> 6, d = idx & 63;
       float c = 0.f;
       if (d < dk) c = sscale * p.q_scale[((size_t)i * H + ph) * dk + d] * p.k_scale[((size_t)i * H + ph) * dk + d];
@@ -185,38 +163,59 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
       sm.vs1[d] = a;
       sm.vsL[d] = w * b;
     }
-    for (int idx = tid; idx < (kMaxV + 2) * kNmax; idx += 256) (&sm.colsum[0][0])[idx] = 0.f;
-    uint4 kraw[8];
+    for (int idx = tid; idx < 2 * kNmax; idx += 512) (&sm.colsum[0][0])[idx] = 0.f;
+    if (tid < 128) (tid < 64 ? sm.qsum : sm.ksraw)[tid & 63] = 0.f;
+    load_tile(sm.Q, kRX, 0, nullptr);
+    __syncthreads();
+    // column sums of the query and of the raw key rows: thread = (8-feature chunk, row group), the four lanes of a warp that
+    // share a chunk are combined by shuffles, then shared atomics
+    {
+      const int ch = tid & 7;
+      float aq[8], ak[8];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      uint4 q = make_uint4(0, 0, 0, 0);
-      kraw[ch] = q;
-      if (tid < N && ch * 8 < dk) {
-        q = *reinterpret_cast<const uint4*>(in_row(tid) + ch * 8);
-        kraw[ch] = *reinterpret_cast<const uint4*>(in_row(tid) + hd + ch * 8);
+      for (int e = 0; e < 8; ++e) { aq[e] = 0.f; ak[e] = 0.f; }
+      for (int n = tid >> 3; n < N; n += 64) {
+        if (ch * 8 < dk) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(in_row(n) + ch * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) aq[e] += f[e];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(in_row(n) + hd + ch * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ak[e] += f[e];
+        }
       }
-      if (tid < kRX) *reinterpret_cast<uint4*>(sm.Q + ch * (kRX * 16) + tid * 16) = q;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], 8);
+        aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], 16);
+        ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 8);
+        ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(&sm.qsum[8 * ch + e], aq[e]); atomicAdd(&sm.ksraw[8 * ch + e], ak[e]); }
+      }
     }
     __syncthreads();
-    float rho[kMaxV], rhoF = 0.f, rhoR = 0.f;   // row means of S_k, log F, log R of this thread's row
+    // row means rho_k[i] and column means kap_k[j] of S_k for this thread's token (as row i and as column j), both threads of a row
+    float rho[kMaxV], kap[kMaxV], rhoF = 0.f, rhoR = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i) rho[i] = 0.f;
+    for (int i = 0; i < kMaxV; ++i) { rho[i] = 0.f; kap[i] = 0.f; }
     // =================================================================================================
     // pass R (views V-1 .. 0): A_k = softmax(S_k) (spilled to the L2-resident scratch), Y <- Y A_k
     // =================================================================================================
     for (int idx = 0; idx < V; ++idx) {
       const int k = V - 1 - idx;
       const bool first = idx == 0, last = idx == V - 1;
-      // scaled keys of view k (every MMA issued so far has completed: each thread waited for its warpgroup's
-      // MMAs before the last CTA barrier)
-      if (tid < kRA) {
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(sm.K + ch * (kRA * 16) + tid * 16) = scale_chunk(kraw[ch], &sm.cvec[k][ch * 8]);
-      }
+      // scaled keys of view k (every MMA issued so far has completed: each thread waited for its row block's MMAs before
+      // the last CTA barrier)
+      if (idx == 1) MOP_TSF(v_begin);
+      load_tile(sm.K, kRA, 1, sm.cvec[k]);
       publish_cta();
+      if (idx == 1) MOP_TSF(v_ktile);
       if (blk_on) {
-        if (t == 0) {
+        if (issuer) {
           const uint32_t id = idesc_bf16(128, NN, 0, 0);
           for (int ks = 0; ks < dks; ++ks)
             mma_ss(tD, desc_kmajor(sQ + 128 * wg * 16, kRX, 16 * ks), desc_kmajor(sK, kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
@@ -224,36 +223,52 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
         }
         mma_wait();
       }
-      // ---- row softmax of S_k, thread per row; row / column sums of S_k for the gate features
+      if (idx == 1) MOP_TSF(v_smma);
+      // ---- row softmax of S_k, two threads per row; row / column sums of S_k for the gate features
       if (warp_on) {
-        float mx = -INFINITY, rs = 0.f;
-        for (int c = 0; c < KS; ++c) {
+        float mx = -INFINITY;
+        for (int c = cb; c < ce; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
           if (c < cfull) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { mx = fmaxf(mx, v[e]); rs += v[e]; }
+            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, v[e]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (16 * c + e < N) { mx = fmaxf(mx, v[e]); rs += v[e]; } else v[e] = 0.f;
+            for (int e = 0; e < 16; ++e)
+              if (16 * c + e < N) mx = fmaxf(mx, v[e]);
+          }
+        }
+        mx = fmaxf(mx, exchange(mx));
+        // S_k = Q Ks_k^T is a product, so its row and column sums are rank-1: row i sums to q_i . (sum_j ks_j), column j to
+        // (sum_i q_i) . ks_j - two 64-term dot products instead of sums over the map.  First thread of the row: the row mean,
+        // with sum_j ks_j = c_k (.) (sum of the raw keys); second thread: the column mean from the scaled key row in the K tile.
+        {
+          float part = 0.f;
+          const unsigned char* src = half ? sm.K : sm.Q;
+          const int R = half ? kRA : kRX;
+          if (row < R) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              float f[8];
+              unpack8(*reinterpret_cast<const uint4*>(src + ch * (R * 16) + row * 16), f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float wv = half ? sm.qsum[8 * ch + e] : sm.cvec[k][8 * ch + e] * sm.ksraw[8 * ch + e];
+                part = fmaf(f[e], wv, part);
+              }
             }
           }
-          if (!row_ok) {
+          part = row_ok ? part * invN : 0.f;
+          const float other = exchange(part);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0.f;
-          }
-          int col;
-          const float cs = warp_colsum16(v, lane, &col);
-          if ((lane & 1) == 0) atomicAdd(&sm.colsum[k][16 * c + col], cs);
+          for (int i = 0; i < kMaxV; ++i)
+            if (i == k) { rho[i] = half ? other : part; kap[i] = half ? part : other; }
         }
-#pragma unroll
-        for (int i = 0; i < kMaxV; ++i)
-          if (i == k) rho[i] = rs * invN;
         float l = 0.f;
         const float mb = mx * kLog2e;
-        for (int c = 0; c < KS; ++c) {
+        for (int c = cb; c < ce; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
@@ -267,8 +282,9 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
           tmem_st_32x32b_x16(tl + 16 * c, v);
         }
         tmem_st_wait();
+        l += exchange(l);
         const float inv_l = 1.f / l;
-        for (int c = 0; c < KS; ++c) {
+        for (int c = cb; c < ce; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
@@ -290,18 +306,21 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
         }
       } else if (row < kRA) {
         // rows of A_k that no active warp writes: they are K-dimension rows of the chain MMAs, keep them zero
-        for (int c = 0; c < 2 * KS; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
+        for (int c = 2 * cb; c < 2 * ce; ++c) *reinterpret_cast<uint4*>(sm.A + c * (kRA * 16) + row * 16) = make_uint4(0, 0, 0, 0);
       }
       publish_cta();
+      if (idx == 1) MOP_TSF(v_softmax);
       if (first) continue;
       if (blk_on) {
-        if (t == 0) chain_mma();
+        if (issuer) chain_mma();
         mma_wait();
       }
-      if (warp_on) chain_epilogue(!last, last, V + 1, rhoR);   // R itself is never needed again
+      if (idx == 1) MOP_TSF(v_cmma);
+      if (warp_on) chain_epilogue(!last, last, 1, rhoR);   // R itself is never needed again
+      if (idx == 1) MOP_TSF(v_cepi);
       if (last && row < kRX) {
-        // X <- A_0: start of the forward chain (this warpgroup's MMA, the only reader of these X rows, is complete)
-        for (int c = 0; c < 2 * KS; ++c)
+        // X <- A_0: start of the forward chain (this row block's MMA, the only reader of these X rows, is complete)
+        for (int c = 2 * cb; c < 2 * ce; ++c)
           *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) =
               row < kRA ? *reinterpret_cast<const uint4*>(sm.A + c * (kRA * 16) + row * 16) : make_uint4(0, 0, 0, 0);
       }
@@ -309,8 +328,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
     // =================================================================================================
     // pass F (views 1 .. V-1): A_k comes back from the scratch, X <- X A_k; F stays in X
     // =================================================================================================
+    MOP_TSF(F1);
     publish_cta();   // X = A_0 visible to the MMAs; nobody reads the A buffer any more
-    // (a single cp.async.bulk of the 86 KB image was measured at ~4 B/cycle; 256 threads x cp.async 16 B are ~10x faster)
     cp_async_block(sm.A, spill + (size_t)1 * kBufA, map_bytes);
     cp_async_commit();
     for (int k = 1; k < V; ++k) {
@@ -318,101 +337,98 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
       cp_async_wait<0>();
       publish_cta();   // A_k landed (and, for k > 1, the rewritten X rows are visible)
       if (blk_on) {
-        if (t == 0) chain_mma();
+        if (issuer) chain_mma();
         mma_wait();
       }
       if (!last) {
         tc_fence_before();
-        __syncthreads();   // both warpgroups' MMAs have read A_k: the next map may land while X is rewritten
+        __syncthreads();   // both row blocks' MMAs have read A_k: the next map may land while X is rewritten
         cp_async_block(sm.A, spill + (size_t)(k + 1) * kBufA, map_bytes);
         cp_async_commit();
       }
-      if (warp_on) chain_epilogue(true, last, V, rhoF);
+      if (warp_on) chain_epilogue(true, last, 0, rhoF);
     }
     // =================================================================================================
     // final stage
     // =================================================================================================
-    publish_cta();   // F complete in X; chain MMAs of both warpgroups are done: A and K buffers are free, colsum is final
+    MOP_TSF(F2);
+    publish_cta();   // F complete in X; chain MMAs of both row blocks are done: A and K buffers are free, colsum is final
     float* bfac = reinterpret_cast<float*>(sm.A + kOffBfac);
     unsigned char* Vt = sm.A + kOffVt;
     unsigned char* KsP = sm.A + kOffKsP + wg * (kMaxV * kKsP);
     unsigned char* Pt = sm.K + wg * kPt;
-    auto load_values = [&](const float* vscale) {
-      if (tid < kRA) {
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 vv = make_uint4(0, 0, 0, 0);
-          if (tid < N && ch * 8 < dk) vv = scale_chunk(*reinterpret_cast<const uint4*>(in_row(tid) + 2 * hd + ch * 8), &vscale[ch * 8]);
-          *reinterpret_cast<uint4*>(Vt + ch * (kRA * 16) + tid * 16) = vv;
-        }
-      }
-    };
-    load_values(sm.vs1);
-    // gate factors: a (row factors of this thread's row, registers) and b (column factors of column `row`, shared)
+    load_tile(Vt, kRA, 2, sm.vs1);
+    // gate factors: a (row factors of this thread's row, registers, both threads of the row) and b (column factors of column
+    // `row`, shared: slots 0..7 from the first thread of the row, 8..15 from the second)
     float afac[kMaxQ];
     {
-      float fr[2 * kMaxV + 2], fc[2 * kMaxV + 2];
+      // the C = 2V + 2 features of this token in the order of the projection weights: as a row (S_c row means, S_c^T row
+      // means = column means of S_c, log F, log R row means) and as a column (roles swapped)
+      constexpr int kMaxC = 2 * kMaxV + 2;
+      float fr[kMaxC], fc[kMaxC];
+      const float kapF = row < kNmax ? sm.colsum[0][row] * invN : 0.f, kapR = row < kNmax ? sm.colsum[1][row] * invN : 0.f;
 #pragma unroll
-      for (int c = 0; c < kMaxV; ++c) {
-        const float kap = (c < V && row < kNmax) ? sm.colsum[c][row] * invN : 0.f;
-        fr[c] = rho[c]; fr[kMaxV + c] = kap;     // row projection sees S_c (row mean) and S_c^T (row mean = column mean of S_c)
-        fc[c] = kap;    fc[kMaxV + c] = rho[c];  // column projection: roles swapped
+      for (int c = 0; c < kMaxC; ++c) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i) {
+          if (c == i && i < V) { a = rho[i]; b = kap[i]; }
+          if (c == V + i && i < V) { a = kap[i]; b = rho[i]; }
+        }
+        if (c == 2 * V) { a = rhoF; b = kapF; }
+        if (c == 2 * V + 1) { a = rhoR; b = kapR; }
+        fr[c] = a; fc[c] = b;
       }
-      const float kapF = row < kNmax ? sm.colsum[V][row] * invN : 0.f, kapR = row < kNmax ? sm.colsum[V + 1][row] * invN : 0.f;
-      fr[2 * kMaxV] = rhoF; fr[2 * kMaxV + 1] = rhoR;
-      fc[2 * kMaxV] = kapF; fc[2 * kMaxV + 1] = kapR;
 #pragma unroll
       for (int qq = 0; qq < kMaxQ; ++qq) {
         const int tg = qq >> 2, kk = qq & 3, q = tg * r + kk;
         float a = 0.f, b = 0.f;
+        const bool mine = (qq >> 3) == half;   // this thread writes b of slot qq
         if (kk < r && row_ok) {
+          // C is even: the weight rows are read as float2 (warp-uniform addresses; 12 scalar loads per row made this phase
+          // load-issue bound)
+          const float2* wr = reinterpret_cast<const float2*>(p.row_w + q * C);
+          const float2* wc = reinterpret_cast<const float2*>(p.col_w + q * C);
           a = __ldg(p.row_b + q);
-          b = __ldg(p.col_b + q);
+          if (mine) b = __ldg(p.col_b + q);
 #pragma unroll
-          for (int c = 0; c < kMaxV; ++c)
-            if (c < V) {
-              a = fmaf(__ldg(p.row_w + q * C + c), fr[c], a);
-              a = fmaf(__ldg(p.row_w + q * C + V + c), fr[kMaxV + c], a);
-              b = fmaf(__ldg(p.col_w + q * C + c), fc[c], b);
-              b = fmaf(__ldg(p.col_w + q * C + V + c), fc[kMaxV + c], b);
+          for (int c2 = 0; c2 < kMaxC / 2; ++c2)
+            if (2 * c2 < C) {
+              const float2 w2 = __ldg(wr + c2);
+              a = fmaf(w2.x, fr[2 * c2], fmaf(w2.y, fr[2 * c2 + 1], a));
+              if (mine) {
+                const float2 v2 = __ldg(wc + c2);
+                b = fmaf(v2.x, fc[2 * c2], fmaf(v2.y, fc[2 * c2 + 1], b));
+              }
             }
-          a = fmaf(__ldg(p.row_w + q * C + 2 * V), fr[2 * kMaxV], a);
-          a = fmaf(__ldg(p.row_w + q * C + 2 * V + 1), fr[2 * kMaxV + 1], a);
-          b = fmaf(__ldg(p.col_w + q * C + 2 * V), fc[2 * kMaxV], b);
-          b = fmaf(__ldg(p.col_w + q * C + 2 * V + 1), fc[2 * kMaxV + 1], b);
         }
         afac[qq] = a;
-        if (row < kNmax) bfac[row * 16 + qq] = b;
+        if (mine && row < kNmax) bfac[row * 16 + qq] = b;
       }
     }
     publish_cta();
-    float m_run = -INFINITY, l_run = 0.f;
+    MOP_TSF(F3);
+    float m_run = -INFINITY, l_run = 0.f;             // l_run: this thread's columns only (combined at the end)
     const uint32_t tS = tD, tO = tD + 160;            // MMA addresses: score panels (V x 32 columns), P V_1 accumulator
     const uint32_t tlS = tl, tlO = tl + 160;          // this warp's lane window
     if (blk_on) {
       const int npanels = (N + kPanel - 1) / kPanel;
-      // raw key chunks of the next panel, prefetched while the current one is processed
-      uint4 raw[2];
+      // raw key chunk of the next panel (one (key, 8-feature chunk) item per thread of the row block), prefetched
+      const int pitem = t + 128 * half, pjj = pitem & 31, pch = pitem >> 5;
+      uint4 raw;
       auto fetch_panel = [&](int j0) {
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int item = t + 128 * it, jj = item & 31, ch = item >> 5, j = j0 + jj;
-          raw[it] = make_uint4(0, 0, 0, 0);
-          if (j < N && ch * 8 < dk) raw[it] = *reinterpret_cast<const uint4*>(in_row(j) + hd + ch * 8);
-        }
+        const int j = j0 + pjj;
+        raw = make_uint4(0, 0, 0, 0);
+        if (j < N && pch * 8 < dk) raw = __ldg(reinterpret_cast<const uint4*>(in_row(j) + hd + pch * 8));
       };
       fetch_panel(0);
       for (int pn = 0; pn < npanels; ++pn) {
         const int j0 = pn * kPanel;
         // scaled key panels of the V views (the score MMAs of the previous panel have completed)
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int item = t + 128 * it, jj = item & 31, ch = item >> 5;
-          for (int k = 0; k < V; ++k)
-            *reinterpret_cast<uint4*>(KsP + k * kKsP + ch * (kPanel * 16) + jj * 16) = scale_chunk(raw[it], &sm.cvec[k][ch * 8]);
-        }
+        for (int k = 0; k < V; ++k)
+          *reinterpret_cast<uint4*>(KsP + k * kKsP + pch * (kPanel * 16) + pjj * 16) = scale_chunk(raw, &sm.cvec[k][pch * 8]);
         publish_wg();
-        if (t == 0) {
+        if (issuer) {
           const uint32_t id = idesc_bf16(128, kPanel, 0, 0);
           for (int k = 0; k < V; ++k)
             for (int ks = 0; ks < dks; ++ks)
@@ -420,11 +436,14 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
           mma_commit(&sm.bar[wg]);
         }
         if (pn + 1 < npanels) fetch_panel(j0 + kPanel);
+        if (pn == 1) MOP_TSF(p_issue);
         mma_wait();   // also covers the P V_1 MMA of the previous panel
+        if (pn == 1) MOP_TSF(p_mma);
         if (warp_on) {
           float pmax = -INFINITY;
 #pragma unroll 1
-          for (int sub = 0; sub < kPanel / 8; ++sub) {
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int sub = 2 * half + s2;   // this thread's 8-column blocks of the panel
             float sv[kMaxV][8];
 #pragma unroll
             for (int i = 0; i < kMaxV; ++i)
@@ -465,6 +484,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
             tmem_st_32x32b_x8(tlS + 8 * sub, val);   // park the mixed scores in the (consumed) columns of S_0
           }
           tmem_st_wait();
+          if (pn == 1) MOP_TSF(p_mix);
+          pmax = fmaxf(pmax, exchange(pmax));
           // online softmax in base 2 with an INTEGER reference exponent per row: rescaling by exact powers of two
           // commutes with the bf16 rounding of P, and the row sum is taken over the ROUNDED probabilities, so that
           // y_base = (sum_j P_ij V_1j) / l_i is exactly the softmax-weighted mean the backward differentiates
@@ -480,7 +501,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
           if (__any_sync(0xffffffffu, need)) {
             const float scl = need ? sc : 1.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c2 = 0; c2 < 2; ++c2) {   // this thread's half of the 64 accumulator columns
+              const int c = 2 * half + c2;
               float o[16];
               tmem_ld_32x32b_x16(tlO + 16 * c, o);
               tmem_ld_wait();
@@ -492,27 +514,28 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
           }
           l_run *= sc;
           m_run = m_new;
-          float smix[kPanel];
-          tmem_ld_32x32b_x32(tlS, smix);
+          float smix[16];
+          tmem_ld_32x32b_x16(tlS + 16 * half, smix);
           tmem_ld_wait();
           float ps = 0.f;
 #pragma unroll
-          for (int c = 0; c < kPanel / 8; ++c) {
+          for (int c2 = 0; c2 < 2; ++c2) {
             uint32_t u[4];
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
-              u[e2] = pack_bf16(fast_exp2(fmaf(smix[8 * c + 2 * e2], kLog2e, -mb)), fast_exp2(fmaf(smix[8 * c + 2 * e2 + 1], kLog2e, -mb)));
+              u[e2] = pack_bf16(fast_exp2(fmaf(smix[8 * c2 + 2 * e2], kLog2e, -mb)), fast_exp2(fmaf(smix[8 * c2 + 2 * e2 + 1], kLog2e, -mb)));
               ps += __uint_as_float(u[e2] << 16) + __uint_as_float(u[e2] & 0xffff0000u);   // the rounded values (exp2(-inf) = 0)
             }
-            *reinterpret_cast<uint4*>(Pt + c * (128 * 16) + t * 16) = make_uint4(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint4*>(Pt + (2 * half + c2) * (128 * 16) + t * 16) = make_uint4(u[0], u[1], u[2], u[3]);
           }
           l_run += ps;
         } else {
 #pragma unroll
-          for (int c = 0; c < kPanel / 8; ++c) *reinterpret_cast<uint4*>(Pt + c * (128 * 16) + t * 16) = make_uint4(0, 0, 0, 0);
+          for (int c2 = 0; c2 < 2; ++c2) *reinterpret_cast<uint4*>(Pt + (2 * half + c2) * (128 * 16) + t * 16) = make_uint4(0, 0, 0, 0);
         }
+        if (pn == 1) MOP_TSF(p_soft);
         publish_wg();
-        if (t == 0) {
+        if (issuer) {
           const uint32_t id = idesc_bf16(128, 64, 0, 1);
           const int nks = min(kPanel, NN - j0) >> 4;
           for (int ks = 0; ks < nks; ++ks)
@@ -522,13 +545,15 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
       }
       mma_wait();
     }
+    MOP_TSF(F4);
+    if (warp_on) l_run += exchange(l_run);   // row sum of the rounded probabilities over both threads' columns
     // ---- y = (P V_1) / l + F (w V_V)
     tc_fence_before();
-    __syncthreads();          // both warpgroups are done with V_1
-    load_values(sm.vsL);
+    __syncthreads();          // both row blocks are done with V_1
+    load_tile(Vt, kRA, 2, sm.vsL);
     publish_cta();
     if (blk_on) {
-      if (t == 0) {
+      if (issuer) {
         const uint32_t id = idesc_bf16(128, 64, 0, 1);
         for (int ks = 0; ks < KS; ++ks)
           mma_ss(tS, desc_kmajor(sX + 128 * wg * 16, kRX, 16 * ks), desc_mnmajor(smem_u32(Vt), kRA, 16 * ks), id, ks > 0 ? 1u : 0u);
@@ -537,10 +562,11 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
       mma_wait();
       if (warp_on) {
         const float il = 1.f / l_run;
-        if (p.row_stats && row_ok) *reinterpret_cast<float2*>(p.row_stats + (((size_t)pb * H + ph) * N + row) * 2) = make_float2(m_run, l_run);
+        if (p.row_stats && row_ok && half == 0) *reinterpret_cast<float2*>(p.row_stats + (((size_t)pb * H + ph) * N + row) * 2) = make_float2(m_run, l_run);
         __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (((size_t)pb * N + row) * H + ph) * dk;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * half + c2;
           float oa[16], of[16];
           tmem_ld_32x32b_x16(tlO + 16 * c, oa);
           tmem_ld_32x32b_x16(tlS + 16 * c, of);
@@ -569,23 +595,15 @@ static __global__ void __launch_bounds__(256, 1) edgewise_fwd_kernel(MopEdgewise
     }
     tc_fence_before();
     __syncthreads();   // tiles, vectors and TMEM are reused by the next problem
+    MOP_TSF(F5);
+#ifdef MOP_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0 && g == 0)
+      for (int i = 0; i < ts_n; ++i) printf("tf %s %lld\n", ts_name[i], ts_v[i]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tmem_dealloc<512>(tbase);
-}
-
-inline bool supported(const MopEdgewiseParams* p) {
-  return p->dtype == MOP_BF16 && p->N >= 1 && p->N <= kMaxTokens && p->dk <= 64 && p->dk % 8 == 0 && p->V >= 2 && p->V <= kMaxV &&
-         p->Vp == 1 && p->gate_mode == MOP_GATE_LOWRANK && p->gate_rank >= 1 && p->gate_rank <= 4 && p->q_scale != nullptr && p->lens_n == 0;
-}
-
-// one persistent CTA per SM (sizing without a device: B200)
-inline int grid_size(const MopEdgewiseParams* p) {
-  int sms = sm_count();
-  if (sms <= 0) sms = 148;
-  const int G = p->B * p->H;
-  return G < sms ? G : sms;
 }
 
 }  // namespace ewl
