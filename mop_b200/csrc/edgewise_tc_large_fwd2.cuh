@@ -33,6 +33,7 @@ struct __align__(128) Smem2 {
   float vs1[64], vsL[64];
   float qsum[64], ksraw[64];       // column sums of the query / raw key rows (row and column means of S_k are rank-1: see row_col_means)
   float xch[512];                  // row-statistic exchange between the two threads of a row
+  float hw[2][kMaxQ * (2 * kMaxV + 2) + kMaxQ];   // gate-head weights + biases (row / column projection), staged once per CTA
   uint64_t bar[2];
   uint32_t tmem_slot;
 };
@@ -59,6 +60,14 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
 
   if (tid < 32) tmem_alloc<512>(&sm.tmem_slot);
   if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
+  {
+    // with 227 KB of shared memory the L1 is a few KB: weights read with __ldg per problem came from L2 every time
+    const int nW = 4 * r * C, nP = nW + 4 * r;
+    for (int idx = tid; idx < 2 * nP; idx += 512) {
+      const int hf = idx / nP, rem = idx % nP;
+      sm.hw[hf][rem] = rem < nW ? (hf ? p.col_w : p.row_w)[rem] : (hf ? p.col_b : p.row_b)[rem - nW];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -385,19 +394,18 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
         float a = 0.f, b = 0.f;
         const bool mine = (qq >> 3) == half;   // this thread writes b of slot qq
         if (kk < r && row_ok) {
-          // C is even: the weight rows are read as float2 (warp-uniform addresses; 12 scalar loads per row made this phase
-          // load-issue bound)
-          const float2* wr = reinterpret_cast<const float2*>(p.row_w + q * C);
-          const float2* wc = reinterpret_cast<const float2*>(p.col_w + q * C);
-          a = __ldg(p.row_b + q);
-          if (mine) b = __ldg(p.col_b + q);
+          // C is even: the weight rows (shared memory, warp-uniform addresses) are read as float2
+          const float2* wr = reinterpret_cast<const float2*>(sm.hw[0] + q * C);
+          const float2* wc = reinterpret_cast<const float2*>(sm.hw[1] + q * C);
+          a = sm.hw[0][4 * r * C + q];
+          if (mine) b = sm.hw[1][4 * r * C + q];
 #pragma unroll
           for (int c2 = 0; c2 < kMaxC / 2; ++c2)
             if (2 * c2 < C) {
-              const float2 w2 = __ldg(wr + c2);
+              const float2 w2 = wr[c2];
               a = fmaf(w2.x, fr[2 * c2], fmaf(w2.y, fr[2 * c2 + 1], a));
               if (mine) {
-                const float2 v2 = __ldg(wc + c2);
+                const float2 v2 = wc[c2];
                 b = fmaf(v2.x, fc[2 * c2], fmaf(v2.y, fc[2 * c2 + 1], b));
               }
             }
