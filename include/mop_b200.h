@@ -258,6 +258,43 @@ int mop_mop2d_partial_rows(void);
 int mop_mop2d_fwd(const float* mel, const float* He, float* R, float* gate, int B, int T, int F, int ks, void* cuda_stream);
 int mop_mop2d_bwd(const float* R, const float* dgate, float* dHe_part, int nparts, int B, int T, int F, int ks, void* cuda_stream);
 
+/* ------------------------------------------------------------------------- */
+/* ViT-MoP token gate                                            */
+/* ------------------------------------------------------------------------- */
+/* mop/models/vit_mop.py:95-114 with components.py:255-303: ViewsLinear (D -> V per token) -> Kernels3 (conv3x3 V -> 16, SiLU,
+ * conv1x1 16 -> K) -> FuseExcInh (conv1x1 V+K -> hid, SiLU, conv1x1 hid -> 2 + bias, sigmoid) -> gate = 1 + a_pos G+ - a_neg G-
+ * -> out = tok * gate.  One fused kernel per direction; a_pos / a_neg = softplus(alpha) are applied by the caller (one-element
+ * device tensors).  Backward outputs are per-CTA partial rows, summed by the caller. */
+typedef struct MopTokenGateParams {
+  int32_t struct_bytes;
+  int32_t dtype;            /* MOP_F32 | MOP_BF16: tokens in / out */
+  int32_t B, T, D;          /* tokens [B, T, D], T = Gh * Gw <= 256, D % 8 == 0, D <= 2048 */
+  int32_t Gh, Gw;
+  int32_t V, K, hid;        /* views (<= 8), kernel maps (<= 8), FuseExcInh hidden width (<= 16) */
+  int32_t nparts;           /* CTAs of the backward = rows of dnet_part (mop_token_gate_partial_rows) */
+  const void* x;            /* [B, T, D] */
+  const float* views_w;     /* [V, D]            ViewsLinear.proj.weight */
+  const float* k3_w;        /* [16, V, 3, 3]     Kernels3.k[0].weight */
+  const float* k1_w;        /* [K, 16]           Kernels3.k[2].weight */
+  const float* f1_w;        /* [hid, V + K]      FuseExcInh.fuse[0].weight */
+  const float* f2_w;        /* [2, hid]          FuseExcInh.fuse[2].weight */
+  const float* f2_b;        /* [2]               FuseExcInh.fuse[2].bias */
+  const float* a_pos;       /* [1] softplus(alpha_pos) */
+  const float* a_neg;       /* [1] softplus(alpha_neg) */
+  void* out;                /* [B, T, D] */
+  float* views;             /* [B, T, V] fwd out, bwd in */
+  float* gate;              /* [B, T]    fwd out, bwd in */
+  const void* dout;         /* [B, T, D] */
+  void* dx;                 /* [B, T, D] */
+  float* dwv_part;          /* [nparts * mop_token_gate_wv_groups(D), V, D] */
+  float* dnet_part;         /* [nparts, n + 2]: k3_w | k1_w | f1_w | f2_w | f2_b (n = mop_token_gate_net_params) | d a_pos | d a_neg */
+} MopTokenGateParams;
+int mop_token_gate_partial_rows(int B);
+int mop_token_gate_wv_groups(int D);
+int mop_token_gate_net_params(const MopTokenGateParams* p);
+int mop_token_gate_fwd(MopTokenGateParams* p, void* cuda_stream);
+int mop_token_gate_bwd(MopTokenGateParams* p, void* cuda_stream);
+
 /* The dropout factor every attention kernel applies to P[b,h,i,j] for (p, seed, offset): out[bh, i, j] = 0 or 1 / (1 - p)
  * (fp32, [BH, Nq, Nk]).  Test infrastructure: lets the CPU oracle be evaluated under the kernels' own mask. */
 int mop_dropout_mask(float* out, int BH, int Nq, int Nk, float p, uint64_t seed, uint64_t offset, void* cuda_stream);

@@ -73,6 +73,15 @@ class QuartetParams(C.Structure):
     ]
 
 
+class TokenGateParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("dtype", i32), ("B", i32), ("T", i32), ("D", i32), ("Gh", i32), ("Gw", i32),
+        ("V", i32), ("K", i32), ("hid", i32), ("nparts", i32),
+        ("x", vp), ("views_w", vp), ("k3_w", vp), ("k1_w", vp), ("f1_w", vp), ("f2_w", vp), ("f2_b", vp), ("a_pos", vp), ("a_neg", vp),
+        ("out", vp), ("views", vp), ("gate", vp), ("dout", vp), ("dx", vp), ("dwv_part", vp), ("dnet_part", vp),
+    ]
+
+
 class LnParams(C.Structure):
     _fields_ = [
         ("struct_bytes", i32), ("rows", i32), ("D", i32), ("r_dtype", i32), ("y_dtype", i32), ("rows_per_sample", i32),
@@ -111,6 +120,15 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_token_gate_partial_rows.restype = C.c_int
+        lib.mop_token_gate_partial_rows.argtypes = [C.c_int]
+        lib.mop_token_gate_wv_groups.restype = C.c_int
+        lib.mop_token_gate_wv_groups.argtypes = [C.c_int]
+        lib.mop_token_gate_net_params.restype = C.c_int
+        lib.mop_token_gate_net_params.argtypes = [C.c_void_p]
+        for fn in (lib.mop_token_gate_fwd, lib.mop_token_gate_bwd):
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p]
         lib.mop_mop2d_partial_rows.restype = C.c_int
         lib.mop_mop2d_fwd.restype = C.c_int
         lib.mop_mop2d_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -46,6 +46,30 @@ def _compat(cls):
 
 
 _ORIGINALS: Dict[tuple, type] = {}
+_FUSED_VIT_MOP: Dict[type, type] = {}
+
+
+def _fused_vit_mop(ref_cls: type) -> type:
+    """The reference's ViT_MoP with the post-encoder token gate (vit_mop.py:95-114) computed by the fused kernel: same
+    constructor, parameters and state_dict (it IS the reference class, only `forward` is replaced)."""
+    if ref_cls in _FUSED_VIT_MOP:
+        return _FUSED_VIT_MOP[ref_cls]
+    import torch.nn.functional as F
+    from . import functional as MF
+
+    def forward(self, x):
+        tok, grid = self.enc(x)
+        k3, k1 = self.kerns.k[0].weight, self.kerns.k[2].weight
+        f1, f2 = self.fuse.fuse[0], self.fuse.fuse[2]
+        if not MF.token_gate_supported(tok, grid, self.n_views, self.n_kernels, f1.weight.shape[0]):
+            return ref_cls.forward(self, x)   # (shapes outside the kernel: the reference's own PyTorch composition)
+        tok = MF.token_gate(tok, grid, self.views.proj.weight, k3, k1, f1.weight, f2.weight, f2.bias,
+                            F.softplus(self.fuse.alpha_pos), F.softplus(self.fuse.alpha_neg))
+        return self.cls(tok.mean(dim=1))
+
+    cls = type(ref_cls.__name__, (ref_cls,), {"forward": forward, "__module__": "mop_b200.dropin", "__doc__": _fused_vit_mop.__doc__})
+    _FUSED_VIT_MOP[ref_cls] = cls
+    return cls
 
 
 def unpatch_reference() -> int:
@@ -70,6 +94,11 @@ def patch_reference(verbose: bool = False) -> Dict[str, List[str]]:
         is_exp = modname in _EXPERIMENT_MODULES
         if not (is_ref_pkg or is_exp):
             continue
+        vm = getattr(mod, "ViT_MoP", None)
+        if isinstance(vm, type) and not vm.__module__.startswith("mop_b200"):
+            _ORIGINALS[(modname, "ViT_MoP")] = vm
+            setattr(mod, "ViT_MoP", _fused_vit_mop(vm))
+            done.setdefault(modname, []).append("ViT_MoP")
         for name, repl in _CANONICAL.items():
             cur = getattr(mod, name, None)
             if cur is None or not isinstance(cur, type) or cur.__module__.startswith("mop_b200"):

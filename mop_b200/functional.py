@@ -641,6 +641,92 @@ def add_layer_norm(x: torch.Tensor, r: Optional[torch.Tensor], scale: Optional[t
 
 
 # ----------------------------------------------------------------------------
+# ViT-MoP token gate
+# ----------------------------------------------------------------------------
+def token_gate_supported(tok: torch.Tensor, grid, n_views: int, n_kernels: int, hid: int) -> bool:
+    """Shapes the fused token-gate kernel takes (others run the reference's own PyTorch composition)."""
+    B, T, D = tok.shape
+    return (tok.is_cuda and tok.dtype in (torch.float32, torch.bfloat16) and grid[0] * grid[1] == T and T <= 256 and D % 8 == 0
+            and D <= 2048 and 1 <= n_views <= 8 and 1 <= n_kernels <= 8 and 1 <= hid <= 16)
+
+
+def _fill_token_gate(p, tok, grid, w):
+    B, T, D = tok.shape
+    p.dtype = _lib.MOP_BF16 if tok.dtype == torch.bfloat16 else _lib.MOP_F32
+    p.B, p.T, p.D, p.Gh, p.Gw = B, T, D, int(grid[0]), int(grid[1])
+    p.V, p.K, p.hid = w[0].shape[0], w[2].shape[0], w[3].shape[0]
+    p.x = _ptr(tok)
+    p.views_w, p.k3_w, p.k1_w, p.f1_w, p.f2_w, p.f2_b, p.a_pos, p.a_neg = (_ptr(t) for t in w)
+
+
+class _TokenGate(torch.autograd.Function):
+    """out = tok * gate(tok).  Inputs after `grid`: views_w [V,D], k3_w [16,V,3,3], k1_w [K,16], f1_w [hid,V+K], f2_w [2,hid],
+    f2_b [2], a_pos [1], a_neg [1]."""
+
+    @staticmethod
+    def forward(ctx, tok, grid, max_ctas, *weights):
+        lib = _lib.load()
+        _need_cuda(tok, "tok")
+        x = tok.detach().contiguous()
+        w = [_f32c(t).reshape(s) for t, s in zip(weights, (
+            (weights[0].shape[0], -1), (16, weights[0].shape[0], 3, 3), (weights[2].shape[0], 16), (weights[3].shape[0], -1),
+            (2, -1), (2,), (1,), (1,)))]
+        B, T, D = x.shape
+        V = w[0].shape[0]
+        out = torch.empty_like(x)
+        views = torch.empty(B, T, V, dtype=torch.float32, device=x.device)
+        gate = torch.empty(B, T, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            p = _lib.new_params(_lib.TokenGateParams)
+            _fill_token_gate(p, x, grid, w)
+            p.out, p.views, p.gate = _ptr(out), _ptr(views), _ptr(gate)
+            _lib.check(lib.mop_token_gate_fwd(C.byref(p), _stream()), "mop_token_gate_fwd")
+        abi_calls["token_gate_fwd"] = abi_calls.get("token_gate_fwd", 0) + 1
+        ctx.save_for_backward(x, views, gate, *w)
+        ctx.grid, ctx.max_ctas = (int(grid[0]), int(grid[1])), max_ctas
+        ctx.wmeta = [(t.shape, t.dtype) for t in weights]
+        ctx.tok_dtype = tok.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, views, gate, *w = ctx.saved_tensors
+        B, T, D = x.shape
+        V = w[0].shape[0]
+        dy = dout.detach().to(x.dtype).contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            p = _lib.new_params(_lib.TokenGateParams)
+            _fill_token_gate(p, x, ctx.grid, w)
+            p.views, p.gate, p.dout, p.dx = _ptr(views), _ptr(gate), _ptr(dy), _ptr(dx)
+            nparts = lib.mop_token_gate_partial_rows(B)
+            if ctx.max_ctas:
+                nparts = max(1, min(nparts, int(ctx.max_ctas)))
+            nnet = lib.mop_token_gate_net_params(C.byref(p))
+            groups = lib.mop_token_gate_wv_groups(D)
+            dwv = torch.empty(nparts * groups, V, D, dtype=torch.float32, device=x.device)
+            dnet = torch.empty(nparts, nnet + 2, dtype=torch.float32, device=x.device)
+            p.nparts, p.dwv_part, p.dnet_part = nparts, _ptr(dwv), _ptr(dnet)
+            _lib.check(lib.mop_token_gate_bwd(C.byref(p), _stream()), "mop_token_gate_bwd")
+        abi_calls["token_gate_bwd"] = abi_calls.get("token_gate_bwd", 0) + 1
+        tot = dnet.sum(0)
+        sizes = [w[1].numel(), w[2].numel(), w[3].numel(), w[4].numel(), 2, 1, 1]
+        pieces = torch.split(tot, sizes)
+        grads = [dwv.sum(0)] + list(pieces)
+        grads = [g.reshape(shape).to(dt) for g, (shape, dt) in zip(grads, ctx.wmeta)]
+        return (dx.to(ctx.tok_dtype), None, None, *grads)
+
+
+def token_gate(tok: torch.Tensor, grid, views_w, k3_w, k1_w, f1_w, f2_w, f2_b, a_pos, a_neg, *, _max_ctas: int = 0) -> torch.Tensor:
+    """``tok * gate`` of the ViT-MoP post-encoder gate (reference vit_mop.py:95-114, components.py:255-303), one fused kernel per
+    direction.  ``tok [B, T, D]`` (fp32 or bf16), ``grid = (Gh, Gw)``; the weights are the module parameters
+    (``ViewsLinear.proj.weight``, ``Kernels3.k[0].weight``, ``Kernels3.k[2].weight``, ``FuseExcInh.fuse[0].weight``,
+    ``FuseExcInh.fuse[2].weight / .bias``) and ``a_pos / a_neg = softplus(alpha)`` as one-element tensors."""
+    return _TokenGate.apply(tok, tuple(grid), _max_ctas, views_w, k3_w, k1_w, f1_w, f2_w, f2_b, a_pos.reshape(1), a_neg.reshape(1))
+
+
+# ----------------------------------------------------------------------------
 # Whisper-MoP 2D gate (SURVEY 8f-3)
 # ----------------------------------------------------------------------------
 class _MoP2DGate(torch.autograd.Function):

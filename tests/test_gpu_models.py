@@ -80,10 +80,13 @@ def _grads_close(ref_model, ours, tol):
 
 def test_patched_reference_vit_baseline_and_vit_mop(patched):
     """Models A and B of the reference (components.MSA inside ViTEncoder blocks) with MSA swapped for the fused kernel."""
-    from mop.models import ViT_Baseline, ViT_MoP
-    for build in (lambda: ViT_Baseline(dim=64, depth=2, heads=2, n_classes=10),
-                  lambda: ViT_MoP(dim=60, depth=2, heads=2, n_classes=10, n_views=3, n_kernels=2)):
+    import mop.models as mm   # (classes are looked up at build time: patch_reference() swaps ViT_MoP itself)
+    from mop_b200 import functional as MF
+    for i, build in enumerate((lambda: mm.ViT_Baseline(dim=64, depth=2, heads=2, n_classes=10),
+                               lambda: mm.ViT_MoP(dim=60, depth=2, heads=2, n_classes=10, n_views=3, n_kernels=2),     # D % 8 != 0: reference gate path
+                               lambda: mm.ViT_MoP(dim=64, depth=2, heads=2, n_classes=10, n_views=5, n_kernels=3))):   # fused token gate
         patched[1].unpatch_reference()
+        calls = MF.abi_calls.get("token_gate_fwd", 0), MF.abi_calls.get("token_gate_bwd", 0)
         ref_model, ours = _twin(build, patched)
         assert any(type(m).__module__.startswith("mop_b200") for m in ours.modules())
         assert not any(type(m).__module__.startswith("mop_b200") for m in ref_model.modules())
@@ -93,6 +96,8 @@ def test_patched_reference_vit_baseline_and_vit_mop(patched):
         assert max_abs(y, y_ref) <= 2e-5
         y_ref.square().sum().backward(); y.square().sum().backward()
         _grads_close(ref_model, ours, 5e-5)
+        if i == 2:   # the post-encoder gate of model B ran in the fused kernel, forward and backward
+            assert MF.abi_calls.get("token_gate_fwd", 0) == calls[0] + 1 and MF.abi_calls.get("token_gate_bwd", 0) == calls[1] + 1
 
 
 def test_patched_reference_gpt_quartet(patched):
