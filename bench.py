@@ -59,8 +59,8 @@ def select_config(name: str, batch: int = 0):
 # problems) from the committed `ncu --set full` capture (a citation, not measured in this run): algorithmic read bytes are
 # 29.4 MB (Q, K, V, dy) + 17.8 MB (the forward's row statistics / feature means / gate factors) = 47.2 MB, i.e. no re-reads
 # (the 22 MB of dqkv written stay in L2 until after the launch).
-DOMINANT_KERNEL_DRAM_BYTES = 47307520 + 1048832
-DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r02b_ew64_bwd3_ncu_full_raw.csv (ncu --set full, one launch; cited constant)"
+DOMINANT_KERNEL_DRAM_BYTES = 47314688 + 1023488
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r02_ew64_ncu_full_raw.csv (ncu --set full, one launch of edgewise_bwd3_kernel; cited constant)"
 WORKLOAD = "ViTEdgewise E+ (dim224 depth8 heads4 V5 share_qkv use_k3 lowrank:mix5 r4), CIFAR-shaped 32x32, batch 256/GPU, fwd+bwd+AdamW"
 
 
@@ -471,6 +471,13 @@ def extra_measurements(dev, flush, pk):
             ms = time_steps(m, ac, 3, 2)
             res[name] = {"ms_per_step": ms, "images_per_sec": BATCH / (ms * 1e-3)}
             del m
+        # ... and the dense + k3 variant of the reference (cuDNN convolutions on [B*H, 12, 64, 64] feature stacks): the fp32-math
+        # dense gate head of this repo is SLOWER than this, see DESIGN.md section 6
+        torch.manual_seed(0)
+        m = reference_vit_edgewise(num_tokens=NTOK, patch=PATCH, **dict(MODEL, gate_mode="dense")).to(dev).train()
+        ms = time_steps(m, True, 3, 2)
+        res["dense_k3_bf16_autocast"] = {"ms_per_step": ms, "images_per_sec": BATCH / (ms * 1e-3)}
+        del m
         out["gpu_reference_eager"] = dict(res, note="unmodified reference modules (baseline/_ref) run eagerly on this GPU, same model / batch")
     except Exception as e:
         out["gpu_reference_eager"] = {"unavailable": repr(e)[:200]}
