@@ -1,6 +1,6 @@
 // Edgewise (Mixture-of-Products) attention backward on tcgen05 / TMEM for token counts up to 200 (ViT-B/16: N = 196).
 //
-// Same execution model as the forward (edgewise_tc_large.cuh): one persistent CTA of 256 threads per SM, one
+// Execution model of edgewise_tc_large.cuh with one thread per row: one persistent CTA of 256 threads per SM, one
 // (batch, head) problem at a time, M=128 row blocks, one thread per row of every fp32 accumulator.  The backward
 // touches ~25 N x N maps per problem, far more than fits on chip, so every map that is needed again later is kept
 // as a bf16 tile image in a per-CTA scratch region of the caller's workspace (27 slots x 86.5 KB; written by the

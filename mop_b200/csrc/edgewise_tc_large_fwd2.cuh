@@ -1,8 +1,8 @@
 // Edgewise (Mixture-of-Products) attention forward on tcgen05 / TMEM for token counts up to 200 (ViT-B/16: N = 196,
 // dk = 64, V = 5), 512 threads: TWO THREADS PER ROW.
 //
-// Same algorithm, buffers and passes as the first version described at the top of edgewise_tc_large.cuh (pass R, pass F, flash-style
-// final stage); what changes is who does the element work.  Every fp32 accumulator row (TMEM lane) is shared by the two
+// Algorithm, buffers and passes: see the top of edgewise_tc_large.cuh (pass R, pass F, flash-style final stage).  The first version
+// of this kernel ran one thread per row (256 threads); what changed is who does the element work.  Every fp32 accumulator row (TMEM lane) is shared by the two
 // threads tid and tid ^ 256 - warps w and w + 8 see the same 32 TMEM lanes - and each takes half of the row's columns
 // (chunks of 16 in the passes, 16 of the 32 panel columns in the final stage).  Row statistics (max, sums, log sums) are
 // combined through a 2 KB exchange buffer (all the shared memory that is left) and 64-thread named barriers.  With one thread per row the SM
