@@ -88,7 +88,10 @@ int mop_edgewise_partial_rows(const MopEdgewiseParams* p) {
 
 size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p) {
   if (check_edgewise(p, false) != MOP_OK) return 0;
-  return (p->impl != MOP_IMPL_SIMT && ewtc::supported(p)) ? (size_t)p->B * p->H * ewtc::kAuxFloats : 0;
+  if (p->impl == MOP_IMPL_SIMT) return 0;
+  if (ewtc::supported(p)) return (size_t)p->B * p->H * ewtc::kAuxFloats;
+  if (ewl::supported(p)) return (size_t)p->B * p->H * ewl::kAuxLFloats;
+  return 0;
 }
 
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward) {

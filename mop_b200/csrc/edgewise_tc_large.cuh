@@ -49,6 +49,13 @@ constexpr int kBufA = kRA * 16 * kMapChunks;  // 86528
 constexpr int kQt = kRX * 16 * 8;             // 25600
 constexpr int kKt = kRA * 16 * 8;             // 26624
 constexpr int kPanel = 32;                    // final-stage panel width (columns)
+// what the forward hands to the backward per (b, h) problem (MopEdgewiseParams::aux, floats, [field][208 tokens] so that one
+// thread per token reads / writes coalesced): per-view softmax statistics, the 14 feature means, the gate factors a and b
+constexpr int kAuxLStats = 0;                             // [V][2][208]: max * log2(e), 1 / sum of the row of S_k
+constexpr int kAuxLFeat = kAuxLStats + kMaxV * 2 * kNmax; // [14][208]: rho_0..4, kap_0..4, rhoF, rhoR, kapF, kapR
+constexpr int kAuxLA = kAuxLFeat + (2 * kMaxV + 4) * kNmax;   // [16][208] row gate factors
+constexpr int kAuxLB = kAuxLA + kMaxQ * kNmax;            // [16][208] column gate factors
+constexpr int kAuxLFloats = kAuxLB + kMaxQ * kNmax;       // 11648 floats = 46.6 KB
 constexpr int kKsP = kPanel * 16 * 8;         // one scaled key panel: 4096
 
 // final-stage aliases inside A (dead once the chain passes are done)

@@ -10,7 +10,8 @@
 //
 // Phases per problem (executable specification: oracle/edgewise_manual.py):
 //   1  forward recompute: pass R and pass F of the forward, keeping A_k, the suffix products A_{V-1}..A_k, the
-//      prefix products A_0..A_k, F and R; gate factors a (registers) and b (shared);
+//      prefix products A_0..A_k, F and R.  The softmax statistics, the feature means and the gate factors a, b come from
+//      the forward (MopEdgewiseParams::aux): A_k is one exp2 pass, no row / column statistics are formed again;
 //   2  mixed-map backward, flash style over 32-column panels: score panels + dA = dY V_1^T panel by MMA, the mix is
 //      recomputed in registers, A = exp2(mix - lse) with the row statistics saved by the forward,
 //      D = A (dA - delta), delta = dY . (A V_1) with A V_1 in fp32 from the forward; keeps A, the four gate pre-activation gradients, the direct
@@ -173,6 +174,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
     auto tok_row = [&](const void* base, int n) { return reinterpret_cast<const __nv_bfloat16*>(base) + (((size_t)pb * N + n) * H + ph) * dk; };
     // row image of a scratch map (R = 208 layout): chunk c of this thread's row
     auto map_chunk = [&](int s, int c) -> unsigned char* { return slot(s) + (size_t)c * (kRA * 16) + row * 16; };
+    // what the forward left for this problem: per-view softmax statistics, feature means, gate factors ([field][208 tokens])
+    const float* aux = p.aux + (size_t)g * kAuxLFloats;
     // =================================================================================================
     // stage 0
     // =================================================================================================
@@ -206,12 +209,8 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       if (tid < kRX) *reinterpret_cast<uint4*>(sm.Q + ch * (kRX * 16) + tid * 16) = q;
     }
     __syncthreads();
-    float rho[kMaxV], rhoF = 0.f, rhoR = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i) rho[i] = 0.f;
-    // accumulator -> bf16 row of X and / or of a scratch map, and / or log statistics
-    auto chain_epilogue = [&](bool store_x, int gslot, bool logs, int cslot, float& rowmean) {
-      float ls = 0.f;
+    // accumulator -> bf16 row of X and / or of a scratch map
+    auto chain_epilogue = [&](bool store_x, int gslot) {
       for (int c = 0; c < KS; ++c) {
         float v[16];
         tmem_ld_32x32b_x16(tl + 16 * c, v);
@@ -227,17 +226,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
           *reinterpret_cast<uint4*>(map_chunk(gslot, 2 * c)) = lo;
           *reinterpret_cast<uint4*>(map_chunk(gslot, 2 * c + 1)) = hi;
         }
-        if (logs) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool ok = row_ok && 16 * c + e < N;
-            v[e] = ok ? kLn2 * fast_log2(v[e] + p.eps) : 0.f;
-            ls += v[e];
-          }
-          colsum16_to(&sm.colsum[cslot][16 * c], v, lane);
-        }
       }
-      if (logs) rowmean = ls * invN;
     };
     MOP_TS(T0);
     // =================================================================================================
@@ -262,50 +251,20 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         mma_wait();
       }
       if (warp_on) {
-        float mx = -INFINITY, rs = 0.f;
+        // A_k = exp2(S_k log2e - mb) / l with the row statistics of the forward: one pass, bit-identical to the forward's A_k
+        const float mb = row_ok ? aux[kAuxLStats + (2 * k) * kNmax + row] : 0.f;
+        const float inv_l = row_ok ? aux[kAuxLStats + (2 * k + 1) * kNmax + row] : 0.f;
         for (int c = 0; c < KS; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
           tmem_ld_wait();
           if (c < cfull) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { mx = fmaxf(mx, v[e]); rs += v[e]; }
+            for (int e = 0; e < 16; ++e) v[e] = fast_exp2(fmaf(v[e], kLog2e, -mb));
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (16 * c + e < N) { mx = fmaxf(mx, v[e]); rs += v[e]; } else v[e] = 0.f;
-            }
+            for (int e = 0; e < 16; ++e) v[e] = (16 * c + e < N) ? fast_exp2(fmaf(v[e], kLog2e, -mb)) : 0.f;
           }
-          if (!row_ok) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0.f;
-          }
-          colsum16_to(&sm.colsum[k][16 * c], v, lane);
-        }
-#pragma unroll
-        for (int i = 0; i < kMaxV; ++i)
-          if (i == k) rho[i] = rs * invN;
-        float l = 0.f;
-        const float mb = mx * kLog2e;
-        for (int c = 0; c < KS; ++c) {
-          float v[16];
-          tmem_ld_32x32b_x16(tl + 16 * c, v);
-          tmem_ld_wait();
-          if (c < cfull) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { v[e] = fast_exp2(fmaf(v[e], kLog2e, -mb)); l += v[e]; }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { v[e] = (16 * c + e < N) ? fast_exp2(fmaf(v[e], kLog2e, -mb)) : 0.f; l += v[e]; }
-          }
-          tmem_st_32x32b_x16(tl + 16 * c, v);
-        }
-        tmem_st_wait();
-        const float inv_l = 1.f / l;
-        for (int c = 0; c < KS; ++c) {
-          float v[16];
-          tmem_ld_32x32b_x16(tl + 16 * c, v);
-          tmem_ld_wait();
           uint4 lo, hi;
           pack16(v, inv_l, lo, hi);
           if (!row_ok) lo = hi = make_uint4(0, 0, 0, 0);
@@ -329,7 +288,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         if (t == 0) { mma_x_a(); commit(); }
         mma_wait();
       }
-      if (warp_on) chain_epilogue(!last, last ? kSlotR : kSlotSfx + k - 1, last, V + 1, rhoR);
+      if (warp_on) chain_epilogue(!last, last ? kSlotR : kSlotSfx + k - 1);
       if (last && row < kRX) {
         for (int c = 0; c < 2 * KS; ++c)
           *reinterpret_cast<uint4*>(sm.X + c * (kRX * 16) + row * 16) =
@@ -353,7 +312,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         sync_cta();
         load_start(sm.A, slot(kSlotA + k + 1), map_bytes);
       }
-      if (warp_on) chain_epilogue(true, last ? kSlotF : kSlotPfx + k - 1, last, V, rhoF);
+      if (warp_on) chain_epilogue(true, last ? kSlotF : kSlotPfx + k - 1);
       if (!last) publish_cta();
     }
     publish_cta();   // F in X and in its slot; colsum final; A and K buffers free
@@ -374,38 +333,26 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
         }
       }
     };
+    // gate factors a (registers) / b (shared) and the feature means of this token, as the forward computed them
     float afac[kMaxQ];
     float fr[2 * kMaxV + 2], fc[2 * kMaxV + 2];
     {
 #pragma unroll
       for (int c = 0; c < kMaxV; ++c) {
-        const float kap = (c < V && row < kNmax) ? sm.colsum[c][row] * invN : 0.f;
-        fr[c] = rho[c]; fr[kMaxV + c] = kap;
-        fc[c] = kap;    fc[kMaxV + c] = rho[c];
+        const float rh = (c < V && row_ok) ? aux[kAuxLFeat + c * kNmax + row] : 0.f;
+        const float kp = (c < V && row_ok) ? aux[kAuxLFeat + (kMaxV + c) * kNmax + row] : 0.f;
+        fr[c] = rh; fr[kMaxV + c] = kp;
+        fc[c] = kp; fc[kMaxV + c] = rh;
       }
-      const float kapF = row < kNmax ? sm.colsum[V][row] * invN : 0.f, kapR = row < kNmax ? sm.colsum[V + 1][row] * invN : 0.f;
-      fr[2 * kMaxV] = rhoF; fr[2 * kMaxV + 1] = rhoR;
-      fc[2 * kMaxV] = kapF; fc[2 * kMaxV + 1] = kapR;
+      fr[2 * kMaxV] = row_ok ? aux[kAuxLFeat + (2 * kMaxV) * kNmax + row] : 0.f;
+      fr[2 * kMaxV + 1] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 1) * kNmax + row] : 0.f;
+      fc[2 * kMaxV] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 2) * kNmax + row] : 0.f;
+      fc[2 * kMaxV + 1] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 3) * kNmax + row] : 0.f;
 #pragma unroll
       for (int qq = 0; qq < kMaxQ; ++qq) {
-        const int tg = qq >> 2, kk = qq & 3, q = tg * r + kk;
-        float a = 0.f, b = 0.f;
-        if (kk < r && row_ok) {
-          a = __ldg(p.row_b + q);
-          b = __ldg(p.col_b + q);
-#pragma unroll
-          for (int c = 0; c < kMaxV; ++c)
-            if (c < V) {
-              a = fmaf(__ldg(p.row_w + q * C + c), fr[c], a);
-              a = fmaf(__ldg(p.row_w + q * C + V + c), fr[kMaxV + c], a);
-              b = fmaf(__ldg(p.col_w + q * C + c), fc[c], b);
-              b = fmaf(__ldg(p.col_w + q * C + V + c), fc[kMaxV + c], b);
-            }
-          a = fmaf(__ldg(p.row_w + q * C + 2 * V), fr[2 * kMaxV], a);
-          a = fmaf(__ldg(p.row_w + q * C + 2 * V + 1), fr[2 * kMaxV + 1], a);
-          b = fmaf(__ldg(p.col_w + q * C + 2 * V), fc[2 * kMaxV], b);
-          b = fmaf(__ldg(p.col_w + q * C + 2 * V + 1), fc[2 * kMaxV + 1], b);
-        }
+        const bool on = (qq & 3) < r && row_ok;
+        const float a = on ? aux[kAuxLA + qq * kNmax + row] : 0.f;
+        const float b = on ? aux[kAuxLB + qq * kNmax + row] : 0.f;
         afac[qq] = a;
         if (row < kNmax) bfac[row * 16 + qq] = b;
         const float asum = warp_sum(a);   // a = 0 for padded rows
@@ -1118,7 +1065,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
   if (tid < 32) tmem_dealloc<512>(tbase);
 }
 
-inline bool supported_bwd(const MopEdgewiseParams* p) { return supported(p) && p->row_stats != nullptr && p->y_base != nullptr; }
+inline bool supported_bwd(const MopEdgewiseParams* p) { return supported(p) && p->row_stats != nullptr && p->y_base != nullptr && p->aux != nullptr; }
 
 }  // namespace ewl
 }  // namespace mop

@@ -138,6 +138,7 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int pb = g / H, ph = g % H;
     auto in_row = [&](int n) { return qkv + (((size_t)pb * N + n) * 3) * hd + (size_t)ph * dk; };   // q; +hd: k; +2hd: v
+    float* aux = p.aux ? p.aux + (size_t)g * kAuxLFloats : nullptr;   // statistics / means / factors for the backward
     MOP_TSF(F0);
     // a [rows x 64] operand tile from the token rows of q (which = 0), k (1) or v (2), optionally scaled per feature:
     // item = (row, 8-feature chunk), consecutive threads take the chunks of one row (128 contiguous bytes)
@@ -293,6 +294,10 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
         tmem_st_wait();
         l += exchange(l);
         const float inv_l = 1.f / l;
+        if (aux && half == 0 && row_ok) {
+          aux[kAuxLStats + (2 * k) * kNmax + row] = mb;
+          aux[kAuxLStats + (2 * k + 1) * kNmax + row] = inv_l;
+        }
         for (int c = cb; c < ce; ++c) {
           float v[16];
           tmem_ld_32x32b_x16(tl + 16 * c, v);
@@ -388,6 +393,14 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
         if (c == 2 * V + 1) { a = rhoR; b = kapR; }
         fr[c] = a; fc[c] = b;
       }
+      if (aux && half == 0 && row_ok) {
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i) { aux[kAuxLFeat + i * kNmax + row] = rho[i]; aux[kAuxLFeat + (kMaxV + i) * kNmax + row] = kap[i]; }
+        aux[kAuxLFeat + (2 * kMaxV) * kNmax + row] = rhoF;
+        aux[kAuxLFeat + (2 * kMaxV + 1) * kNmax + row] = rhoR;
+        aux[kAuxLFeat + (2 * kMaxV + 2) * kNmax + row] = kapF;
+        aux[kAuxLFeat + (2 * kMaxV + 3) * kNmax + row] = kapR;
+      }
 #pragma unroll
       for (int qq = 0; qq < kMaxQ; ++qq) {
         const int tg = qq >> 2, kk = qq & 3, q = tg * r + kk;
@@ -412,6 +425,7 @@ static __global__ void __launch_bounds__(512, 1) edgewise_fwd2_kernel(MopEdgewis
         }
         afac[qq] = a;
         if (mine && row < kNmax) bfac[row * 16 + qq] = b;
+        if (aux && mine && row_ok) { aux[kAuxLA + qq * kNmax + row] = a; aux[kAuxLB + qq * kNmax + row] = b; }
       }
     }
     publish_cta();
