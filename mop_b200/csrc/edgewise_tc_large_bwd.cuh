@@ -72,7 +72,8 @@ constexpr int kOffDy = 0;                          // kQt bytes (R = 200)
 constexpr int kAbf = kRA * 16 * 2;                 // 6656: [208 x 16] bf16
 constexpr int kOffAbf = kQt;                       // 4 x kAbf
 constexpr int kOffDab = kOffAbf + 4 * kAbf;        // float da[16][208], db[16][208]
-static_assert(kOffDab + 2 * 16 * kNmax * 4 <= kBufX, "phase-3 staging overflows the X buffer");
+constexpr int kOffHw = kOffDab + 2 * 16 * kNmax * 4;      // gate-head weights (row | column projection), phase 3
+static_assert(kOffHw + 2 * kMaxQ * (2 * kMaxV + 2) * 4 <= kBufX, "phase-3 staging overflows the X buffer");
 
 // column sums over the 32 rows of a warp for 16 columns, added to dst[col] (shared memory)
 __device__ __forceinline__ void colsum16_to(float* dst, const float* v, int lane) {
@@ -348,14 +349,17 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       fr[2 * kMaxV + 1] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 1) * kNmax + row] : 0.f;
       fc[2 * kMaxV] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 2) * kNmax + row] : 0.f;
       fc[2 * kMaxV + 1] = row_ok ? aux[kAuxLFeat + (2 * kMaxV + 3) * kNmax + row] : 0.f;
+      float bq[kMaxQ];
+#pragma unroll
+      for (int qq = 0; qq < kMaxQ; ++qq) {   // every load is issued before the first shuffle / atomic below
+        const bool on = (qq & 3) < r && row_ok;
+        afac[qq] = on ? aux[kAuxLA + qq * kNmax + row] : 0.f;
+        bq[qq] = on ? aux[kAuxLB + qq * kNmax + row] : 0.f;
+      }
 #pragma unroll
       for (int qq = 0; qq < kMaxQ; ++qq) {
-        const bool on = (qq & 3) < r && row_ok;
-        const float a = on ? aux[kAuxLA + qq * kNmax + row] : 0.f;
-        const float b = on ? aux[kAuxLB + qq * kNmax + row] : 0.f;
-        afac[qq] = a;
-        if (row < kNmax) bfac[row * 16 + qq] = b;
-        const float asum = warp_sum(a);   // a = 0 for padded rows
+        if (row < kNmax) bfac[row * 16 + qq] = bq[qq];
+        const float asum = warp_sum(afac[qq]);   // a = 0 for padded rows
         if (lane == 0 && asum != 0.f) atomicAdd(&sm.amean[qq], asum);
       }
     }
@@ -363,19 +367,42 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
     // exact (fp32) column sums of the four gate pre-activation gradients, accumulated in phase 2: [4][208] in the K region
     float* cs_s = reinterpret_cast<float*>(sm.K);
     for (int idx = tid; idx < 4 * kNmax; idx += 256) cs_s[idx] = 0.f;
+    // delta = rowsum(dA . A) = dY . (A V_1), with A V_1 in fp32 from the forward: eight lanes per row (32 B of y_base and 16 B
+    // of dY per lane; four rows per warp instruction, seven passes per warp, all loads of a pass group in flight) - one thread
+    // per 256-byte row costs 32 sectors per load instruction and 24 dependent round trips
+    float* delta_s = cs_s + 4 * kNmax;   // [208]
+    {
+      const int wrp = tid >> 5, sub = lane >> 3, l8 = lane & 7;
+      for (int ps0 = 0; ps0 < 7; ps0 += 4) {
+        float4 ya[4], yb4[4];
+        uint4 da4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ps = ps0 + i, rr = 28 * wrp + 4 * ps + sub;   // 8 warps x 28 rows >= 208
+          const bool ok = ps < 7 && rr < N && 8 * l8 < dk;
+          const size_t o = (((size_t)pb * N + (ok ? rr : 0)) * H + ph) * dk + 8 * l8;
+          ya[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.y_base + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          yb4[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.y_base + o + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          da4[i] = ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + o)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ps = ps0 + i, rr = 28 * wrp + 4 * ps + sub;
+          float dv[8];
+          unpack8(da4[i], dv);
+          float d = fmaf(dv[0], ya[i].x, fmaf(dv[1], ya[i].y, fmaf(dv[2], ya[i].z, dv[3] * ya[i].w)));
+          d = fmaf(dv[4], yb4[i].x, fmaf(dv[5], yb4[i].y, fmaf(dv[6], yb4[i].z, fmaf(dv[7], yb4[i].w, d))));
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (l8 == 0 && ps < 7 && rr < kNmax) delta_s[rr] = d;
+        }
+      }
+    }
     publish_cta();
-    // delta = rowsum(dA . A) = dY . (A V_1), with A V_1 in fp32 from the forward
     float delta = 0.f, lse2 = 0.f, inv_lmix = 0.f;
     if (row_ok) {
-      const __nv_bfloat16* dyr = tok_row(p.dy, row);
-      const float* yb = p.y_base + (((size_t)pb * N + row) * H + ph) * dk;
-      for (int d0 = 0; d0 < dk; d0 += 8) {
-        float dv[8];
-        unpack8(*reinterpret_cast<const uint4*>(dyr + d0), dv);
-        const float4 y0 = *reinterpret_cast<const float4*>(yb + d0), y1 = *reinterpret_cast<const float4*>(yb + d0 + 4);
-        delta = fmaf(dv[0], y0.x, fmaf(dv[1], y0.y, fmaf(dv[2], y0.z, fmaf(dv[3], y0.w, delta))));
-        delta = fmaf(dv[4], y1.x, fmaf(dv[5], y1.y, fmaf(dv[6], y1.z, fmaf(dv[7], y1.w, delta))));
-      }
+      delta = delta_s[row];
       const float2 st2 = *reinterpret_cast<const float2*>(p.row_stats + (((size_t)pb * H + ph) * N + row) * 2);
       lse2 = st2.x;          // integer reference exponent (base 2) of this row of the mixed map
       inv_lmix = 1.f / st2.y;   // 1 / sum of the bf16-rounded exp2(mix - reference)
@@ -560,6 +587,13 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
 #pragma unroll
       for (int c = 0; c < 2 * kMaxV + 2; ++c) { fr_s[c * kNmax + row] = row_ok ? fr[c] : 0.f; fc_s[c * kNmax + row] = row_ok ? fc[c] : 0.f; }
     }
+    // the projection weights for the feature-mean gradients below (the L1 next to 227 KB of shared memory is a few KB: read
+    // with __ldg inside the loops they came from L2 one dependent load at a time)
+    float* hw_s = reinterpret_cast<float*>(sm.X + kOffHw);
+    {
+      const int nW = 4 * r * C;
+      for (int idx = tid; idx < 2 * nW; idx += 256) hw_s[idx] = idx < nW ? p.row_w[idx] : p.col_w[idx - nW];
+    }
     publish_cta();
     for (int tg = 0; tg < 4; ++tg) {
       load_start(sm.A, slot(kSlotDG + tg), map_bytes);
@@ -570,6 +604,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
       }
       sync_cta();   // both warpgroups' MMAs have read the map
     }
+    load_start(sm.A, slot(kSlotAmix), map_bytes);   // for phase 4: lands during the vector work below
     MOP_TS(T4a);
     float db[kMaxQ];
 #pragma unroll
@@ -594,15 +629,15 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
 #pragma unroll
           for (int c = 0; c < kMaxV; ++c)
             if (c < V) {
-              drho[c] = fmaf(__ldg(p.row_w + q * C + c), da[qq], drho[c]);
-              drho[kMaxV + c] = fmaf(__ldg(p.row_w + q * C + V + c), da[qq], drho[kMaxV + c]);
-              dkap[c] = fmaf(__ldg(p.col_w + q * C + c), db[qq], dkap[c]);
-              dkap[kMaxV + c] = fmaf(__ldg(p.col_w + q * C + V + c), db[qq], dkap[kMaxV + c]);
+              drho[c] = fmaf(hw_s[q * C + c], da[qq], drho[c]);
+              drho[kMaxV + c] = fmaf(hw_s[q * C + V + c], da[qq], drho[kMaxV + c]);
+              dkap[c] = fmaf(hw_s[4 * r * C + q * C + c], db[qq], dkap[c]);
+              dkap[kMaxV + c] = fmaf(hw_s[4 * r * C + q * C + V + c], db[qq], dkap[kMaxV + c]);
             }
-          drho[2 * kMaxV] = fmaf(__ldg(p.row_w + q * C + 2 * V), da[qq], drho[2 * kMaxV]);
-          drho[2 * kMaxV + 1] = fmaf(__ldg(p.row_w + q * C + 2 * V + 1), da[qq], drho[2 * kMaxV + 1]);
-          dkap[2 * kMaxV] = fmaf(__ldg(p.col_w + q * C + 2 * V), db[qq], dkap[2 * kMaxV]);
-          dkap[2 * kMaxV + 1] = fmaf(__ldg(p.col_w + q * C + 2 * V + 1), db[qq], dkap[2 * kMaxV + 1]);
+          drho[2 * kMaxV] = fmaf(hw_s[q * C + 2 * V], da[qq], drho[2 * kMaxV]);
+          drho[2 * kMaxV + 1] = fmaf(hw_s[q * C + 2 * V + 1], da[qq], drho[2 * kMaxV + 1]);
+          dkap[2 * kMaxV] = fmaf(hw_s[4 * r * C + q * C + 2 * V], db[qq], dkap[2 * kMaxV]);
+          dkap[2 * kMaxV + 1] = fmaf(hw_s[4 * r * C + q * C + 2 * V + 1], db[qq], dkap[2 * kMaxV + 1]);
         }
       }
 #pragma unroll
@@ -647,8 +682,7 @@ static __global__ void __launch_bounds__(256, 1) edgewise_bwd_kernel(MopEdgewise
     // =================================================================================================
     // phase 4: dV = (A^T dY) vs_1 + (F^T dY) w vs_V ; v_scale partials ; chain_value_logit partial
     // =================================================================================================
-    load_start(sm.A, slot(kSlotAmix), map_bytes);
-    load_wait();
+    load_wait();   // A = softmax(mix), started at the end of phase 3
     if (blk_on) {
       if (t == 0) { mma_at_tile(0, smem_u32(dYt), kRX, 64, false); commit(); }
       mma_wait();
