@@ -436,6 +436,9 @@ def _fill_quartet(p, q, k, v, q2, k2, mixture, gamma, add_mask, cfg):
     p.dropout_p, p.dropout_seed, p.dropout_offset = cfg.get("dropout", (0.0, 0, 0))
 
 
+quartet_reuse_prep = True   # keep the forward workspace for the backward (ABI v9 `fwd_workspace`); False: the backward redoes the key preparation
+
+
 class _Quartet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, q, k, v, q2, k2, mixture, gamma, add_mask):
@@ -471,7 +474,7 @@ class _Quartet(torch.autograd.Function):
         if y32 is not None:
             saved.append(y32)
         # the tensor-core backward reads the forward's key preparation (centred keys, Gram tiles) from the forward workspace
-        ctx.has_ws = p.impl_used == _lib.MOP_IMPL_TCGEN05 and any(ctx.needs_input_grad)
+        ctx.has_ws = quartet_reuse_prep and p.impl_used == _lib.MOP_IMPL_TCGEN05 and any(ctx.needs_input_grad)
         if ctx.has_ws:
             saved.append(ws)
         ctx.save_for_backward(*saved)

@@ -125,3 +125,30 @@ def test_tcgen05_vs_oracle_and_simt(B, H, T, dk, quart, mask):
     lim = {n: BF16_TOL for n in worst}
     bad = {n: e for n, e in worst.items() if not (e[0] <= lim[n])}
     assert not bad, f"tcgen05 grads off (tc_err, simt_err): {worst}"
+
+
+@pytest.mark.parametrize("B,H,T,quart", [(2, 3, 300, True), (40, 8, 128, True), (2, 2, 200, False)])
+def test_backward_with_the_forward_key_preparation(B, H, T, quart):
+    """ABI v9: the tensor-core backward reads the centred keys / Gram tiles the forward call left in its workspace
+    (`fwd_workspace`) instead of re-running the key preparation - same gradients either way.  (40 x 8 x 2 maps = 640 problems:
+    the one-launch preparation; the small cases take the split preparation with atomics, hence a tolerance.)"""
+    from mop_b200 import functional as MF, quartet_attention
+    g = torch.Generator(device="cuda").manual_seed(T)
+    mk = lambda: torch.randn(B, T, H, 64, generator=g, device="cuda").bfloat16()
+    base = [mk() for _ in range(5)]
+    dy = mk()
+    grads = {}
+    for reuse in (True, False):
+        MF.quartet_reuse_prep = reuse
+        try:
+            ts = [t.clone().requires_grad_(True) for t in base]
+            mix = torch.tensor([0.3], device="cuda", requires_grad=True)
+            gam = torch.tensor([0.9], device="cuda", requires_grad=True)
+            args = (ts[0], ts[1], ts[2], ts[3], ts[4], mix, gam) if quart else (ts[0], ts[1], ts[2])
+            y = quartet_attention(*args, impl="tcgen05")
+            y.backward(dy)
+            grads[reuse] = [t.grad.float() for t in (ts if quart else ts[:3])] + ([mix.grad, gam.grad] if quart else [])
+        finally:
+            MF.quartet_reuse_prep = True
+    for a, b in zip(grads[True], grads[False]):
+        assert max_abs(a, b) <= 1e-3 * max(1.0, b.abs().max().item())
