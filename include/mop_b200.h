@@ -295,6 +295,29 @@ int mop_token_gate_net_params(const MopTokenGateParams* p);
 int mop_token_gate_fwd(MopTokenGateParams* p, void* cuda_stream);
 int mop_token_gate_bwd(MopTokenGateParams* p, void* cuda_stream);
 
+/* GPT-MoP 1-D token gate: MoPBlock.apply_mop mop/models/gpt_mop.py:102-123 (ViewsLinear1D :19-33, Kernels1D :36-49,
+ * FuseExcInh1D :52-67).  Linear and bias-free: the caller folds Kernels1D, FuseExcInh1D and alpha into a 3-tap filter of the views,
+ * w_eff [3, V]; gate[t] = 1 + sum_tau sum_v w_eff[tau+1][v] views[t+tau][v] (zero outside the sequence), out = x * gate. */
+typedef struct MopTokenGate1dParams {
+  int32_t struct_bytes;
+  int32_t dtype;            /* MOP_F32 | MOP_BF16: tokens in / out */
+  int32_t B, T, D, V;       /* x [B, T, D], D % 8 == 0, D <= 2048, V <= 8 */
+  int32_t nparts;           /* CTAs of the backward (mop_token_gate1d_partial_rows) */
+  const void* x;
+  const float* views_w;     /* [V, D] */
+  const float* w_eff;       /* [3, V] */
+  void* out;                /* [B, T, D] */
+  float* views;             /* [B, T, V] fwd out, bwd in */
+  float* gate;              /* [B, T]    fwd out, bwd in */
+  const void* dout;
+  void* dx;
+  float* dwv_part;          /* [nparts * mop_token_gate_wv_groups(D), V, D] */
+  float* dweff_part;        /* [nparts, 3 V] */
+} MopTokenGate1dParams;
+int mop_token_gate1d_partial_rows(int B, int T);
+int mop_token_gate1d_fwd(MopTokenGate1dParams* p, void* cuda_stream);
+int mop_token_gate1d_bwd(MopTokenGate1dParams* p, void* cuda_stream);
+
 /* The dropout factor every attention kernel applies to P[b,h,i,j] for (p, seed, offset): out[bh, i, j] = 0 or 1 / (1 - p)
  * (fp32, [BH, Nq, Nk]).  Test infrastructure: lets the CPU oracle be evaluated under the kernels' own mask. */
 int mop_dropout_mask(float* out, int BH, int Nq, int Nk, float p, uint64_t seed, uint64_t offset, void* cuda_stream);

@@ -82,6 +82,14 @@ class TokenGateParams(C.Structure):
     ]
 
 
+class TokenGate1dParams(C.Structure):
+    _fields_ = [
+        ("struct_bytes", i32), ("dtype", i32), ("B", i32), ("T", i32), ("D", i32), ("V", i32), ("nparts", i32),
+        ("x", vp), ("views_w", vp), ("w_eff", vp), ("out", vp), ("views", vp), ("gate", vp), ("dout", vp), ("dx", vp),
+        ("dwv_part", vp), ("dweff_part", vp),
+    ]
+
+
 class LnParams(C.Structure):
     _fields_ = [
         ("struct_bytes", i32), ("rows", i32), ("D", i32), ("r_dtype", i32), ("y_dtype", i32), ("rows_per_sample", i32),
@@ -127,6 +135,11 @@ def load():
         lib.mop_token_gate_net_params.restype = C.c_int
         lib.mop_token_gate_net_params.argtypes = [C.c_void_p]
         for fn in (lib.mop_token_gate_fwd, lib.mop_token_gate_bwd):
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mop_token_gate1d_partial_rows.restype = C.c_int
+        lib.mop_token_gate1d_partial_rows.argtypes = [C.c_int, C.c_int]
+        for fn in (lib.mop_token_gate1d_fwd, lib.mop_token_gate1d_bwd):
             fn.restype = C.c_int
             fn.argtypes = [C.c_void_p, C.c_void_p]
         lib.mop_mop2d_partial_rows.restype = C.c_int

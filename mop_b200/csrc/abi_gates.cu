@@ -96,4 +96,60 @@ int mop_token_gate_bwd(MopTokenGateParams* p, void* stream) {
   return MOP_OK;
 }
 
+static int check_token_gate1d(const MopTokenGate1dParams* p, bool bwd) {
+  MOP_REQUIRE(p != nullptr, MOP_EINVAL, "null params");
+  MOP_REQUIRE(p->struct_bytes == (int)sizeof(MopTokenGate1dParams), MOP_EINVAL, "MopTokenGate1dParams size mismatch: caller %d, library %zu", p->struct_bytes, sizeof(MopTokenGate1dParams));
+  MOP_REQUIRE(p->dtype == MOP_F32 || p->dtype == MOP_BF16, MOP_EINVAL, "dtype");
+  MOP_REQUIRE(p->B > 0 && p->T > 0, MOP_EINVAL, "empty input");
+  MOP_REQUIRE(p->D >= 8 && p->D % 8 == 0 && p->D <= 8 * tokgate::kThreads, MOP_EUNSUPPORTED, "D=%d (multiple of 8, <= %d)", p->D, 8 * tokgate::kThreads);
+  MOP_REQUIRE(p->V >= 1 && p->V <= tokgate::kMaxV, MOP_EUNSUPPORTED, "V=%d (<= %d)", p->V, tokgate::kMaxV);
+  MOP_REQUIRE(p->x && p->views_w && p->w_eff && p->views && p->gate, MOP_EINVAL, "null tensor");
+  if (bwd) {
+    MOP_REQUIRE(p->dout && p->dx && p->dwv_part && p->dweff_part, MOP_EINVAL, "null gradient tensor");
+    MOP_REQUIRE(p->nparts >= 1, MOP_EWORKSPACE, "nparts=%d", p->nparts);
+  } else {
+    MOP_REQUIRE(p->out != nullptr, MOP_EINVAL, "null out");
+  }
+  return MOP_OK;
+}
+
+int mop_token_gate1d_partial_rows(int B, int T) {
+  int sms = sm_count();
+  const long long chunks = (long long)(B > 0 ? B : 1) * ((T + tokgate1d::kChunk - 1) / tokgate1d::kChunk), cap = (sms > 0 ? sms : 148) * 2;
+  return (int)(chunks < cap ? (chunks > 0 ? chunks : 1) : cap);
+}
+
+int mop_token_gate1d_fwd(MopTokenGate1dParams* p, void* stream) {
+  int rc = check_token_gate1d(p, false);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  const size_t smem = tokgate1d::smem_floats(*p) * sizeof(float);
+  const int grid = mop_token_gate1d_partial_rows(p->B, p->T);
+  if (p->dtype == MOP_BF16) {
+    if ((rc = allow_smem(tokgate1d::fwd_kernel<__nv_bfloat16>, smem))) return rc;
+    tokgate1d::fwd_kernel<__nv_bfloat16><<<grid, tokgate::kThreads, smem, (cudaStream_t)stream>>>(*p);
+  } else {
+    if ((rc = allow_smem(tokgate1d::fwd_kernel<float>, smem))) return rc;
+    tokgate1d::fwd_kernel<float><<<grid, tokgate::kThreads, smem, (cudaStream_t)stream>>>(*p);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
+int mop_token_gate1d_bwd(MopTokenGate1dParams* p, void* stream) {
+  int rc = check_token_gate1d(p, true);
+  if (rc != MOP_OK) return rc;
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  const size_t smem = tokgate1d::smem_floats(*p) * sizeof(float);
+  if (p->dtype == MOP_BF16) {
+    if ((rc = allow_smem(tokgate1d::bwd_kernel<__nv_bfloat16>, smem))) return rc;
+    tokgate1d::bwd_kernel<__nv_bfloat16><<<p->nparts, tokgate::kThreads, smem, (cudaStream_t)stream>>>(*p);
+  } else {
+    if ((rc = allow_smem(tokgate1d::bwd_kernel<float>, smem))) return rc;
+    tokgate1d::bwd_kernel<float><<<p->nparts, tokgate::kThreads, smem, (cudaStream_t)stream>>>(*p);
+  }
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 }  // extern "C"

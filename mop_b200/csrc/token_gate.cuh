@@ -431,4 +431,199 @@ static __global__ void __launch_bounds__(kThreads) bwd_kernel(MopTokenGateParams
 }
 
 }  // namespace tokgate
+
+// GPT-MoP 1-D token gate (reference mop/models/gpt_mop.py:19-67, 102-123): views = ViewsLinear1D(x) (D -> V per token), kernel
+// maps = Conv1d(V -> K, k = 3, padding 1), [g_pos, g_neg] = Conv1d 1x1([views; kernel maps]), gate = 1 + a_pos g_pos - a_neg g_neg,
+// x * gate.  No nonlinearity anywhere: the caller folds the three weight tensors and alpha into ONE 3-tap filter of the views,
+//   gate[t] = 1 + sum_{tau in -1..1} sum_v We[tau + 1][v] views[t + tau][v]     (zero outside the sequence),
+// (tiny, differentiable PyTorch) and the kernels run per chunk of 64 tokens (+ one halo token each side, recomputed).
+namespace tokgate1d {
+
+using tokgate::kMaxV;
+using tokgate::kThreads;
+using tokgate::load8;
+using tokgate::store8;
+constexpr int kChunk = 64;
+constexpr int kHalo = kChunk + 2;
+
+inline size_t smem_floats(const MopTokenGate1dParams& p) { return (size_t)p.V * p.D + 3 * kMaxV + (size_t)(2 * kMaxV + 2) * kHalo; }
+__host__ __device__ inline int wv_groups(int D) { return kThreads / (D / 8); }
+
+// views of tokens t0 - 1 .. t0 + 64 of sequence b (zero outside [0, T)): warp per token
+template <typename T>
+__device__ inline void project_chunk(const MopTokenGate1dParams& p, const T* xseq, int t0, const float* wv_s, float* sv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, V = p.V, D = p.D;
+  for (int i = warp; i < kHalo; i += kThreads / 32) {
+    const int t = t0 - 1 + i;
+    float acc[kMaxV];
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) acc[v] = 0.f;
+    if (t >= 0 && t < p.T) {
+      for (int d0 = lane * 8; d0 < D; d0 += 256) {
+        float f[8];
+        load8<T>(xseq + (size_t)t * D + d0, f);
+#pragma unroll
+        for (int v = 0; v < kMaxV; ++v)
+          if (v < V) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v] = fmaf(f[e], wv_s[v * D + d0 + e], acc[v]);
+          }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v)
+      if (v < V) {
+        const float s = warp_sum(acc[v]);
+        if (lane == 0) sv[v * kHalo + i] = s;
+      }
+  }
+}
+
+// grid: min(chunks, 2 SMs) CTAs of 256 threads
+template <typename T>
+static __global__ void __launch_bounds__(kThreads) fwd_kernel(MopTokenGate1dParams p) {
+  extern __shared__ __align__(16) float smf[];
+  const int V = p.V, D = p.D, Tn = p.T, tid = threadIdx.x;
+  float* wv_s = smf;
+  float* we = wv_s + V * D;            // [3][kMaxV]
+  float* sv = we + 3 * kMaxV;          // [V][66]
+  float* gate_s = sv + kMaxV * kHalo;  // [64]
+  for (int i = tid; i < V * D; i += kThreads) wv_s[i] = p.views_w[i];
+  if (tid < 3 * kMaxV) we[tid] = (tid % kMaxV) < V ? p.w_eff[(tid / kMaxV) * V + tid % kMaxV] : 0.f;
+  __syncthreads();
+  const int cpt = (Tn + kChunk - 1) / kChunk, nchunks = p.B * cpt, nc = D / 8;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int b = c / cpt, t0 = (c % cpt) * kChunk;
+    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)b * Tn * D;
+    T* os = reinterpret_cast<T*>(p.out) + (size_t)b * Tn * D;
+    project_chunk<T>(p, xs, t0, wv_s, sv);
+    __syncthreads();
+    if (tid < kChunk && t0 + tid < Tn) {
+      float g = 1.f;
+#pragma unroll
+      for (int v = 0; v < kMaxV; ++v)
+        if (v < V) {
+          g = fmaf(we[v], sv[v * kHalo + tid], fmaf(we[kMaxV + v], sv[v * kHalo + tid + 1], fmaf(we[2 * kMaxV + v], sv[v * kHalo + tid + 2], g)));
+          p.views[((size_t)b * Tn + t0 + tid) * V + v] = sv[v * kHalo + tid + 1];
+        }
+      gate_s[tid] = g;
+      p.gate[(size_t)b * Tn + t0 + tid] = g;
+    }
+    __syncthreads();
+    const int nt = min(kChunk, Tn - t0);
+    for (int item = tid; item < nt * nc; item += kThreads) {
+      const int t = item / nc, ch = item % nc;
+      float f[8];
+      load8<T>(xs + (size_t)(t0 + t) * D + 8 * ch, f);
+      const float g = gate_s[t];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= g;
+      store8<T>(os + (size_t)(t0 + t) * D + 8 * ch, f);
+    }
+    __syncthreads();
+  }
+}
+
+// grid: nparts CTAs; partial rows: dweff_part [nparts][3 V], dwv_part [nparts * wv_groups(D)][V][D]
+template <typename T>
+static __global__ void __launch_bounds__(kThreads) bwd_kernel(MopTokenGate1dParams p) {
+  extern __shared__ __align__(16) float smf[];
+  const int V = p.V, D = p.D, Tn = p.T, tid = threadIdx.x;
+  float* wv_s = smf;
+  float* we = wv_s + V * D;
+  float* sv = we + 3 * kMaxV;          // [V][66] saved views (zero outside the sequence)
+  float* dvw = sv + kMaxV * kHalo;     // [V][66] d views (first 64 used)
+  float* dg = dvw + kMaxV * kHalo;     // [66]    d gate of tokens t0 - 1 .. t0 + 64
+  float* gate_s = dg + kHalo;          // [66]    (first 64 used)
+  for (int i = tid; i < V * D; i += kThreads) wv_s[i] = p.views_w[i];
+  if (tid < 3 * kMaxV) we[tid] = (tid % kMaxV) < V ? p.w_eff[(tid / kMaxV) * V + tid % kMaxV] : 0.f;
+  __syncthreads();
+  const int cpt = (Tn + kChunk - 1) / kChunk, nchunks = p.B * cpt, nc = D / 8, groups = wv_groups(D);
+  const int wc = tid % nc, wg = tid / nc;
+  const bool w_on = wg < groups;
+  float wacc[kMaxV][8];
+#pragma unroll
+  for (int v = 0; v < kMaxV; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wacc[v][e] = 0.f;
+  float eacc = 0.f;   // thread tau * kMaxV + v < 3 kMaxV: d We[tau][v]
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int b = c / cpt, t0 = (c % cpt) * kChunk;
+    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)b * Tn * D;
+    const T* ds = reinterpret_cast<const T*>(p.dout) + (size_t)b * Tn * D;
+    T* dxs = reinterpret_cast<T*>(p.dx) + (size_t)b * Tn * D;
+    for (int i = tid; i < kHalo * V; i += kThreads) {
+      const int hi = i / V, v = i % V, t = t0 - 1 + hi;
+      sv[v * kHalo + hi] = (t >= 0 && t < Tn) ? p.views[((size_t)b * Tn + t) * V + v] : 0.f;
+    }
+    if (tid < kChunk) gate_s[tid] = t0 + tid < Tn ? p.gate[(size_t)b * Tn + t0 + tid] : 0.f;
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int i = warp; i < kHalo; i += kThreads / 32) {
+        const int t = t0 - 1 + i;
+        float a = 0.f;
+        if (t >= 0 && t < Tn) {
+          for (int d0 = lane * 8; d0 < D; d0 += 256) {
+            float f[8], g[8];
+            load8<T>(xs + (size_t)t * D + d0, f);
+            load8<T>(ds + (size_t)t * D + d0, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a = fmaf(f[e], g[e], a);
+          }
+        }
+        a = warp_sum(a);
+        if (lane == 0) dg[i] = a;
+      }
+    }
+    __syncthreads();
+    // d views[t][v] = sum_tau We[tau][v] d gate[t - tau]   (halo index of token t0 + i is i + 1)
+    for (int i = tid; i < kChunk * V; i += kThreads) {
+      const int t = i / V, v = i % V;
+      dvw[v * kHalo + t] = we[v] * dg[t + 2] + we[kMaxV + v] * dg[t + 1] + we[2 * kMaxV + v] * dg[t];
+    }
+    // d We[tau][v] += sum over the chunk's tokens of d gate[t] views[t + tau][v]
+    if (tid < 3 * kMaxV && (tid % kMaxV) < V) {
+      const int tau = tid / kMaxV, v = tid % kMaxV, nt = min(kChunk, Tn - t0);
+      float a = 0.f;
+      for (int t = 0; t < nt; ++t) a = fmaf(dg[t + 1], sv[v * kHalo + t + tau], a);
+      eacc += a;
+    }
+    __syncthreads();
+    if (w_on) {
+      const int nt = min(kChunk, Tn - t0);
+      for (int t = wg; t < nt; t += groups) {
+        float f[8], g[8], o[8];
+        load8<T>(xs + (size_t)(t0 + t) * D + 8 * wc, f);
+        load8<T>(ds + (size_t)(t0 + t) * D + 8 * wc, g);
+        const float gt = gate_s[t];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = g[e] * gt;
+#pragma unroll
+        for (int v = 0; v < kMaxV; ++v)
+          if (v < V) {
+            const float dv = dvw[v * kHalo + t];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              o[e] = fmaf(dv, wv_s[v * D + 8 * wc + e], o[e]);
+              wacc[v][e] = fmaf(dv, f[e], wacc[v][e]);
+            }
+          }
+        store8<T>(dxs + (size_t)(t0 + t) * D + 8 * wc, o);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 3 * kMaxV && (tid % kMaxV) < V) p.dweff_part[(size_t)blockIdx.x * 3 * V + (tid / kMaxV) * V + tid % kMaxV] = eacc;
+  if (w_on) {
+    float* dw = p.dwv_part + (size_t)(blockIdx.x * groups + wg) * V * D;
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v)
+      if (v < V) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dw[(size_t)v * D + 8 * wc + e] = wacc[v][e];
+      }
+  }
+}
+
+}  // namespace tokgate1d
 }  // namespace mop

@@ -72,6 +72,27 @@ def _fused_vit_mop(ref_cls: type) -> type:
     return cls
 
 
+_FUSED_MOP_BLOCK: Dict[type, type] = {}
+
+
+def _fused_mop_block(ref_cls: type) -> type:
+    """The reference's `MoPBlock` with `apply_mop` (gpt_mop.py:102-123) through the fused 1-D token-gate kernel: same constructor,
+    parameters and state_dict (a subclass that only replaces that method)."""
+    if ref_cls in _FUSED_MOP_BLOCK:
+        return _FUSED_MOP_BLOCK[ref_cls]
+    from . import functional as MF
+
+    def apply_mop(self, x):
+        conv = self.kernels.conv
+        if not MF.token_gate_1d_supported(x, self.n_views, conv.kernel_size[0]) or conv.padding[0] != 1:
+            return ref_cls.apply_mop(self, x)   # (shapes outside the kernel: the reference's own PyTorch composition)
+        return MF.token_gate_1d(x, self.views.proj.weight, conv.weight, self.fuse.conv.weight, self.fuse.alpha)
+
+    cls = type(ref_cls.__name__, (ref_cls,), {"apply_mop": apply_mop, "__module__": "mop_b200.dropin", "__doc__": _fused_mop_block.__doc__})
+    _FUSED_MOP_BLOCK[ref_cls] = cls
+    return cls
+
+
 def unpatch_reference() -> int:
     """Undo patch_reference(): restore the reference's own classes.  Returns how many names were restored."""
     n = 0
@@ -94,6 +115,11 @@ def patch_reference(verbose: bool = False) -> Dict[str, List[str]]:
         is_exp = modname in _EXPERIMENT_MODULES
         if not (is_ref_pkg or is_exp):
             continue
+        blk = getattr(mod, "MoPBlock", None)
+        if isinstance(blk, type) and not blk.__module__.startswith("mop_b200"):
+            _ORIGINALS[(modname, "MoPBlock")] = blk
+            setattr(mod, "MoPBlock", _fused_mop_block(blk))
+            done.setdefault(modname, []).append("MoPBlock")
         vm = getattr(mod, "ViT_MoP", None)
         if isinstance(vm, type) and not vm.__module__.startswith("mop_b200"):
             _ORIGINALS[(modname, "ViT_MoP")] = vm

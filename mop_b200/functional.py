@@ -729,6 +729,77 @@ def token_gate(tok: torch.Tensor, grid, views_w, k3_w, k1_w, f1_w, f2_w, f2_b, a
     return _TokenGate.apply(tok, tuple(grid), _max_ctas, views_w, k3_w, k1_w, f1_w, f2_w, f2_b, a_pos.reshape(1), a_neg.reshape(1))
 
 
+class _TokenGate1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, views_w, w_eff, max_ctas):
+        lib = _lib.load()
+        _need_cuda(x, "x")
+        xc = x.detach().contiguous()
+        wv, we = _f32c(views_w), _f32c(w_eff)
+        B, T, D = xc.shape
+        V = wv.shape[0]
+        out = torch.empty_like(xc)
+        views = torch.empty(B, T, V, dtype=torch.float32, device=xc.device)
+        gate = torch.empty(B, T, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            p = _lib.new_params(_lib.TokenGate1dParams)
+            p.dtype = _lib.MOP_BF16 if xc.dtype == torch.bfloat16 else _lib.MOP_F32
+            p.B, p.T, p.D, p.V = B, T, D, V
+            p.x, p.views_w, p.w_eff, p.out, p.views, p.gate = _ptr(xc), _ptr(wv), _ptr(we), _ptr(out), _ptr(views), _ptr(gate)
+            _lib.check(lib.mop_token_gate1d_fwd(C.byref(p), _stream()), "mop_token_gate1d_fwd")
+        abi_calls["token_gate1d_fwd"] = abi_calls.get("token_gate1d_fwd", 0) + 1
+        ctx.save_for_backward(xc, views, gate, wv, we)
+        ctx.meta = (x.dtype, views_w.dtype, w_eff.dtype, views_w.shape, max_ctas)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        xc, views, gate, wv, we = ctx.saved_tensors
+        x_dt, wv_dt, we_dt, wv_shape, max_ctas = ctx.meta
+        B, T, D = xc.shape
+        V = wv.shape[0]
+        dy = dout.detach().to(xc.dtype).contiguous()
+        dx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            p = _lib.new_params(_lib.TokenGate1dParams)
+            p.dtype = _lib.MOP_BF16 if xc.dtype == torch.bfloat16 else _lib.MOP_F32
+            p.B, p.T, p.D, p.V = B, T, D, V
+            nparts = lib.mop_token_gate1d_partial_rows(B, T)
+            if max_ctas:
+                nparts = max(1, min(nparts, int(max_ctas)))
+            groups = lib.mop_token_gate_wv_groups(D)
+            dwv = torch.empty(nparts * groups, V, D, dtype=torch.float32, device=xc.device)
+            dwe = torch.empty(nparts, 3 * V, dtype=torch.float32, device=xc.device)
+            p.nparts = nparts
+            p.x, p.views_w, p.w_eff, p.views, p.gate = _ptr(xc), _ptr(wv), _ptr(we), _ptr(views), _ptr(gate)
+            p.dout, p.dx, p.dwv_part, p.dweff_part = _ptr(dy), _ptr(dx), _ptr(dwv), _ptr(dwe)
+            _lib.check(lib.mop_token_gate1d_bwd(C.byref(p), _stream()), "mop_token_gate1d_bwd")
+        abi_calls["token_gate1d_bwd"] = abi_calls.get("token_gate1d_bwd", 0) + 1
+        return dx.to(x_dt), dwv.sum(0).reshape(wv_shape).to(wv_dt), dwe.sum(0).reshape(3, V).to(we_dt), None
+
+
+def token_gate_1d_supported(x: torch.Tensor, n_views: int, kernel_size: int) -> bool:
+    return (x.is_cuda and x.dim() == 3 and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 2048
+            and 1 <= n_views <= 8 and kernel_size == 3)
+
+
+def token_gate_1d(x: torch.Tensor, views_w, kernels_w, fuse_w, alpha, *, _max_ctas: int = 0) -> torch.Tensor:
+    """``x * gate`` of ``MoPBlock.apply_mop`` (reference gpt_mop.py:102-123), one fused kernel per direction.
+
+    x ``[B, T, D]``; ``views_w [V, D]`` (``ViewsLinear1D.proj.weight``), ``kernels_w [K, V, 3]`` (``Kernels1D.conv.weight``),
+    ``fuse_w [2, V+K, 1]`` (``FuseExcInh1D.conv.weight``), ``alpha [2]``.  The module is linear and bias-free, so the last three fold
+    into one 3-tap filter of the views (differentiable PyTorch, a few hundred flops)."""
+    V = views_w.shape[0]
+    fw = fuse_w.reshape(2, -1).float()
+    we = torch.einsum("ck,kvt->ctv", fw[:, V:], kernels_w.float())      # through Kernels1D: [2, 3, V]
+    centre = torch.zeros_like(we)
+    centre[:, 1] = fw[:, :V]                                             # the views themselves (1x1 path)
+    we = we + centre
+    w_eff = alpha[0].float() * we[0] - alpha[1].float() * we[1]          # [3, V]
+    return _TokenGate1d.apply(x, views_w, w_eff, _max_ctas)
+
+
 # ----------------------------------------------------------------------------
 # Whisper-MoP 2D gate (SURVEY 8f-3)
 # ----------------------------------------------------------------------------

@@ -115,6 +115,24 @@ def test_patched_reference_gpt_quartet(patched):
     _grads_close(ref_model, ours, 1e-4)
 
 
+def test_patched_reference_gpt_mop(patched):
+    """create_gpt_mop: Quartet attention blocks + the 1-D token gate (MoPBlock.apply_mop) through the fused kernels."""
+    import mop.models.gpt_mop as gm
+    from mop.models.quartet_attn_patch import TransformerConfig
+    from mop_b200 import functional as MF
+    cfg = TransformerConfig(n_layer=2, n_head=2, n_embd=32, dropout=0.0, block_size=80)
+    calls = MF.abi_calls.get("token_gate1d_fwd", 0), MF.abi_calls.get("token_gate1d_bwd", 0)
+    ref_model, ours = _twin(lambda: gm.create_gpt_mop(97, cfg), patched)
+    ids = torch.randint(0, 97, (2, 70))
+    out_ref = ref_model(ids)
+    out = ours(ids.cuda())
+    lr, lo = (o[0] if isinstance(o, (tuple, list)) else o for o in (out_ref, out))
+    assert max_abs(lo, lr) <= 5e-5
+    lr.square().mean().backward(); lo.square().mean().backward()
+    _grads_close(ref_model, ours, 1e-4)
+    assert MF.abi_calls.get("token_gate1d_fwd", 0) == calls[0] + 2 and MF.abi_calls.get("token_gate1d_bwd", 0) == calls[1] + 2
+
+
 def test_patched_reference_whisper(patched):
     from mop.models import WhisperConfig, create_whisper_mop
     cfg = WhisperConfig(n_mels=16, n_audio_ctx=64, vocab_size=50, n_text_ctx=16, n_embd=32, n_head=2, n_layer_enc=2, n_layer_dec=2,

@@ -62,3 +62,42 @@ def test_token_gate_rejects_bad_shapes():
     with pytest.raises(RuntimeError):
         mop_b200.functional.token_gate(tok, (8, 8), w["views_w"], w["k3_w"], w["k1_w"], w["f1_w"], w["f2_w"], w["f2_b"],
                                        torch.ones(1, device=dev), torch.ones(1, device=dev))
+
+
+@pytest.mark.parametrize("B,T,D,V,K,dtype,ctas", [
+    (2, 50, 64, 5, 3, torch.float32, 0),
+    (3, 200, 256, 5, 3, torch.float32, 2),       # several chunks per sequence and per CTA: halos, partial accumulation
+    (2, 129, 768, 4, 2, torch.float32, 0),       # chunk boundary + 1
+    (1, 64, 96, 8, 8, torch.float32, 0),
+    (4, 300, 768, 5, 3, torch.bfloat16, 3),
+])
+def test_token_gate_1d_vs_oracle(B, T, D, V, K, dtype, ctas):
+    """GPT-MoP apply_mop (gpt_mop.py:102-123): fused kernel vs the reference's composition in fp64."""
+    import torch.nn.functional as F
+    import mop_b200
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(T * 7 + D)
+    rn = lambda *s: torch.randn(*s, generator=gen, device=dev)
+    w = dict(views_w=rn(V, D) / D ** 0.5, kernels_w=rn(K, V, 3) / (3 * V) ** 0.5, fuse_w=rn(2, V + K, 1) / (V + K) ** 0.5,
+             alpha=torch.tensor([0.9, 0.7], device=dev))
+    for t in w.values():
+        t.requires_grad_(True)
+    x = rn(B, T, D).to(dtype).requires_grad_(True)
+    dy = rn(B, T, D).to(dtype)
+    out = mop_b200.functional.token_gate_1d(x, w["views_w"], w["kernels_w"], w["fuse_w"], w["alpha"], _max_ctas=ctas)
+    out.backward(dy)
+
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = {k: v.detach().double().requires_grad_(True) for k, v in w.items()}
+    views = (x64 @ w64["views_w"].t()).transpose(1, 2)                       # ViewsLinear1D
+    kmaps = F.conv1d(views, w64["kernels_w"], padding=1)                     # Kernels1D
+    g = F.conv1d(torch.cat([views, kmaps], dim=1), w64["fuse_w"])            # FuseExcInh1D
+    gate = 1 + w64["alpha"][0] * g[:, :1] - w64["alpha"][1] * g[:, 1:]
+    ref = x64 * gate.transpose(1, 2)
+    ref.backward(dy.double())
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+    scale = lambda r: max(1.0, r.abs().max().item())
+    assert max_abs(out.double(), ref.detach()) <= tol * scale(ref.detach())
+    assert max_abs(x.grad.double(), x64.grad) <= tol * scale(x64.grad)
+    for k in w:
+        assert max_abs(w[k].grad.double(), w64[k].grad) <= tol * scale(w64[k].grad), k
