@@ -192,6 +192,7 @@ static __global__ void __launch_bounds__(kThreads) fwd_kernel(MopTokenGateParams
     }
     __syncthreads();
     const int nc = D / 8;
+#pragma unroll 4
     for (int item = threadIdx.x; item < Tn * nc; item += kThreads) {
       const int t = item / nc, c = item % nc;
       float f[8];
@@ -380,24 +381,37 @@ static __global__ void __launch_bounds__(kThreads) bwd_kernel(MopTokenGateParams
     // dx = dout * gate + d views . Wv ;  d Wv += d views^T x   (thread = (8-feature chunk, token group))
     if (w_on) {
       const int c = wc;
-      for (int t = wg; t < Tn; t += groups) {
-        float f[8], g[8], o[8];
-        load8<T>(x + (size_t)t * D + 8 * c, f);
-        load8<T>(dout + (size_t)t * D + 8 * c, g);
-        const float gt = gate_s[t];
+      for (int tb = wg; tb < Tn; tb += 4 * groups) {   // four tokens per step: all loads in flight before the first use
+        float f[4][8], g[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = g[e] * gt;
-#pragma unroll
-        for (int v = 0; v < kMaxV; ++v)
-          if (v < V) {
-            const float dv = dvw[v * Tn + t];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              o[e] = fmaf(dv, wv_s[v * D + 8 * c + e], o[e]);
-              wacc[v][e] = fmaf(dv, f[e], wacc[v][e]);
-            }
+        for (int u = 0; u < 4; ++u) {
+          const int t = tb + u * groups;
+          if (t < Tn) {
+            load8<T>(x + (size_t)t * D + 8 * c, f[u]);
+            load8<T>(dout + (size_t)t * D + 8 * c, g[u]);
           }
-        store8<T>(dx + (size_t)t * D + 8 * c, o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = tb + u * groups;
+          if (t < Tn) {
+            float o[8];
+            const float gt = gate_s[t];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = g[u][e] * gt;
+#pragma unroll
+            for (int v = 0; v < kMaxV; ++v)
+              if (v < V) {
+                const float dv = dvw[v * Tn + t];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  o[e] = fmaf(dv, wv_s[v * D + 8 * c + e], o[e]);
+                  wacc[v][e] = fmaf(dv, f[u][e], wacc[v][e]);
+                }
+              }
+            store8<T>(dx + (size_t)t * D + 8 * c, o);
+          }
+        }
       }
     }
     __syncthreads();
@@ -511,6 +525,7 @@ static __global__ void __launch_bounds__(kThreads) fwd_kernel(MopTokenGate1dPara
     }
     __syncthreads();
     const int nt = min(kChunk, Tn - t0);
+#pragma unroll 4
     for (int item = tid; item < nt * nc; item += kThreads) {
       const int t = item / nc, ch = item % nc;
       float f[8];
@@ -591,24 +606,39 @@ static __global__ void __launch_bounds__(kThreads) bwd_kernel(MopTokenGate1dPara
     __syncthreads();
     if (w_on) {
       const int nt = min(kChunk, Tn - t0);
-      for (int t = wg; t < nt; t += groups) {
-        float f[8], g[8], o[8];
-        load8<T>(xs + (size_t)(t0 + t) * D + 8 * wc, f);
-        load8<T>(ds + (size_t)(t0 + t) * D + 8 * wc, g);
-        const float gt = gate_s[t];
+      // four tokens per step: their eight 16/32-byte loads are issued before the first use (one token at a time left every
+      // load's latency exposed: this phase is the whole cost of the kernel)
+      for (int tb = wg; tb < nt; tb += 4 * groups) {
+        float f[4][8], g[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = g[e] * gt;
-#pragma unroll
-        for (int v = 0; v < kMaxV; ++v)
-          if (v < V) {
-            const float dv = dvw[v * kHalo + t];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              o[e] = fmaf(dv, wv_s[v * D + 8 * wc + e], o[e]);
-              wacc[v][e] = fmaf(dv, f[e], wacc[v][e]);
-            }
+        for (int u = 0; u < 4; ++u) {
+          const int t = tb + u * groups;
+          if (t < nt) {
+            load8<T>(xs + (size_t)(t0 + t) * D + 8 * wc, f[u]);
+            load8<T>(ds + (size_t)(t0 + t) * D + 8 * wc, g[u]);
           }
-        store8<T>(dxs + (size_t)(t0 + t) * D + 8 * wc, o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = tb + u * groups;
+          if (t < nt) {
+            float o[8];
+            const float gt = gate_s[t];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = g[u][e] * gt;
+#pragma unroll
+            for (int v = 0; v < kMaxV; ++v)
+              if (v < V) {
+                const float dv = dvw[v * kHalo + t];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  o[e] = fmaf(dv, wv_s[v * D + 8 * wc + e], o[e]);
+                  wacc[v][e] = fmaf(dv, f[u][e], wacc[v][e]);
+                }
+              }
+            store8<T>(dxs + (size_t)(t0 + t) * D + 8 * wc, o);
+          }
+        }
       }
     }
     __syncthreads();
