@@ -222,6 +222,10 @@ def run_ours(args):
     from mop_b200.ddp import FlatGradAllReduce
     flat = FlatGradAllReduce(model, bucket_mb=0.0 if use_graph else args.bucket_mb) if ddp else None
     net = model
+    # bf16 compute copies of the Linear weights, refreshed after every optimizer step (mop_b200/mixed.py): the step loses the
+    # ~70 weight-cast / gradient-cast kernels autocast would launch; --no-shadow keeps plain autocast
+    from mop_b200.mixed import Bf16Shadow
+    shadow = None if args.no_shadow else Bf16Shadow(model)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True, capturable=use_graph)
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
     x_host = torch.randn(BATCH, 3, IMG, IMG, generator=gen).pin_memory()
@@ -239,11 +243,16 @@ def run_ours(args):
         loss.backward()
         return loss
 
+    def opt_step():
+        opt.step()
+        if shadow is not None:
+            shadow.refresh()
+
     def step(x, y):
         loss = fwd_bwd(x, y)
         if flat is not None:
             flat.reduce()
-        opt.step()
+        opt_step()
         return loss
 
     # ---- the step captured in CUDA graphs and replayed.  N = 1: one graph (fwd + loss + bwd + AdamW).  N > 1: graph A
@@ -269,7 +278,7 @@ def run_ours(args):
             graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph_b):
                 flat.scale()
-                opt.step()
+                opt_step()
         eager_step = step
 
         def step(x, y):  # noqa: F811  (same signature; inputs are copied into the graph's static buffers)
@@ -380,6 +389,7 @@ def run_ours(args):
                                           f"{len(flat.buckets)} buckets of ~{args.bucket_mb:g} MB launched from grad hooks during the backward"),
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
                        "attention_impl": impl_used, "loss": loss_val,
+                       "precision": ("bf16 autocast, fp32 master weights" + ("" if shadow is None else " with bf16 compute copies of the Linear weights (mop_b200/mixed.py)")),
                        "step_launch": "cuda_graph_replay" if graph is not None else "eager"},
             "clocks": clocks,
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
@@ -493,6 +503,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the attention-shape table, the dense+k3 variant and the reference-eager-on-GPU arm")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-shadow", action="store_true", help="plain autocast for the Linear layers (no bf16 compute copies of their weights)")
     ap.add_argument("--config", default="vit_e_cifar", choices=["vit_e_cifar", "vit_b16"],
                     help="vit_e_cifar: BASELINE.json configs[1] (headline); vit_b16: configs[2], ViT-B/16-MoP at 224x224")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 256)")

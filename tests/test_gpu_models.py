@@ -245,3 +245,39 @@ def test_mop2d_gate_vs_reference_module(B, T, Fb, V, K, ks, patched):
     assert max_abs(g, g_ref) <= 1e-5 * max(1.0, g_ref.abs().max().item())
     for (k, p), (_, q) in zip(ref.named_parameters(), ours.named_parameters()):
         assert max_abs(q.grad, p.grad) <= 2e-5 * max(1.0, p.grad.abs().max().item()), k
+
+
+def test_bf16_shadow_weights_match_autocast():
+    """mop_b200.mixed.Bf16Shadow: same loss as plain autocast (same bf16-rounded weights), gradients within bf16 rounding of the
+    autocast ones (the shadow path skips the bf16 rounding of the weight gradient), and refresh() follows the optimizer."""
+    import copy
+    import torch.nn.functional as F
+    import mop_b200
+    from mop_b200.mixed import Bf16Shadow
+    torch.manual_seed(0)
+    kw = dict(dim=64, depth=2, heads=2, n_classes=10, n_views=3, gate_mode="lowrank", gate_rank=2, drop_path=0.0)   # no random masks
+    m1 = mop_b200.ViTEdgewise(num_tokens=64, patch=4, **kw).cuda().train()
+    m2 = copy.deepcopy(m1)
+    sh = Bf16Shadow(m2)
+    assert len(sh.mods) >= 9
+    x = torch.randn(8, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (8,), device="cuda")
+    opts = [torch.optim.AdamW(m.parameters(), lr=1e-2) for m in (m1, m2)]
+    for it in range(2):
+        losses = []
+        for m, opt in zip((m1, m2), opts):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = F.cross_entropy(m(x), y)
+            loss.backward()
+            losses.append(loss.item())
+        assert abs(losses[0] - losses[1]) <= (1e-3 if it == 0 else 2e-2) * max(1.0, abs(losses[0])), losses
+        if it == 0:
+            for (k, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+                assert max_abs(q.grad, p.grad) <= 2e-2 * max(1e-6, p.grad.abs().max().item()), k
+        for opt in opts:
+            opt.step()
+        sh.refresh()
+    sh.disable()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert torch.isfinite(m2(x)).all()
