@@ -216,7 +216,10 @@ class _Edgewise(torch.autograd.Function):
         dts = ctx.in_dtypes
         if scales is not None:
             ds = dscale_part.view(R // H, H, 3, V, dk).sum(0).permute(1, 2, 0, 3)  # [3,V,H,dk]  (row i belongs to head i % H)
-            dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
+            if tuple(ctx.scale_shape) == (V, H, 1, dk):   # strided views: autograd accumulates them as they are (no copy kernels)
+                dq_s, dk_s, dv_s = (ds[i].unsqueeze(2).to(dts[i]) for i in range(3))
+            else:
+                dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:
             dq_s = dk_s = dv_s = None
         if keep_partials:

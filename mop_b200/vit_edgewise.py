@@ -54,13 +54,15 @@ class BlockEdgewise(nn.Module):
         keep = 1.0 - dp.drop_prob
         return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep) / keep
 
-    def forward_fused(self, x: torch.Tensor, branch: Optional[torch.Tensor], scale: Optional[torch.Tensor]):
+    def forward_fused(self, x: torch.Tensor, branch: Optional[torch.Tensor], scale: Optional[torch.Tensor], dp_scales=None):
         """Same math as ``forward`` with the residual adds deferred: takes the residual stream and the not-yet-added branch
-        of the previous block, returns the stream and this block's not-yet-added MLP branch ``(x, branch, scale)``."""
+        of the previous block, returns the stream and this block's not-yet-added MLP branch ``(x, branch, scale)``.
+        ``dp_scales``: this block's two per-sample DropPath factors when the caller drew them for the whole model at once."""
+        s1, s2 = dp_scales if dp_scales is not None else (self._dp_scale(self.dp1, x), self._dp_scale(self.dp2, x))
         x, h = MF.add_layer_norm(x, branch, scale, self.ln1.weight, self.ln1.bias, self.ln1.eps)
         a = self.attn(h)
-        x, h = MF.add_layer_norm(x, a, self._dp_scale(self.dp1, x), self.ln2.weight, self.ln2.bias, self.ln2.eps)
-        return x, self.mlp(h), self._dp_scale(self.dp2, x)
+        x, h = MF.add_layer_norm(x, a, s1, self.ln2.weight, self.ln2.bias, self.ln2.eps)
+        return x, self.mlp(h), s2
 
 
 class ViTEdgewise(nn.Module):
@@ -87,6 +89,19 @@ class ViTEdgewise(nn.Module):
         self.head = nn.Linear(dim, n_classes, bias=False)
         nn.init.normal_(self.pos, mean=0.0, std=0.02)
 
+    def _draw_drop_path(self, tok: torch.Tensor):
+        """All per-sample DropPath factors mask / keep of one forward ([2 * depth, B], reference components.py:14-27) from ONE
+        uniform draw - four small kernels per step instead of two per residual branch (32 for depth 8)."""
+        rates = [dp.drop_prob for blk in self.blocks for dp in (blk.dp1, blk.dp2)]
+        if not self.training or not any(r > 0.0 for r in rates):
+            return None
+        keep = getattr(self, "_dp_keep", None)
+        if keep is None or keep.device != tok.device or keep.numel() != len(rates):
+            keep = torch.tensor([1.0 - r for r in rates], dtype=torch.float32, device=tok.device).unsqueeze(1)
+            self._dp_keep = keep
+        u = torch.rand(len(rates), tok.shape[0], dtype=torch.float32, device=tok.device)
+        return (u < keep).to(torch.float32) / keep
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         tok, _ = self.patch(x)
         tok = tok + self.pos
@@ -94,8 +109,9 @@ class ViTEdgewise(nn.Module):
             # fused residual stream: every `x + dp(branch)` rides on the LayerNorm that follows it (one pass, one kernel)
             tok = tok.contiguous()
             branch = scale = None
-            for blk in self.blocks:
-                tok, branch, scale = blk.forward_fused(tok, branch, scale)
+            dps = self._draw_drop_path(tok)
+            for i, blk in enumerate(self.blocks):
+                tok, branch, scale = blk.forward_fused(tok, branch, scale, None if dps is None else (dps[2 * i], dps[2 * i + 1]))
             _, h = MF.add_layer_norm(tok, branch, scale, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps, out_dtype=torch.float32)
             return self.head(h.mean(dim=1))
         for blk in self.blocks:
