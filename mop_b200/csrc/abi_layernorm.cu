@@ -26,6 +26,19 @@ static void launch(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
   if (bwd) ln::bwd_kernel<PL, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
   else ln::fwd_kernel<PL, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
 }
+template <int NV, typename TR, typename TY>
+static void launch_v(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
+  if (bwd) ln::bwd_kernel_v<NV, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
+  else ln::fwd_kernel_v<NV, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
+}
+template <int NV>
+static void launch_vt(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
+  const bool rb = p.r_dtype == MOP_BF16, yb = p.y_dtype == MOP_BF16;
+  if (rb && yb) launch_v<NV, __nv_bfloat16, __nv_bfloat16>(p, bwd, grid, st);
+  else if (rb) launch_v<NV, __nv_bfloat16, float>(p, bwd, grid, st);
+  else if (yb) launch_v<NV, float, __nv_bfloat16>(p, bwd, grid, st);
+  else launch_v<NV, float, float>(p, bwd, grid, st);
+}
 template <int PL>
 static void launch_t(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
   const bool rb = p.r_dtype == MOP_BF16, yb = p.y_dtype == MOP_BF16;
@@ -41,7 +54,14 @@ static int ln_launch(MopLnParams* p, void* stream, bool bwd) {
   const int grid = ln::grid_size(p->rows, sm_count());
   if (bwd) MOP_REQUIRE(p->nparts >= grid, MOP_EWORKSPACE, "dgamma_part / dbeta_part hold %d partial rows, need %d", p->nparts, grid);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->D <= 256) launch_t<8>(*p, bwd, grid, st);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool aligned = al16(p->x) && al16(p->r) && al16(p->x_new) && al16(p->y) && al16(p->dy) && al16(p->dx_new) && al16(p->dx) && al16(p->dr);
+  if (p->D % 8 == 0 && aligned) {   // 16-byte accesses: D % 8 == 0 keeps every row of a 16-byte aligned tensor aligned
+    if (p->D <= 256) launch_vt<1>(*p, bwd, grid, st);
+    else if (p->D <= 512) launch_vt<2>(*p, bwd, grid, st);
+    else if (p->D <= 768) launch_vt<3>(*p, bwd, grid, st);
+    else launch_vt<4>(*p, bwd, grid, st);
+  } else if (p->D <= 256) launch_t<8>(*p, bwd, grid, st);
   else if (p->D <= 768) launch_t<24>(*p, bwd, grid, st);
   else launch_t<32>(*p, bwd, grid, st);
   MOP_CHECK_CUDA(cudaGetLastError());

@@ -21,6 +21,9 @@ def _ref(x, r, scale, g, b, eps):
     (4, 64, 224, False, False, torch.float32, torch.float32),     # plain LayerNorm (first block)
     (1, 1, 8, True, True, torch.float32, torch.bfloat16),
     (300, 10, 96, True, True, torch.bfloat16, torch.float32),     # more rows than the persistent grid covers in one sweep
+    (2, 33, 60, True, True, torch.bfloat16, torch.bfloat16),      # D % 8 != 0: the scalar kernels
+    (2, 9, 500, True, True, torch.float32, torch.bfloat16),
+    (5, 64, 512, True, True, torch.bfloat16, torch.bfloat16),     # two 256-feature steps per lane
 ])
 def test_add_layer_norm_vs_torch(B, N, D, with_r, with_scale, rdt, ydt):
     from mop_b200 import functional as MF
