@@ -215,11 +215,11 @@ class _Edgewise(torch.autograd.Function):
         abi_calls["edgewise_bwd"] += 1
         dts = ctx.in_dtypes
         if scales is not None:
-            ds = dscale_part.view(R // H, H, 3, V, dk).sum(0).permute(1, 2, 0, 3)  # [3,V,H,dk]  (row i belongs to head i % H)
-            if tuple(ctx.scale_shape) == (V, H, 1, dk):   # strided views: autograd accumulates them as they are (no copy kernels)
-                dq_s, dk_s, dv_s = (ds[i].unsqueeze(2).to(dts[i]) for i in range(3))
-            else:
-                dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
+            # row i of the partials belongs to head i % H.  One reduction writes the sum straight into the [3, V, H, dk] layout of
+            # the parameters, so the three gradients are contiguous views (autograd keeps them: no permute copies, no clones)
+            ds = torch.empty(3, V, H, dk, dtype=torch.float32, device=dev)
+            torch.sum(dscale_part.view(R // H, H, 3, V, dk).permute(0, 2, 3, 1, 4), dim=0, out=ds)
+            dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:
             dq_s = dk_s = dv_s = None
         if keep_partials:
