@@ -220,7 +220,7 @@ def run_ours(args):
     # ViT-B/16 (a 300 ms step, 346 MB of gradients): eager launches, gradient buckets all-reduced WHILE the backward runs
     use_graph = not args.no_graph and CONFIG == "vit_e_cifar"
     from mop_b200.ddp import FlatGradAllReduce
-    flat = FlatGradAllReduce(model, bucket_mb=0.0 if use_graph else args.bucket_mb) if ddp else None
+    flat = FlatGradAllReduce(model, bucket_mb=0.0 if use_graph else args.bucket_mb, pack=use_graph) if ddp else None
     net = model
     # bf16 compute copies of the Linear weights, refreshed after every optimizer step (mop_b200/mixed.py): the step loses the
     # ~70 weight-cast / gradient-cast kernels autocast would launch; --no-shadow keeps plain autocast
@@ -275,6 +275,10 @@ def run_ours(args):
         else:
             with torch.cuda.graph(graph):
                 static_loss = fwd_bwd(static_x, static_y)
+                if flat.packed:
+                    flat.pack()    # the gradient tensors of the captured backward -> the flat buffer (one concatenation)
+            if flat.packed:
+                flat.bind()        # the optimizer graph reads the reduced gradients from the flat buffer
             graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph_b):
                 flat.scale()

@@ -66,8 +66,15 @@ class FlatGradAllReduce:
     captured scale + optimizer graph.  Use ``zero()`` instead of ``optimizer.zero_grad(set_to_none=True)``.
     """
 
-    def __init__(self, model: torch.nn.Module, bucket_mb: float = 0.0):
-        """``bucket_mb > 0``: overlapped mode for models whose gradients are large (ViT-B/16: 346 MB).  The flat buffer is cut
+    def __init__(self, model: torch.nn.Module, bucket_mb: float = 0.0, pack: bool = False):
+        """``pack=True`` (small, launch-bound models; needs ``bucket_mb == 0``): the gradients are NOT accumulated into views of
+        the flat buffer (that costs one ``add_`` kernel per parameter and step: autograd adds into an existing ``.grad``).  Instead
+        every step starts with ``begin()`` (``p.grad = None``: autograd keeps the freshly computed gradient tensors), ``pack()``
+        gathers them into the flat buffer with one concatenation, and ``bind()`` points every ``p.grad`` at its slice of the
+        (reduced) flat buffer for the optimizer.  Under CUDA graphs the gradient tensors of the captured backward have fixed
+        addresses, so ``begin`` / ``pack`` are captured with the backward and ``bind`` once before the optimizer graph.
+
+        ``bucket_mb > 0``: overlapped mode for models whose gradients are large (ViT-B/16: 346 MB).  The flat buffer is cut
         into buckets of about that size in REVERSE parameter order (the order the backward produces gradients); a
         post-accumulate-grad hook on every parameter counts its bucket down and, when a bucket is complete, launches its
         all-reduce asynchronously on NCCL's stream while the backward continues.  ``reduce()`` then only waits and scales.
@@ -76,12 +83,19 @@ class FlatGradAllReduce:
         total = sum(p.numel() for p in params)
         dev = params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params = params
+        self.packed = bool(pack)
+        if self.packed and bucket_mb > 0:
+            raise ValueError("pack=True is the one-all-reduce mode (bucket_mb must be 0)")
+        self.views = []
         off = 0
         for p in params:
             if p.dtype != torch.float32:
                 raise TypeError("FlatGradAllReduce expects fp32 parameters (use autocast for bf16 compute)")
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self.views.append(self.flat[off:off + n].view_as(p))
+            if not self.packed:
+                p.grad = self.views[-1]
             off += n
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:  # same initial weights on every rank
@@ -119,7 +133,26 @@ class FlatGradAllReduce:
                 self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
         return hook
 
+    # ---- pack mode ----
+    def begin(self) -> None:
+        """Start of a step: autograd will keep (not add) the gradients it computes."""
+        for p in self.params:
+            p.grad = None
+
+    def pack(self) -> None:
+        """After the backward: gather the gradients into the flat buffer (one concatenation; a missing gradient is zero)."""
+        gs = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(gs, out=self.flat)
+
+    def bind(self) -> None:
+        """Point every p.grad at its slice of the flat buffer (what the optimizer reads after the all-reduce)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
     def zero(self) -> None:
+        if self.packed:
+            self.begin()
+            return
         self.flat.zero_()
         if self.buckets:
             self._pending = list(self._counts)
@@ -145,5 +178,9 @@ class FlatGradAllReduce:
             self.flat.mul_(1.0 / self.world)
 
     def reduce(self) -> None:
+        if self.packed:
+            self.pack()
         self.all_reduce_sum()
         self.scale()
+        if self.packed:
+            self.bind()

@@ -49,13 +49,13 @@ def test_sharded_gradients_match_full_batch(tmp_path):
     assert got["slow"] == 2.0
 
 
-def _worker_flat(rank, world, port, out, bucket_mb=0.0):
+def _worker_flat(rank, world, port, out, bucket_mb=0.0, pack=False):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     from mop_b200 import ddp
     ddp.init("gloo")
     torch.manual_seed(rank)   # different initial weights per rank: the constructor broadcasts rank 0's
     model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
-    flat = ddp.FlatGradAllReduce(model, bucket_mb=bucket_mb)
+    flat = ddp.FlatGradAllReduce(model, bucket_mb=bucket_mb, pack=pack)
     if bucket_mb > 0:
         assert len(flat.buckets) >= 2 and flat.buckets[0][1] == flat.flat.numel() and flat.buckets[-1][0] == 0
     g = torch.Generator().manual_seed(1)
@@ -94,6 +94,21 @@ def test_bucketed_overlapped_allreduce_matches_full_batch(tmp_path):
     during the backward (the ViT-B/16 path: 346 MB of gradients) == full-batch gradients, on both steps."""
     out = str(tmp_path / "fb.pt")
     mp.spawn(_worker_flat, args=(2, _free_port(), out, 0.0002), nprocs=2, join=True)   # ~50-element buckets: two buckets
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(10, 12, generator=g), torch.randint(0, 5, (10,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()
+    for a, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(a, p.grad, atol=1e-6)
+
+
+def test_packed_gradient_allreduce_matches_full_batch(tmp_path):
+    """FlatGradAllReduce(pack=True), the CUDA-graph bench path at N > 1: autograd keeps fresh gradient tensors (no add_ per parameter),
+    pack() concatenates them into the flat buffer, bind() points p.grad at the reduced slices == full-batch gradients, on both steps."""
+    out = str(tmp_path / "fp.pt")
+    mp.spawn(_worker_flat, args=(2, _free_port(), out, 0.0, True), nprocs=2, join=True)
     got = torch.load(out)
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.GELU(), torch.nn.Linear(16, 5))
