@@ -50,7 +50,23 @@ static TensorMapEncodeFn tensor_map_encoder() {
 }
 // bf16 tensor [B][N][H][dk] with element strides (sb, sn, sh), last dimension contiguous, described to the TMA unit as
 // (column, token, head, batch); box = 64 columns x box_rows tokens, 128-byte swizzle (tc_common.cuh: tma_load_tile_sw)
+// The encoded descriptors are kept in a small per-thread cache keyed by every argument (a training loop asks for the same ~10
+// maps every step - the caching allocator hands the same addresses back -, and each driver call costs about a microsecond of host
+// time per map: eight per plain-attention backward).  A descriptor depends on nothing but these arguments.
+struct TileMapKey {
+  const void* base; int B, N, H, dk, box_rows; int64_t sb, sn, sh;
+  bool operator==(const TileMapKey& o) const {
+    return base == o.base && B == o.B && N == o.N && H == o.H && dk == o.dk && box_rows == o.box_rows && sb == o.sb && sn == o.sn && sh == o.sh;
+  }
+};
 int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int dk, int64_t sb, int64_t sn, int64_t sh, int box_rows) {
+  constexpr int kSlots = 64;
+  thread_local TileMapKey keys[kSlots];
+  thread_local CUtensorMap maps[kSlots];
+  thread_local int used = 0, next = 0;
+  const TileMapKey key{base, B, N, H, dk, box_rows, sb, sn, sh};
+  for (int i = 0; i < used; ++i)
+    if (keys[i] == key) { *tm = maps[i]; return MOP_OK; }
   TensorMapEncodeFn enc = tensor_map_encoder();
   MOP_REQUIRE(enc != nullptr, MOP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   auto stride = [](int64_t elems, int dim) -> cuuint64_t { return (dim > 1 && elems > 0) ? (cuuint64_t)elems * 2 : 16; };
@@ -62,6 +78,9 @@ int make_tile_map_sw(CUtensorMap* tm, const void* base, int B, int N, int H, int
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MOP_REQUIRE(rc == CUDA_SUCCESS, MOP_ECUDA, "cuTensorMapEncodeTiled (128B swizzle) failed with code %d (N=%d H=%d dk=%d strides %lld %lld %lld)", (int)rc, N,
               H, dk, (long long)sb, (long long)sn, (long long)sh);
+  const int slot = used < kSlots ? used++ : (next = (next + 1) % kSlots);   // round-robin replacement once full
+  keys[slot] = key;
+  maps[slot] = *tm;
   return MOP_OK;
 }
 }  // namespace mop
