@@ -133,6 +133,11 @@ int mop_edgewise_needs_row_stats(const MopEdgewiseParams* p);
 /* rows R of dscale_part / dhead_part that mop_edgewise_bwd writes for these params (B*H, or the persistent grid) */
 int mop_edgewise_partial_rows(const MopEdgewiseParams* p);
 /* number of floats of `aux` the forward would write / the backward needs for these params (0: none) */
+/* Sums of the gradient partials of one mop_edgewise_bwd call in one launch (deterministic): dscale [3,V,H,dk] from dscale_part
+ * [R,3,V,dk] (row i belongs to head i % H), dhead [nhead] from dhead_part [R,nhead], dlogit [1] from dlogit_part [G].  dscale_part /
+ * dhead_part may be NULL together with their outputs. */
+int mop_edgewise_reduce_partials(const float* dscale_part, const float* dhead_part, const float* dlogit_part, int R, int H, int V, int dk,
+                                 int nhead, int G, float* dscale, float* dhead, float* dlogit, void* cuda_stream);
 size_t mop_edgewise_aux_floats(const MopEdgewiseParams* p);
 /* bytes of workspace needed by mop_edgewise_fwd (backward=0) / mop_edgewise_bwd (backward=1) */
 size_t mop_edgewise_workspace_bytes(const MopEdgewiseParams* p, int backward);

@@ -128,6 +128,9 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_edgewise_reduce_partials.restype = C.c_int
+        lib.mop_edgewise_reduce_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mop_token_gate_partial_rows.restype = C.c_int
         lib.mop_token_gate_partial_rows.argtypes = [C.c_int]
         lib.mop_token_gate_wv_groups.restype = C.c_int

@@ -65,7 +65,59 @@ static ew::Layout edgewise_layout(const MopEdgewiseParams* p, int bwd) {
 
 using namespace mop;
 
+namespace mop {
+// Sums of the per-CTA / per-problem gradient partials of one Edgewise backward call in ONE launch (the caller used three
+// torch reductions per layer).  Fixed summation order: deterministic.
+//   dscale[c][v][h][d] = sum_j dscale_part[(j H + h)][c][v][d]      (row i of the partials belongs to head i % H)
+//   dhead[n]           = sum_i dhead_part[i][n]
+//   dlogit             = sum_g dlogit_part[g]
+static __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* dscale_part, const float* dhead_part, const float* dlogit_part,
+                                                                     int R, int H, int V, int dk, int nhead, int G, float* dscale, float* dhead,
+                                                                     float* dlogit) {
+  const int nscale = dscale_part ? 3 * V * H * dk : 0, nh = dhead_part ? nhead : 0;
+  if ((int)blockIdx.x == (int)gridDim.x - 1) {   // last CTA: the scalar
+    __shared__ float red[8];
+    float a = 0.f;
+    for (int g = threadIdx.x; g < G; g += 256) a += dlogit_part[g];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      dlogit[0] = t;
+    }
+    return;
+  }
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx < nscale) {
+    const int d = idx % dk, h = (idx / dk) % H, cv = idx / (dk * H);   // cv = c * V + v
+    const float* src = dscale_part + (size_t)h * 3 * V * dk + (size_t)cv * dk + d;
+    float a = 0.f;
+    for (int j = 0; j < R / H; ++j) a += src[(size_t)j * H * 3 * V * dk];
+    dscale[idx] = a;
+  } else if (idx < nscale + nh) {
+    const int n = idx - nscale;
+    float a = 0.f;
+    for (int i = 0; i < R; ++i) a += dhead_part[(size_t)i * nhead + n];
+    dhead[n] = a;
+  }
+}
+}  // namespace mop
+
 extern "C" {
+int mop_edgewise_reduce_partials(const float* dscale_part, const float* dhead_part, const float* dlogit_part, int R, int H, int V, int dk,
+                                 int nhead, int G, float* dscale, float* dhead, float* dlogit, void* stream) {
+  MOP_REQUIRE(dlogit_part && dlogit && R > 0 && H > 0 && R % H == 0 && G > 0, MOP_EINVAL, "bad partial-sum arguments (R=%d H=%d G=%d)", R, H, G);
+  MOP_REQUIRE((dscale_part == nullptr) == (dscale == nullptr) && (dhead_part == nullptr) == (dhead == nullptr), MOP_EINVAL, "partial / output pairs must be set together");
+  MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
+  const int n = (dscale_part ? 3 * V * H * dk : 0) + (dhead_part ? nhead : 0);
+  mop::reduce_partials_kernel<<<(n + 255) / 256 + 1, 256, 0, (cudaStream_t)stream>>>(dscale_part, dhead_part, dlogit_part, R, H, V, dk, nhead, G, dscale,
+                                                                               dhead, dlogit);
+  MOP_CHECK_CUDA(cudaGetLastError());
+  return MOP_OK;
+}
+
 
 size_t mop_edgewise_head_param_count(const MopEdgewiseParams* p) {
   if (!p) return 0;

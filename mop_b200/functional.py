@@ -214,18 +214,21 @@ class _Edgewise(torch.autograd.Function):
         last_impl["edgewise_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["edgewise_bwd"] += 1
         dts = ctx.in_dtypes
+        # the sums of the per-CTA / per-problem partials: one launch (row i of the partials belongs to head i % H; the scale sums
+        # come out in the [3, V, H, dk] layout of the parameters, so the three gradients are contiguous views)
+        ds = torch.empty(3, V, H, dk, dtype=torch.float32, device=dev) if scales is not None else None
+        flat = torch.empty(nhead, dtype=torch.float32, device=dev) if dhead_part is not None else None
+        dlogit32 = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mop_edgewise_reduce_partials(_ptr(dscale_part), _ptr(dhead_part), _ptr(dlogit_part), R, H, V, dk, nhead, G,
+                                                        _ptr(ds), _ptr(flat), _ptr(dlogit32), _stream()), "mop_edgewise_reduce_partials")
         if scales is not None:
-            # row i of the partials belongs to head i % H.  One reduction writes the sum straight into the [3, V, H, dk] layout of
-            # the parameters, so the three gradients are contiguous views (autograd keeps them: no permute copies, no clones)
-            ds = torch.empty(3, V, H, dk, dtype=torch.float32, device=dev)
-            torch.sum(dscale_part.view(R // H, H, 3, V, dk).permute(0, 2, 3, 1, 4), dim=0, out=ds)
             dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:
             dq_s = dk_s = dv_s = None
         if keep_partials:
             last_partials["edgewise_dlogit"] = dlogit_part.detach().clone()
-        dlogit = dlogit_part.sum().reshape(()).to(dts[3])
-        flat = dhead_part.sum(0) if dhead_part is not None else None
+        dlogit = dlogit32.reshape(()).to(dts[3])
         dheads, off = [], 0
         n_gate = len(ctx.head_shapes) - (1 if dlens_part is not None else 0)
         for shp, dt in zip(ctx.head_shapes[:n_gate], dts[4:]):
