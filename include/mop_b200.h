@@ -247,6 +247,9 @@ typedef struct MopLnParams {
 
 /* number of per-CTA partial rows the backward writes for a [rows, D] problem on the current device */
 int mop_ln_partial_rows(int rows);
+/* recommended number of partial rows (= CTAs of mop_ln_bwd) for feature count D; mop_ln_bwd launches exactly `nparts` CTAs and
+ * writes every partial row, so any count from 1 to 16 x the SM count is valid */
+int mop_ln_partial_rows_d(int rows, int D);
 int mop_ln_fwd(MopLnParams* p, void* cuda_stream);
 int mop_ln_bwd(MopLnParams* p, void* cuda_stream);
 

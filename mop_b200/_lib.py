@@ -128,6 +128,8 @@ def load():
                 fn = getattr(lib, f"mop_{name}_{d}")
                 fn.restype = C.c_int
                 fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.mop_ln_partial_rows_d.restype = C.c_int
+        lib.mop_ln_partial_rows_d.argtypes = [C.c_int, C.c_int]
         lib.mop_edgewise_reduce_partials.restype = C.c_int
         lib.mop_edgewise_reduce_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

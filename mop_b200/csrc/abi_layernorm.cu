@@ -28,7 +28,7 @@ static void launch(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
 }
 template <int NV, typename TR, typename TY>
 static void launch_v(const MopLnParams& p, bool bwd, int grid, cudaStream_t st) {
-  if (bwd) ln::bwd_kernel_v<NV, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
+  if (bwd) ln::bwd_kernel_v<NV, TR, TY><<<grid, ln::BwdWarps<NV>::value * 32, 0, st>>>(p);
   else ln::fwd_kernel_v<NV, TR, TY><<<grid, ln::kWarps * 32, 0, st>>>(p);
 }
 template <int NV>
@@ -51,8 +51,14 @@ static int ln_launch(MopLnParams* p, void* stream, bool bwd) {
   int rc = check_ln(p, bwd);
   if (rc != MOP_OK) return rc;
   MOP_REQUIRE(sm_count() > 0, MOP_ECUDA, "no CUDA device (libmop_b200 has no CPU fallback)");
-  const int grid = ln::grid_size(p->rows, sm_count());
-  if (bwd) MOP_REQUIRE(p->nparts >= grid, MOP_EWORKSPACE, "dgamma_part / dbeta_part hold %d partial rows, need %d", p->nparts, grid);
+  // forward: one warp per row over a persistent grid.  backward: exactly nparts CTAs (every partial row is written - a CTA without
+  // rows writes zeros -, so the caller may sum all of them): mop_ln_partial_rows_d() is the recommended count
+  int grid = ln::grid_size(p->rows, sm_count());
+  if (bwd) {
+    MOP_REQUIRE(p->nparts >= 1, MOP_EWORKSPACE, "dgamma_part / dbeta_part need at least one partial row (nparts=%d)", p->nparts);
+    grid = p->nparts < sm_count() * 16 ? p->nparts : sm_count() * 16;
+    MOP_REQUIRE(grid == p->nparts, MOP_EWORKSPACE, "nparts=%d partial rows (at most %d)", p->nparts, sm_count() * 16);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool aligned = al16(p->x) && al16(p->r) && al16(p->x_new) && al16(p->y) && al16(p->dy) && al16(p->dx_new) && al16(p->dx) && al16(p->dr);
@@ -76,6 +82,11 @@ int mop_ln_partial_rows(int rows) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   return ln::grid_size(rows, sms);
+}
+int mop_ln_partial_rows_d(int rows, int D) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  return D % 8 == 0 ? ln::bwd_grid_size_v(rows, D, sms) : ln::grid_size(rows, sms);
 }
 int mop_ln_fwd(MopLnParams* p, void* stream) { return ln_launch(p, stream, false); }
 int mop_ln_bwd(MopLnParams* p, void* stream) { return ln_launch(p, stream, true); }

@@ -215,8 +215,12 @@ static __global__ void __launch_bounds__(kWarps * 32) fwd_kernel_v(MopLnParams p
   }
 }
 
+// KW warps per CTA: the fewer CTAs, the fewer partial rows the caller has to sum afterwards (that sum cost as much as this kernel
+// with 1184 CTAs of 4 warps at the bench shape); 16 warps for one 256-feature step, fewer where the staging array would not fit
+template <int NV> struct BwdWarps { static constexpr int value = NV == 1 ? 16 : NV == 2 ? 8 : 4; };
 template <int NV, typename TR, typename TY>
-static __global__ void __launch_bounds__(kWarps * 32) bwd_kernel_v(MopLnParams p) {
+static __global__ void __launch_bounds__(BwdWarps<NV>::value * 32) bwd_kernel_v(MopLnParams p) {
+  constexpr int kWarps = BwdWarps<NV>::value;   // (shadows the namespace constant inside this kernel)
   __shared__ float red[2][kWarps][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = p.D;
@@ -298,6 +302,12 @@ static __global__ void __launch_bounds__(kWarps * 32) bwd_kernel_v(MopLnParams p
 
 inline int grid_size(int rows, int sms) {
   const int want = (rows + kWarps - 1) / kWarps, cap = sms * 8;
+  return want < cap ? want : cap;
+}
+// CTAs (= partial rows) of the vectorised backward for feature count D: the same number of resident warps per SM as above
+inline int bwd_grid_size_v(int rows, int D, int sms) {
+  const int nv = (D + 255) / 256, kw = nv == 1 ? 16 : nv == 2 ? 8 : 4;
+  const int want = (rows + kw - 1) / kw, cap = sms * 32 / kw;
   return want < cap ? want : cap;
 }
 

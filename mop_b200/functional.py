@@ -619,7 +619,7 @@ class _AddLayerNorm(torch.autograd.Function):
         dx = torch.empty(rows, D, dtype=torch.float32, device=dev)
         dr = torch.empty(rows, D, dtype=r_dtype, device=dev) if has_r else None
         with torch.cuda.device(dev):
-            nparts = lib.mop_ln_partial_rows(rows)
+            nparts = lib.mop_ln_partial_rows_d(rows, D)
             parts = torch.empty(2, nparts, D, dtype=torch.float32, device=dev)
             p = _ln_params(xs, dr, sc if has_scale else None, g32, g32, eps, rps, y_dtype)
             p.r = _ptr(dr)          # only its presence / dtype matters to the backward
