@@ -20,6 +20,21 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _weight_grad(dy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """dW = dy2^T x2 in fp32.  For the small Linear layers of the ViT-MoP models the output has few tiles (672 x 224: 77 tiles of
+    64 x 32 on 148 SMs) and the reduction is long (16384 tokens): the tokens are split into up to 8 slices, one batched GEMM forms the
+    slice products and a small sum adds them (measured on B200, CUDA-graph replays: 21.5 -> 13.4 us for 672 x 16384 x 224)."""
+    M, O = dy2.shape
+    I = x2.shape[1]
+    tiles = -(-O // 64) * -(-I // 32)
+    S = 1
+    while S < 8 and tiles * S < 296 and M % (2 * S) == 0 and M // (2 * S) >= 1024:
+        S *= 2
+    if S == 1 or not (dy2.is_contiguous() and x2.is_contiguous()):
+        return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+    return torch.bmm(dy2.view(S, M // S, O).transpose(1, 2), x2.view(S, M // S, I), out_dtype=torch.float32).sum(0)
+
+
 class _ShadowLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w32, w16, b):
@@ -33,7 +48,7 @@ class _ShadowLinear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])
         dx = torch.matmul(dy, w16) if ctx.needs_input_grad[0] else None
-        dw = torch.mm(dy2.t(), x2, out_dtype=torch.float32)          # fp32 straight out of the GEMM: no bf16 round trip, no cast kernel
+        dw = _weight_grad(dy2, x2)                                   # fp32 straight out of the GEMM: no bf16 round trip, no cast kernel
         db = dy2.sum(0, dtype=torch.float32) if ctx.has_bias else None
         return dx, dw, None, db
 

@@ -281,3 +281,16 @@ def test_bf16_shadow_weights_match_autocast():
     sh.disable()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert torch.isfinite(m2(x)).all()
+
+
+def test_shadow_weight_grad_token_split():
+    """mop_b200.mixed._weight_grad: the token-sliced (split-K) form of dW = dy^T x equals the single GEMM."""
+    from mop_b200.mixed import _weight_grad
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for M, O, I in ((16384, 672, 224), (8192, 224, 224), (4096, 96, 40), (1000, 64, 32)):   # S = 4, 8, 4 (or 2), 1
+        dy = torch.randn(M, O, generator=g, device="cuda").bfloat16()
+        x = torch.randn(M, I, generator=g, device="cuda").bfloat16()
+        ref = dy.double().t() @ x.double()
+        got = _weight_grad(dy, x)
+        assert got.dtype == torch.float32 and got.shape == (O, I)
+        assert max_abs(got, ref) <= 1e-3 * ref.abs().max().item()
