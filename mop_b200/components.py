@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import functional as MF
 
@@ -35,6 +36,14 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_ch, dim, kernel_size=patch, stride=patch, bias=False)
 
     def forward(self, x):
+        p = self.proj.kernel_size[0]
+        B, C, Hh, Ww = x.shape
+        if x.is_cuda and Hh % p == 0 and Ww % p == 0:
+            # kernel == stride: the convolution is one GEMM over the flattened patches ([B, Gh*Gw, C*p*p] x [C*p*p, dim]).  cuDNN
+            # wraps its implicit GEMM in NCHW <-> NHWC transposes (six extra launches per step for a 3 -> dim, 4 x 4 projection)
+            Gh, Gw = Hh // p, Ww // p
+            tok = x.view(B, C, Gh, p, Gw, p).permute(0, 2, 4, 1, 3, 5).reshape(B, Gh * Gw, C * p * p)
+            return F.linear(tok, self.proj.weight.view(self.proj.out_channels, -1), self.proj.bias), (Gh, Gw)
         f = self.proj(x)
         return f.flatten(2).transpose(1, 2), tuple(f.shape[-2:])
 
