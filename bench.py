@@ -226,7 +226,15 @@ def run_ours(args):
     # ~70 weight-cast / gradient-cast kernels autocast would launch; --no-shadow keeps plain autocast
     from mop_b200.mixed import Bf16Shadow
     shadow = None if args.no_shadow else Bf16Shadow(model)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True, capturable=use_graph)
+    # graph mode: parameters re-homed into one flat buffer and fused AdamW over ONE tensor (mop_b200/mixed.py: one kernel instead
+    # of four multi-tensor launches over ~150 small tensors; same update).  --no-flat-opt: torch's per-parameter fused AdamW
+    flatp = None
+    if not args.no_flat_opt and use_graph:
+        from mop_b200.mixed import FlatParams
+        flatp = FlatParams(model)
+        if flat is not None:
+            flatp.use_grad_buffer(flat.flat)
+    opt = torch.optim.AdamW([flatp.param] if flatp is not None else model.parameters(), lr=1e-3, weight_decay=0.05, fused=True, capturable=use_graph)
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
     x_host = torch.randn(BATCH, 3, IMG, IMG, generator=gen).pin_memory()
     y_host = torch.randint(0, MODEL["n_classes"], (BATCH,), generator=gen).pin_memory()
@@ -236,11 +244,15 @@ def run_ours(args):
     def fwd_bwd(x, y):
         if flat is not None:
             flat.zero()
+        elif flatp is not None:
+            flatp.begin()
         else:
             opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = F.cross_entropy(net(x), y)
         loss.backward()
+        if flatp is not None and flat is None:
+            flatp.pack_grads()
         return loss
 
     def opt_step():
@@ -269,7 +281,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         if flat is None:
-            opt.zero_grad(set_to_none=True)
+            if flatp is None:
+                opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
                 static_loss = step(static_x, static_y)
         else:
@@ -394,6 +407,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
                        "attention_impl": impl_used, "loss": loss_val,
                        "precision": ("bf16 autocast, fp32 master weights" + ("" if shadow is None else " with bf16 compute copies of the Linear weights (mop_b200/mixed.py)")),
+                       "optimizer": "AdamW lr 1e-3 wd 0.05, fused" + (", one flat parameter buffer" if flatp is not None else ""),
                        "step_launch": "cuda_graph_replay" if graph is not None else "eager"},
             "clocks": clocks,
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
@@ -507,6 +521,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the attention-shape table, the dense+k3 variant and the reference-eager-on-GPU arm")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-flat-opt", action="store_true", help="per-parameter fused AdamW instead of one flat parameter buffer")
     ap.add_argument("--no-shadow", action="store_true", help="plain autocast for the Linear layers (no bf16 compute copies of their weights)")
     ap.add_argument("--config", default="vit_e_cifar", choices=["vit_e_cifar", "vit_b16"],
                     help="vit_e_cifar: BASELINE.json configs[1] (headline); vit_b16: configs[2], ViT-B/16-MoP at 224x224")

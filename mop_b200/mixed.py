@@ -86,3 +86,44 @@ def _bound_forward(m: nn.Linear):
             return _ShadowLinear.apply(x.to(torch.bfloat16), m.weight, m._mop_w16, m.bias)
         return F.linear(x, m.weight, m.bias)
     return forward
+
+
+class FlatParams:
+    """All trainable fp32 parameters of a model re-homed into ONE flat buffer (each `p.data` becomes a view of it), with a
+    matching flat gradient buffer: a fused optimizer then updates the whole model with one kernel over one tensor instead of one
+    multi-tensor launch per ~40 parameters.  The per-parameter gradients autograd produces are gathered with `pack_grads()`
+    (one concatenation), or the flat gradient buffer of `ddp.FlatGradAllReduce(pack=True)` is adopted with `use_grad_buffer()`.
+
+        fp = FlatParams(model); opt = torch.optim.AdamW([fp.param], fused=True, ...)
+        loss.backward(); fp.pack_grads(); opt.step()          # p.grad must be None before the backward (fp.begin())
+    """
+
+    def __init__(self, model: nn.Module):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if any(p.dtype != torch.float32 for p in self.params):
+            raise TypeError("FlatParams expects fp32 parameters")
+        total = sum(p.numel() for p in self.params)
+        flat = torch.empty(total, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + n].view_as(p)
+                off += n
+        self.param = nn.Parameter(flat)
+        self.grad_buf = torch.zeros_like(flat)
+        self.param.grad = self.grad_buf
+
+    def use_grad_buffer(self, flat_grad: torch.Tensor) -> None:
+        self.grad_buf = flat_grad
+        self.param.grad = flat_grad
+
+    def begin(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    def pack_grads(self) -> None:
+        gs = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(gs, out=self.grad_buf)
+        self.param.grad = self.grad_buf   # (an optimizer.zero_grad(set_to_none=True) in between must not detach the buffer)
