@@ -214,14 +214,21 @@ class _Edgewise(torch.autograd.Function):
         last_impl["edgewise_bwd"] = _lib.IMPL_NAMES.get(p.impl_used, "?")
         abi_calls["edgewise_bwd"] += 1
         dts = ctx.in_dtypes
-        # the sums of the per-CTA / per-problem partials: one launch (row i of the partials belongs to head i % H; the scale sums
-        # come out in the [3, V, H, dk] layout of the parameters, so the three gradients are contiguous views)
+        # the sums of the per-CTA / per-problem partials (row i of the partials belongs to head i % H; the scale sums come out in
+        # the [3, V, H, dk] layout of the parameters, so the three gradients are contiguous views).  Few rows (one per CTA: the
+        # N = 64 kernels): one launch for all three.  One row per problem (thousands): three tree reductions.
         ds = torch.empty(3, V, H, dk, dtype=torch.float32, device=dev) if scales is not None else None
-        flat = torch.empty(nhead, dtype=torch.float32, device=dev) if dhead_part is not None else None
-        dlogit32 = torch.empty(1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.mop_edgewise_reduce_partials(_ptr(dscale_part), _ptr(dhead_part), _ptr(dlogit_part), R, H, V, dk, nhead, G,
-                                                        _ptr(ds), _ptr(flat), _ptr(dlogit32), _stream()), "mop_edgewise_reduce_partials")
+        if R <= 1024:
+            flat = torch.empty(nhead, dtype=torch.float32, device=dev) if dhead_part is not None else None
+            dlogit32 = torch.empty(1, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.mop_edgewise_reduce_partials(_ptr(dscale_part), _ptr(dhead_part), _ptr(dlogit_part), R, H, V, dk, nhead, G,
+                                                            _ptr(ds), _ptr(flat), _ptr(dlogit32), _stream()), "mop_edgewise_reduce_partials")
+        else:
+            if scales is not None:
+                torch.sum(dscale_part.view(R // H, H, 3, V, dk).permute(0, 2, 3, 1, 4), dim=0, out=ds)
+            flat = dhead_part.sum(0) if dhead_part is not None else None
+            dlogit32 = dlogit_part.sum()
         if scales is not None:
             dq_s, dk_s, dv_s = (ds[i].reshape(ctx.scale_shape).to(dts[i]) for i in range(3))
         else:

@@ -284,6 +284,7 @@ LARGE_BWD_CASES = [
     (4, 2, 200, 64, 4, 3),
     (4, 2, 17, 16, 5, 4),
     (150, 1, 80, 24, 2, 4),    # persistent loop: scratch slots, tiles, TMEM and barriers are reused
+    (550, 2, 17, 16, 2, 2),    # 1100 partial rows: the tree-reduction path of the partial sums
 ]
 
 
